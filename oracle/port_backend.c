@@ -1,0 +1,63 @@
+/* oracle/port_backend.c — TEST INFRASTRUCTURE ONLY.  Binds the CPU restatement (port_recon.c) behind
+ * the decoder's backend interface so that the host parser + record ABI can be validated against the
+ * compiled reference decoder without a GPU (tests/test_oracle_vs_ref.py), and so that GPU output can
+ * be compared with it picture by picture.  Linked only into oracle/liboracle_dec.so. */
+#include <stdlib.h>
+#include <string.h>
+#include "../edge264_b200/csrc/dec.h"
+
+void port_recon_picture(uint8_t *frames, const E264PicDesc *pd, const E264MbRec *recs, const int16_t *coefs, const E264SliceRec *slices);
+
+typedef struct PortCtx {
+	E264PicDesc g; int n_slots;
+	uint8_t *frames_alloc, *frames;
+	E264MbRec *recs[E264_MAX_SLOTS];
+	int16_t *coefs; uint32_t coef_cap;
+	E264SliceRec *slices;
+	int cur_slot;
+} PortCtx;
+
+static int port_create(void **ctx) { *ctx = calloc(1, sizeof(PortCtx)); return *ctx ? 0 : -1; }
+static void port_free_all(PortCtx *c) {
+	free(c->frames_alloc); for (int i = 0; i < E264_MAX_SLOTS; i++) { free(c->recs[i]); c->recs[i] = NULL; }
+	free(c->coefs); free(c->slices); c->frames_alloc = NULL; c->coefs = NULL; c->slices = NULL;
+}
+static void port_destroy(void *ctx) { port_free_all((PortCtx *)ctx); free(ctx); }
+static int port_configure(void *ctx, const E264PicDesc *g, int n_slots) {
+	PortCtx *c = (PortCtx *)ctx;
+	port_free_all(c);
+	c->g = *g; c->n_slots = n_slots;
+	size_t margin = (size_t)g->stride_y * 2 + 64;
+	c->frames_alloc = (uint8_t *)calloc((size_t)g->frame_bytes * n_slots + 2 * margin, 1);
+	if (!c->frames_alloc) return -1;
+	c->frames = c->frames_alloc + margin;
+	size_t nmb = (size_t)g->width_mbs * g->height_mbs;
+	for (int i = 0; i < n_slots; i++) if (!(c->recs[i] = (E264MbRec *)calloc(nmb, sizeof(E264MbRec)))) return -1;
+	c->coef_cap = (uint32_t)(nmb * 408);
+	c->coefs = (int16_t *)calloc(c->coef_cap, sizeof(int16_t));
+	c->slices = (E264SliceRec *)calloc(E264_MAX_SLICES, sizeof(E264SliceRec));
+	return c->coefs && c->slices ? 0 : -1;
+}
+static void *port_host_alloc(void *ctx, size_t bytes) { (void)ctx; return calloc(bytes, 1); }
+static void port_host_free(void *ctx, void *p) { (void)ctx; free(p); }
+static int port_acquire(void *ctx, int slot, E264MbRec **recs, int16_t **coefs, uint32_t *cap, E264SliceRec **slices) {
+	PortCtx *c = (PortCtx *)ctx;
+	*recs = c->recs[slot]; *coefs = c->coefs; *cap = c->coef_cap; *slices = c->slices; c->cur_slot = slot;
+	return 0;
+}
+static int port_submit(void *ctx, const E264PicDesc *pd, uint8_t *host_out, uint64_t *ticket) {
+	PortCtx *c = (PortCtx *)ctx;
+	port_recon_picture(c->frames, pd, c->recs[pd->dst_slot], c->coefs, c->slices);
+	memcpy(host_out, c->frames + (size_t)pd->dst_slot * pd->frame_bytes, (size_t)pd->frame_bytes);
+	*ticket = 0;
+	return 0;
+}
+static int port_wait(void *ctx, uint64_t ticket) { (void)ctx; (void)ticket; return 0; }
+static int port_fill(void *ctx, int slot, int y, int cc) {
+	PortCtx *c = (PortCtx *)ctx;
+	uint8_t *f = c->frames + (size_t)slot * c->g.frame_bytes;
+	memset(f, y, (size_t)c->g.plane_y); memset(f + c->g.plane_y, cc, (size_t)c->g.frame_bytes - c->g.plane_y);
+	return 0;
+}
+static const E264Backend port_backend = {"oracle-port", port_create, port_destroy, port_configure, port_host_alloc, port_host_free, port_acquire, port_submit, port_wait, port_fill};
+const E264Backend *e264_default_backend(void) { return &port_backend; }
