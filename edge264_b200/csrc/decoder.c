@@ -401,6 +401,8 @@ static int configure_sequence(Edge264Decoder *d, const SPS *s) {
 	return 0;
 }
 
+static inline int clamp8(int v) { return v < -128 ? -128 : v > 127 ? 127 : v; }   /* bounded reads like the reference's get_se16(-128,127) (headers.c:721-731) */
+
 /* ------------------------------------------------------------------------------------------ */
 /* slice header                                                                                 */
 /* ------------------------------------------------------------------------------------------ */
@@ -454,9 +456,9 @@ static int parse_slice_header(Edge264Decoder *d, BitReader *b, int nal_unit_type
 			h->luma_log2_wd = br_ue(b); h->chroma_log2_wd = br_ue(b);
 			if (h->luma_log2_wd > 7 || h->chroma_log2_wd > 7) return EBADMSG;
 			for (int l = 0; l <= h->slice_type; l++) for (int i = 0; i < h->num_ref[l]; i++) {
-				if (br_u1(b)) { h->w[l][i][0] = (int16_t)br_se(b); h->o[l][i][0] = (int16_t)br_se(b); }
+				if (br_u1(b)) { h->w[l][i][0] = (int16_t)clamp8(br_se(b)); h->o[l][i][0] = (int16_t)clamp8(br_se(b)); }
 				else { h->w[l][i][0] = (int16_t)(1 << h->luma_log2_wd); h->o[l][i][0] = 0; }
-				if (br_u1(b)) for (int c = 1; c < 3; c++) { h->w[l][i][c] = (int16_t)br_se(b); h->o[l][i][c] = (int16_t)br_se(b); }
+				if (br_u1(b)) for (int c = 1; c < 3; c++) { h->w[l][i][c] = (int16_t)clamp8(br_se(b)); h->o[l][i][c] = (int16_t)clamp8(br_se(b)); }
 				else for (int c = 1; c < 3; c++) { h->w[l][i][c] = (int16_t)(1 << h->chroma_log2_wd); h->o[l][i][c] = 0; }
 			}
 		}
@@ -686,6 +688,8 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 		int wp = h->slice_type == 0 ? p->weighted_pred_flag : p->weighted_bipred_idc;
 		sr->wp_mode = (uint8_t)wp; sr->luma_log2_wd = (uint8_t)h->luma_log2_wd; sr->chroma_log2_wd = (uint8_t)h->chroma_log2_wd;
 		if (wp == 1) for (int l = 0; l < 2; l++) for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) { sr->wp_w[l][i][k] = h->w[l][i][k]; sr->wp_o[l][i][k] = h->o[l][i][k]; }
+		if (wp == 1 && getenv("E264_DEBUG")) for (int l = 0; l <= (h->slice_type == 1); l++) for (int i = 0; i < h->num_ref[l]; i++)
+			fprintf(stderr, "wp l%d ref%d logwd %d/%d w %d %d %d o %d %d %d\n", l, i, h->luma_log2_wd, h->chroma_log2_wd, h->w[l][i][0], h->w[l][i][1], h->w[l][i][2], h->o[l][i][0], h->o[l][i][1], h->o[l][i][2]);
 		if (wp == 2) {   /* 8.4.2.3.1 implicit weights from POC distances */
 			for (int i0 = 0; i0 < h->num_ref[0] && i0 < 16; i0++) for (int i1 = 0; i1 < h->num_ref[1] && i1 < 16; i1++) {
 				int w1 = 32;

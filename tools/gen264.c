@@ -344,12 +344,12 @@ static void encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr
 			int wp = pp->type == 0 ? g->wp_p : g->wp_b;
 			if (wp == 1) {
 				if (sl == 0) {
-					lwd = rnd(g, 8); cwd = rnd(g, 8);
+					lwd = rnd(g, pp->type == 1 ? 7 : 8); cwd = rnd(g, pp->type == 1 ? 7 : 8);   /* logWD 7 + inferred weight 128 is only legal for uni-prediction */
 					for (int l = 0; l < 2; l++) for (int i = 0; i < 16; i++) for (int c = 0; c < 3; c++) {
 						int wd = c ? cwd : lwd;
 						int r = rnd(g, 10);
-						w_tab[l][i][c] = (int16_t)(r < 2 ? (1 << wd) : r == 2 ? (wd == 7 ? 127 : 1 << wd) : rnd(g, 72) - 16);
-						if (w_tab[l][i][c] > 63 && wd < 7) w_tab[l][i][c] = 63;
+						w_tab[l][i][c] = (int16_t)(r < 2 ? (wd == 7 ? 127 : 1 << wd) : rnd(g, 72) - 16);   /* coded values stay in -128..127 */
+						if (pp->type == 1 && w_tab[l][i][c] > 63) w_tab[l][i][c] = 63;                       /* bi-pred: w0 + w1 <= 127 */
 						o_tab[l][i][c] = (int16_t)(rnd(g, 41) - 20);
 					}
 				}
