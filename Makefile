@@ -1,0 +1,27 @@
+# Build of the product library (host C + sm_100a CUDA), the test tools and the oracle.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CC ?= gcc
+CSRC := edge264_b200/csrc
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wno-unused-function
+CFLAGS := -std=gnu11 -O3 -fPIC -Wall -Wno-unused-function -Wno-unused-variable -Wno-unused-but-set-variable
+LIB := edge264_b200/libedge264_b200.so
+
+all: $(LIB) tools/gen264 tools/b200_decode oracle
+
+$(CSRC)/recon.o: $(CSRC)/recon.cu $(CSRC)/recon_kernels.cuh $(wildcard $(CSRC)/*.h) include/e264b_recon.h
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(CSRC)/recon.ptxas.log || (cat $(CSRC)/recon.ptxas.log; false)
+$(CSRC)/decoder.o: $(CSRC)/decoder.c $(wildcard $(CSRC)/*.h)
+	$(CC) $(CFLAGS) -c $< -o $@
+$(CSRC)/slice_dec.o: $(CSRC)/slice_dec.c $(wildcard $(CSRC)/*.h)
+	$(CC) $(CFLAGS) -c $< -o $@
+$(LIB): $(CSRC)/recon.o $(CSRC)/decoder.o $(CSRC)/slice_dec.o
+	$(NVCC) -shared -o $@ $^ -cudart shared
+tools/gen264: tools/gen264.c $(wildcard $(CSRC)/*.h)
+	$(CC) $(CFLAGS) -O2 -o $@ $<
+tools/b200_decode: tools/e264_decode.c $(LIB)
+	$(CC) -O2 -std=gnu11 -Iinclude $< -o $@ -Wl,-rpath,'$$ORIGIN/../edge264_b200' -Ledge264_b200 -ledge264_b200
+oracle:
+	$(MAKE) -C oracle all
+clean:
+	rm -f $(CSRC)/*.o $(LIB) tools/gen264 tools/b200_decode
+.PHONY: all oracle clean

@@ -1,0 +1,289 @@
+/* recon.cu — CUDA runtime of the reconstruction backend + its C-ABI shim (include/e264b_recon.h).
+ *
+ * Replaces the reference's in-process contract between the slice parser and the pixel functions
+ * (reference: prototypes edge264_internal.h:1349-1374, call sites edge264_slice.c:466-664,881,1816,
+ * edge264_mvpred.c:73-513, edge264_headers.c:510,551) by: pinned staging filled by the parser ->
+ * cudaMemcpyAsync -> two kernels per picture on the decoder's stream -> cudaMemcpyAsync of the
+ * finished frame into a pinned host mirror.  Frames live in HBM in the reference's own layout
+ * (edge264_headers.c:2027-2046) so the mirror is what edge264_get_frame hands out.
+ * There is NO CPU fallback: without a CUDA device e264b_create() fails and edge264_alloc() returns NULL.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "recon_kernels.cuh"
+extern "C" {
+#include "dec.h"
+}
+#include "../../include/e264b_recon.h"
+
+#define NSTAGE 4
+#define NTICK 64
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "edge264_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -1; } } while (0)
+
+struct Staging {
+	E264MbRec *d_recs; int16_t *d_coefs, *h_coefs; E264SliceRec *d_slices, *h_slices;
+	cudaEvent_t done; bool busy;
+};
+struct KeptPic { E264PicDesc pd; E264MbRec *d_recs; int16_t *d_coefs; E264SliceRec *d_slices; };
+
+struct E264bDevice {
+	int dev; cudaStream_t stream;
+	E264PicDesc g; int n_slots; size_t nmb; uint32_t coef_cap;
+	uint8_t *d_frames;
+	E264MbRec *h_recs[E264_MAX_SLOTS]; cudaEvent_t rec_up[E264_MAX_SLOTS]; bool rec_busy[E264_MAX_SLOTS];
+	Staging st[NSTAGE]; int stage;
+	unsigned *d_sync;            /* [0..1] tickets, [2] err, then flags[2*nmb] */
+	unsigned epoch;
+	cudaEvent_t tick_ev[NTICK]; uint64_t tick_seq;
+	bool keep; std::vector<KeptPic> kept;
+	uint64_t launches, h2d_bytes, d2h_bytes;
+	int sm_count;
+};
+
+static void free_geometry(E264bDevice *c) {
+	cudaStreamSynchronize(c->stream);
+	if (c->d_frames) cudaFree(c->d_frames);
+	c->d_frames = NULL;
+	for (int i = 0; i < E264_MAX_SLOTS; i++) { if (c->h_recs[i]) cudaFreeHost(c->h_recs[i]); c->h_recs[i] = NULL; c->rec_busy[i] = false; }
+	for (int i = 0; i < NSTAGE; i++) {
+		Staging *s = &c->st[i];
+		if (s->d_recs) cudaFree(s->d_recs); if (s->d_coefs) cudaFree(s->d_coefs); if (s->d_slices) cudaFree(s->d_slices);
+		if (s->h_coefs) cudaFreeHost(s->h_coefs); if (s->h_slices) cudaFreeHost(s->h_slices);
+		s->d_recs = NULL; s->d_coefs = NULL; s->d_slices = NULL; s->h_coefs = NULL; s->h_slices = NULL; s->busy = false;
+	}
+	if (c->d_sync) cudaFree(c->d_sync);
+	c->d_sync = NULL;
+	for (auto &k : c->kept) { cudaFree(k.d_recs); cudaFree(k.d_coefs); cudaFree(k.d_slices); }
+	c->kept.clear();
+}
+
+extern "C" int e264b_create(E264bDevice **out) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+		fprintf(stderr, "edge264_b200: no CUDA device — the reconstruction backend has no CPU fallback\n");
+		return -1;
+	}
+	const char *e = getenv("E264B_DEVICE");
+	int dev = e ? atoi(e) : 0;
+	if (dev < 0 || dev >= n) dev = 0;
+	CK(cudaSetDevice(dev));
+	E264bDevice *c = new E264bDevice();
+	memset((void *)c, 0, offsetof(E264bDevice, kept));
+	c->dev = dev;
+	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	for (int i = 0; i < E264_MAX_SLOTS; i++) CK(cudaEventCreateWithFlags(&c->rec_up[i], cudaEventDisableTiming));
+	for (int i = 0; i < NSTAGE; i++) CK(cudaEventCreateWithFlags(&c->st[i].done, cudaEventDisableTiming));
+	for (int i = 0; i < NTICK; i++) CK(cudaEventCreateWithFlags(&c->tick_ev[i], cudaEventDisableTiming));
+	cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
+	const char *k = getenv("E264B_KEEP");
+	c->keep = k && atoi(k) != 0;
+	*out = c;
+	return 0;
+}
+
+extern "C" void e264b_destroy(E264bDevice *c) {
+	if (!c) return;
+	cudaSetDevice(c->dev);
+	free_geometry(c);
+	for (int i = 0; i < E264_MAX_SLOTS; i++) cudaEventDestroy(c->rec_up[i]);
+	for (int i = 0; i < NSTAGE; i++) cudaEventDestroy(c->st[i].done);
+	for (int i = 0; i < NTICK; i++) cudaEventDestroy(c->tick_ev[i]);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots) {
+	CK(cudaSetDevice(c->dev));
+	free_geometry(c);
+	c->g = *g; c->n_slots = n_slots; c->nmb = (size_t)g->width_mbs * g->height_mbs;
+	c->coef_cap = (uint32_t)(c->nmb * 408);
+	size_t pool = (size_t)g->frame_bytes * n_slots;
+	CK(cudaMalloc(&c->d_frames, pool + 256));
+	CK(cudaMemsetAsync(c->d_frames, 128, pool + 256, c->stream));
+	for (int i = 0; i < n_slots; i++) CK(cudaHostAlloc(&c->h_recs[i], c->nmb * sizeof(E264MbRec), cudaHostAllocDefault));
+	for (int i = 0; i < NSTAGE; i++) {
+		Staging *s = &c->st[i];
+		CK(cudaMalloc(&s->d_recs, c->nmb * sizeof(E264MbRec)));
+		CK(cudaMalloc(&s->d_coefs, (size_t)c->coef_cap * 2 + 64));
+		CK(cudaMalloc(&s->d_slices, E264_MAX_SLICES * sizeof(E264SliceRec)));
+		CK(cudaHostAlloc(&s->h_coefs, (size_t)c->coef_cap * 2 + 64, cudaHostAllocDefault));
+		CK(cudaHostAlloc(&s->h_slices, E264_MAX_SLICES * sizeof(E264SliceRec), cudaHostAllocDefault));
+	}
+	CK(cudaMalloc(&c->d_sync, (4 + 2 * c->nmb) * sizeof(unsigned)));
+	CK(cudaMemsetAsync(c->d_sync, 0, (4 + 2 * c->nmb) * sizeof(unsigned), c->stream));
+	c->epoch = 0; c->stage = 0;
+	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+extern "C" void *e264b_host_alloc(E264bDevice *c, size_t bytes) {
+	void *p = NULL;
+	cudaSetDevice(c->dev);
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return NULL;
+	return p;
+}
+extern "C" void e264b_host_free(E264bDevice *c, void *p) { cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream); cudaFreeHost(p); }
+
+extern "C" int e264b_acquire_staging(E264bDevice *c, int slot, E264MbRec **recs, int16_t **coefs, uint32_t *cap, E264SliceRec **slices) {
+	CK(cudaSetDevice(c->dev));
+	c->stage = (c->stage + 1) % NSTAGE;
+	Staging *s = &c->st[c->stage];
+	if (s->busy) { CK(cudaEventSynchronize(s->done)); s->busy = false; }
+	if (c->rec_busy[slot]) { CK(cudaEventSynchronize(c->rec_up[slot])); c->rec_busy[slot] = false; }
+	*recs = c->h_recs[slot]; *coefs = s->h_coefs; *cap = c->coef_cap; *slices = s->h_slices;
+	return 0;
+}
+
+static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, const E264MbRec *recs, const int16_t *coefs, const E264SliceRec *slices) {
+	PicJob J;
+	J.recs = recs; J.coefs = coefs; J.slices = slices; J.frames = c->d_frames;
+	J.frame_bytes = pd->frame_bytes; J.w_mbs = pd->width_mbs; J.h_mbs = pd->height_mbs;
+	J.stride_y = pd->stride_y; J.stride_c = pd->stride_c; J.plane_y = pd->plane_y; J.dst_slot = pd->dst_slot; J.n_slots = c->n_slots;
+	J.tickets = c->d_sync; J.err = c->d_sync + 2; J.flags = c->d_sync + 4;
+	J.epoch = ++c->epoch;
+	return J;
+}
+static int launch_picture(E264bDevice *c, const PicJob &J, int any_deblock) {
+	int nmb = J.w_mbs * J.h_mbs;
+	int blocks = (nmb + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+	int cap = c->sm_count * 8;
+	if (blocks > cap) blocks = cap;
+	CK(cudaMemsetAsync(c->d_sync, 0, 2 * sizeof(unsigned), c->stream));
+	e264_recon_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+	c->launches++;
+	if (any_deblock) { e264_deblock_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++; }
+	CK(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int e264b_submit(E264bDevice *c, const E264PicDesc *pd, uint8_t *host_out, uint64_t *ticket) {
+	CK(cudaSetDevice(c->dev));
+	Staging *s = &c->st[c->stage];
+	size_t rec_bytes = c->nmb * sizeof(E264MbRec), coef_bytes = ((size_t)pd->n_coefs * 2 + 15) & ~(size_t)15, sl_bytes = (size_t)pd->n_slices * sizeof(E264SliceRec);
+	CK(cudaMemcpyAsync(s->d_recs, c->h_recs[pd->dst_slot], rec_bytes, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaEventRecord(c->rec_up[pd->dst_slot], c->stream)); c->rec_busy[pd->dst_slot] = true;
+	if (coef_bytes) CK(cudaMemcpyAsync(s->d_coefs, s->h_coefs, coef_bytes, cudaMemcpyHostToDevice, c->stream));
+	if (sl_bytes) CK(cudaMemcpyAsync(s->d_slices, s->h_slices, sl_bytes, cudaMemcpyHostToDevice, c->stream));
+	c->h2d_bytes += rec_bytes + coef_bytes + sl_bytes;
+	PicJob J = make_job(c, pd, s->d_recs, s->d_coefs, s->d_slices);
+	if (launch_picture(c, J, pd->any_deblock)) return -1;
+	if (host_out) { CK(cudaMemcpyAsync(host_out, c->d_frames + (size_t)pd->dst_slot * pd->frame_bytes, (size_t)pd->frame_bytes - 16, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (size_t)pd->frame_bytes - 16; }
+	if (c->keep) {
+		KeptPic k; k.pd = *pd;
+		CK(cudaMalloc(&k.d_recs, rec_bytes)); CK(cudaMalloc(&k.d_coefs, coef_bytes + 64)); CK(cudaMalloc(&k.d_slices, sl_bytes + 64));
+		CK(cudaMemcpyAsync(k.d_recs, s->d_recs, rec_bytes, cudaMemcpyDeviceToDevice, c->stream));
+		if (coef_bytes) CK(cudaMemcpyAsync(k.d_coefs, s->d_coefs, coef_bytes, cudaMemcpyDeviceToDevice, c->stream));
+		if (sl_bytes) CK(cudaMemcpyAsync(k.d_slices, s->d_slices, sl_bytes, cudaMemcpyDeviceToDevice, c->stream));
+		c->kept.push_back(k);
+	}
+	CK(cudaEventRecord(s->done, c->stream)); s->busy = true;
+	uint64_t t = ++c->tick_seq;
+	CK(cudaEventRecord(c->tick_ev[t % NTICK], c->stream));
+	*ticket = t;
+	return 0;
+}
+
+extern "C" int e264b_wait(E264bDevice *c, uint64_t ticket) {
+	if (ticket == 0) return 0;
+	/* the ring slot holds this ticket or a later one of the same stream: either way it implies completion */
+	CK(cudaSetDevice(c->dev));
+	CK(cudaEventSynchronize(c->tick_ev[ticket % NTICK]));
+	return 0;
+}
+
+extern "C" int e264b_fill_slot(E264bDevice *c, int slot, int y, int cc) {
+	CK(cudaSetDevice(c->dev));
+	uint8_t *f = c->d_frames + (size_t)slot * c->g.frame_bytes;
+	CK(cudaMemsetAsync(f, y, (size_t)c->g.plane_y, c->stream));
+	CK(cudaMemsetAsync(f + c->g.plane_y, cc, (size_t)c->g.frame_bytes - c->g.plane_y, c->stream));
+	return 0;
+}
+
+extern "C" int e264b_error_flag(E264bDevice *c) {
+	unsigned v = 0;
+	cudaSetDevice(c->dev);
+	cudaStreamSynchronize(c->stream);
+	cudaMemcpy(&v, c->d_sync + 2, sizeof(v), cudaMemcpyDeviceToHost);
+	return (int)v;
+}
+extern "C" void e264b_stats(E264bDevice *c, uint64_t *launches, uint64_t *h2d, uint64_t *d2h) { if (launches) *launches = c->launches; if (h2d) *h2d = c->h2d_bytes; if (d2h) *d2h = c->d2h_bytes; }
+extern "C" int e264b_kept_count(E264bDevice *c) { return (int)c->kept.size(); }
+
+/* algorithmic bytes of the kept pictures per SURVEY.md §8(d): Rec + 384*(1+L) + 768*D per macroblock */
+extern "C" double e264b_kept_algorithmic_bytes(E264bDevice *c, double *recon_bytes, double *deblock_bytes, uint64_t *mbs) {
+	cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
+	double rec = 0, db = 0; uint64_t n = 0;
+	std::vector<E264MbRec> h(c->nmb);
+	for (auto &k : c->kept) {
+		cudaMemcpy(h.data(), k.d_recs, c->nmb * sizeof(E264MbRec), cudaMemcpyDeviceToHost);
+		rec += (double)k.pd.n_coefs * 2 + (double)c->nmb * sizeof(E264MbRec);
+		for (size_t i = 0; i < c->nmb; i++) {
+			int L = 0;
+			if (h[i].kind == MBK_INTER) { int l0 = 0, l1 = 0; for (int j = 0; j < 4; j++) { l0 |= h[i].ref_idx[0][j] >= 0; l1 |= h[i].ref_idx[1][j] >= 0; } L = l0 + l1; }
+			rec += 384.0 * (1 + L);
+			if (h[i].flags & MBF_DEBLOCK) db += 768.0;
+		}
+		n += c->nmb;
+	}
+	if (recon_bytes) *recon_bytes = rec; if (deblock_bytes) *deblock_bytes = db; if (mbs) *mbs = n;
+	return rec + db;
+}
+
+/* replay the kept pictures of several decoders concurrently (one stream each), `reps` times;
+ * returns the elapsed device time in ms between a start event and the last stream's end */
+extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, float *ms_total, float *ms_recon_only, uint64_t *launches) {
+	if (n <= 0) return -1;
+	CK(cudaSetDevice(cs[0]->dev));
+	cudaEvent_t start, stop; std::vector<cudaEvent_t> ends(n);
+	CK(cudaEventCreate(&start)); CK(cudaEventCreate(&stop));
+	for (int i = 0; i < n; i++) { CK(cudaEventCreateWithFlags(&ends[i], cudaEventDisableTiming)); CK(cudaStreamSynchronize(cs[i]->stream)); }
+	size_t npic = cs[0]->kept.size();
+	for (int i = 1; i < n; i++) if (cs[i]->kept.size() < npic) npic = cs[i]->kept.size();
+	uint64_t l0 = 0; for (int i = 0; i < n; i++) l0 += cs[i]->launches;
+	for (int pass = 0; pass < (ms_recon_only ? 2 : 1); pass++) {
+		CK(cudaEventRecord(start, cs[0]->stream));
+		for (int i = 1; i < n; i++) CK(cudaStreamWaitEvent(cs[i]->stream, start, 0));
+		for (int r = 0; r < reps; r++)
+			for (size_t k = 0; k < npic; k++)
+				for (int i = 0; i < n; i++) {
+					KeptPic &kp = cs[i]->kept[k];
+					PicJob J = make_job(cs[i], &kp.pd, kp.d_recs, kp.d_coefs, kp.d_slices);
+					if (launch_picture(cs[i], J, pass == 0 ? kp.pd.any_deblock : 0)) return -1;
+				}
+		for (int i = 1; i < n; i++) { CK(cudaEventRecord(ends[i], cs[i]->stream)); CK(cudaStreamWaitEvent(cs[0]->stream, ends[i], 0)); }
+		CK(cudaEventRecord(stop, cs[0]->stream));
+		CK(cudaEventSynchronize(stop));
+		float ms = 0; CK(cudaEventElapsedTime(&ms, start, stop));
+		if (pass == 0) { if (ms_total) *ms_total = ms; uint64_t l1 = 0; for (int i = 0; i < n; i++) l1 += cs[i]->launches; if (launches) *launches = l1 - l0; }
+		else *ms_recon_only = ms;
+	}
+	cudaEventDestroy(start); cudaEventDestroy(stop); for (int i = 0; i < n; i++) cudaEventDestroy(ends[i]);
+	return 0;
+}
+
+/* checksum of a frame slot (FNV-1a over the whole slot), for replay-vs-decode comparisons */
+extern "C" uint64_t e264b_slot_hash(E264bDevice *c, int slot) {
+	cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream);
+	std::vector<uint8_t> h((size_t)c->g.frame_bytes);
+	cudaMemcpy(h.data(), c->d_frames + (size_t)slot * c->g.frame_bytes, h.size(), cudaMemcpyDeviceToHost);
+	uint64_t x = 0xcbf29ce484222325ull;
+	for (size_t i = 0; i + 16 < h.size(); i++) x = (x ^ h[i]) * 0x100000001b3ull;
+	return x;
+}
+
+/* ---- backend vtable for decoder.c ---- */
+static int be_create(void **ctx) { return e264b_create((E264bDevice **)ctx); }
+static void be_destroy(void *ctx) { e264b_destroy((E264bDevice *)ctx); }
+static int be_configure(void *ctx, const E264PicDesc *g, int n) { return e264b_configure((E264bDevice *)ctx, g, n); }
+static void *be_host_alloc(void *ctx, size_t b) { return e264b_host_alloc((E264bDevice *)ctx, b); }
+static void be_host_free(void *ctx, void *p) { e264b_host_free((E264bDevice *)ctx, p); }
+static int be_acquire(void *ctx, int slot, E264MbRec **r, int16_t **c, uint32_t *cap, E264SliceRec **s) { return e264b_acquire_staging((E264bDevice *)ctx, slot, r, c, cap, s); }
+static int be_submit(void *ctx, const E264PicDesc *pd, uint8_t *out, uint64_t *t) { return e264b_submit((E264bDevice *)ctx, pd, out, t); }
+static int be_wait(void *ctx, uint64_t t) { return e264b_wait((E264bDevice *)ctx, t); }
+static int be_fill(void *ctx, int slot, int y, int c) { return e264b_fill_slot((E264bDevice *)ctx, slot, y, c); }
+static const E264Backend cuda_backend = {"cuda-sm_100a", be_create, be_destroy, be_configure, be_host_alloc, be_host_free, be_acquire, be_submit, be_wait, be_fill};
+extern "C" const E264Backend *e264_default_backend(void) { return &cuda_backend; }
+extern "C" E264bDevice *e264b_of_decoder(Edge264Decoder *d) { return d ? (E264bDevice *)d->be_ctx : NULL; }

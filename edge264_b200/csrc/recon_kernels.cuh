@@ -1,0 +1,801 @@
+/* recon_kernels.cuh — sm_100a device code of the pixel-reconstruction path.
+ *
+ * One warp per macroblock.  Two kernels per picture:
+ *   e264_recon_kernel    inverse quantisation + 4x4/8x8 inverse transforms + DC transforms
+ *                        (reference edge264_residual.c:108-538), intra prediction of every mode
+ *                        (edge264_intra.c:291-765), 6-tap / bilinear motion compensation with
+ *                        default / explicit / implicit weighting (edge264_inter.c:416-1251);
+ *   e264_deblock_kernel  boundary strengths and the in-loop filter (edge264_deblock.c:284-1123).
+ * Warps take macroblocks in raster order from a ticket counter; an intra macroblock waits on the
+ * "done" flags of its A/B/C/D neighbours, a deblocked macroblock on (x-1,y) and (x+1,y-1) — the
+ * same dependencies the reference resolves by decoding in raster order with deblocking one row
+ * behind (edge264_slice.c:1809-1826).  Arithmetic is restated from ITU-T H.264 with the reference's
+ * observable integer widths; results are bit-exact with the reference decoder (tests/test_gpu_*.py).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "records.h"
+#include "h264_tables.h"
+
+struct PicJob {
+	const E264MbRec *recs; const int16_t *coefs; const E264SliceRec *slices;
+	uint8_t *frames;
+	int frame_bytes, w_mbs, h_mbs, stride_y, stride_c, plane_y, dst_slot, n_slots;
+	unsigned *flags;      /* [2][nmb]: recon done / deblock done == epoch */
+	unsigned epoch;
+	unsigned *tickets;    /* [2] zeroed before the picture */
+	unsigned *err;
+};
+
+#define WARPS_PER_BLOCK 4
+#define YT_STRIDE 48     /* luma tile row: [15]=left neighbour, [16..31]=samples, [32..39]=top-right */
+#define CT_STRIDE 16     /* chroma tile row: [7]=left neighbour, [8..15]=samples */
+#define WIN_STRIDE 24
+
+struct __align__(16) WarpSmem {
+	uint4 rec4[12];                 /* the macroblock record */
+	int16_t res[384];               /* residual: luma y*16+x, then Cb, Cr 8x8 */
+	uint8_t ytile[17 * YT_STRIDE];  /* row 0 = samples above the macroblock */
+	uint8_t ctile[2][9 * CT_STRIDE];
+	int dc[24];                     /* scaled DC: 16 luma (raster over blocks), 4 Cb, 4 Cr */
+	union {
+		int16_t t8[4 * 64];         /* 8x8 transform transpose buffer */
+		uint8_t win[21 * WIN_STRIDE + 2 * 9 * 12];   /* MC windows: luma, Cb, Cr */
+		int edge[2][28];            /* intra 8x8 filtered reference samples */
+	} u;
+};
+
+__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int sat16(int v) { return min(max(v, -32768), 32767); }
+__device__ __forceinline__ int blk_x(int b) { return (b & 1) | ((b >> 1) & 2); }
+__device__ __forceinline__ int blk_y(int b) { return ((b >> 1) & 1) | ((b >> 2) & 2); }
+__device__ __forceinline__ int blk_z(int x, int y) { return (x & 1) | ((y & 1) << 1) | ((x & 2) << 1) | ((y & 2) << 2); }
+__device__ __forceinline__ int norm4(int m, int i, int j) { return h264_norm4x4[m][((i & 1) && (j & 1)) ? 1 : (!(i & 1) && !(j & 1)) ? 0 : 2]; }
+__device__ __forceinline__ int norm8(int m, int i, int j) {
+	int k;
+	if (!(i & 3) && !(j & 3)) k = 0;
+	else if ((i & 1) && (j & 1)) k = 1;
+	else if ((i & 3) == 2 && (j & 3) == 2) k = 2;
+	else if ((!(i & 3) && (j & 1)) || ((i & 1) && !(j & 3))) k = 3;
+	else if ((!(i & 3) && (j & 3) == 2) || ((i & 3) == 2 && !(j & 3))) k = 4;
+	else k = 5;
+	return h264_norm8x8[m][k];
+}
+
+/* spin until flags[idx] == epoch (lane 0), bounded so that a bug cannot hang the GPU */
+__device__ __forceinline__ bool wait_flag(const unsigned *flags, int idx, unsigned epoch, unsigned *err) {
+	const volatile unsigned *f = flags + idx;
+	unsigned spins = 0;
+	while (*f != epoch) {
+		__nanosleep(64);
+		if (++spins > (1u << 24)) { atomicExch(err, 1u); return false; }
+	}
+	return true;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* residual                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+/* 4x4 inverse transform of 16 levels at c (16-byte aligned) -> residual written to dst[y*dstride+x] */
+__device__ __forceinline__ void idct4x4(const int16_t *c, bool have_levels, const uint8_t *scaling, int qp, bool dc_override, int dc, int16_t *dst, int dstride) {
+	int d[16];
+	if (have_levels) {
+		uint4 a = __ldg((const uint4 *)c), b = __ldg((const uint4 *)c + 1);
+		int16_t lv[16];
+		*(uint4 *)lv = a; *(uint4 *)(lv + 8) = b;
+		int sh = qp / 6, m = qp - sh * 6;
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				int ls = scaling[i * 4 + j] * norm4(m, i, j);
+				d[i * 4 + j] = (int)(((unsigned)(lv[i * 4 + j] * ls) << sh) + 8u) >> 4;
+			}
+	} else {
+#pragma unroll
+		for (int i = 0; i < 16; i++) d[i] = 0;
+	}
+	if (dc_override) d[0] = dc;
+	int f[16];
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		int e0 = d[i * 4] + d[i * 4 + 2], e1 = d[i * 4] - d[i * 4 + 2];
+		int e2 = (d[i * 4 + 1] >> 1) - d[i * 4 + 3], e3 = d[i * 4 + 1] + (d[i * 4 + 3] >> 1);
+		f[i * 4] = e0 + e3; f[i * 4 + 1] = e1 + e2; f[i * 4 + 2] = e1 - e2; f[i * 4 + 3] = e0 - e3;
+	}
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		int g0 = f[j] + f[8 + j], g1 = f[j] - f[8 + j];
+		int g2 = (f[4 + j] >> 1) - f[12 + j], g3 = f[4 + j] + (f[12 + j] >> 1);
+		dst[j] = (int16_t)sat16((g0 + g3 + 32) >> 6);
+		dst[dstride + j] = (int16_t)sat16((g1 + g2 + 32) >> 6);
+		dst[2 * dstride + j] = (int16_t)sat16((g1 - g2 + 32) >> 6);
+		dst[3 * dstride + j] = (int16_t)sat16((g0 - g3 + 32) >> 6);
+	}
+}
+
+/* one 8-point pass in the reference's int16 arithmetic (edge264_residual.c:250-296) */
+__device__ __forceinline__ void idct8_1d(short a[8]) {
+	short e0 = (short)(a[0] + a[4]), e1 = (short)(a[5] - a[3] - (short)((a[7] >> 1) + a[7])), e2 = (short)(a[0] - a[4]);
+	short e3 = (short)(a[1] + a[7] - (short)((a[3] >> 1) + a[3])), e4 = (short)((a[2] >> 1) - a[6]);
+	short e5 = (short)(a[7] - a[1] + (short)((a[5] >> 1) + a[5])), e6 = (short)((a[6] >> 1) + a[2]);
+	short e7 = (short)(a[3] + a[5] + (short)((a[1] >> 1) + a[1]));
+	short f0 = (short)(e0 + e6), f1 = (short)((e7 >> 2) + e1), f2 = (short)(e2 + e4), f3 = (short)((e5 >> 2) + e3);
+	short f4 = (short)(e2 - e4), f5 = (short)((e3 >> 2) - e5), f6 = (short)(e0 - e6), f7 = (short)(e7 - (e1 >> 2));
+	a[0] = (short)(f0 + f7); a[1] = (short)(f2 + f5); a[2] = (short)(f4 + f3); a[3] = (short)(f6 + f1);
+	a[4] = (short)(f6 - f1); a[5] = (short)(f4 - f3); a[6] = (short)(f2 - f5); a[7] = (short)(f0 - f7);
+}
+
+__device__ void residual_stage(WarpSmem *ws, const E264MbRec *r, const E264SliceRec *sr, const int16_t *pool, int lane) {
+	/* clear */
+	uint4 z = make_uint4(0, 0, 0, 0);
+	((uint4 *)ws->res)[lane] = z;
+	if (lane < 16) ((uint4 *)ws->res)[32 + lane] = z;
+	const unsigned coded = r->coded;
+	const int inter = r->kind == MBK_INTER, i16 = r->kind == MBK_I16x16;
+	const int16_t *cf = pool + r->coef_off;
+	const int qpy = r->qp[0];
+	/* --- DC transforms first --- */
+	if (coded & CODED_Y_DC) {
+		if (lane < 16) {
+			int i = lane >> 2, j = lane & 3, u = 0;
+			const unsigned neg[4] = {0x0, 0xC, 0x6, 0xA};
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+#pragma unroll
+				for (int l = 0; l < 4; l++) {
+					int v = __ldg(cf + k * 4 + l);
+					int s = ((neg[i] >> k) ^ (neg[j] >> l)) & 1;
+					u += s ? -v : v;
+				}
+			int ls = (sr->scaling4x4[0][0] * h264_norm4x4[qpy % 6][0]) << (qpy / 6);
+			ws->dc[lane] = (u * ls + 32) >> 6;
+		}
+		cf += 16;
+	} else if (lane < 16) ws->dc[lane] = 0;
+	const int n_luma = (r->flags & MBF_T8x8) ? 64 * __popc(coded & 0x1111) : 16 * __popc(coded & 0xffff);
+	const int16_t *cf_luma = cf;
+	cf += n_luma;
+	const bool any_cdc = (coded & (CODED_CB_DC | CODED_CR_DC)) != 0;
+	if (lane >= 16 && lane < 24) {
+		int pl = (lane - 16) >> 2, i = lane & 3, v = 0;
+		if (any_cdc) {
+			int a = __ldg(cf + 4 * pl), b = __ldg(cf + 4 * pl + 1), c = __ldg(cf + 4 * pl + 2), d = __ldg(cf + 4 * pl + 3);
+			int f = i == 0 ? a + b + c + d : i == 1 ? a - b + c - d : i == 2 ? a + b - c - d : a - b - c + d;
+			int qpc = r->qp[1 + pl];
+			int ls = (sr->scaling4x4[1 + pl + inter * 3][0] * h264_norm4x4[qpc % 6][0]) << (qpc / 6);
+			v = (f * ls) >> 5;
+		}
+		ws->dc[16 + pl * 4 + i] = v;
+	}
+	if (any_cdc) cf += 8;
+	__syncwarp();
+	/* --- luma --- */
+	if (r->flags & MBF_T8x8) {
+		int blk = lane >> 3, k = lane & 7;
+		bool on = (coded >> (blk * 4)) & 1;
+		short a[8];
+		if (on) {
+			int idx = __popc(coded & 0x1111 & ((1u << (blk * 4)) - 1));
+			uint4 q = __ldg((const uint4 *)(cf_luma + idx * 64 + k * 8));
+			short lv[8]; *(uint4 *)lv = q;
+			int div = qpy / 6, m = qpy - div * 6;
+			const uint8_t *sc = sr->scaling8x8[inter] + k * 8;
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				int ls = sc[j] * norm8(m, k, j);
+				a[j] = div < 6 ? (short)sat16((lv[j] * ls + (1 << (5 - div))) >> (6 - div)) : (short)(lv[j] * (short)(ls << (div - 6)));
+			}
+			idct8_1d(a);
+#pragma unroll
+			for (int j = 0; j < 8; j++) ws->u.t8[blk * 64 + k * 8 + j] = a[j];
+		}
+		__syncwarp();
+		if (on) {
+#pragma unroll
+			for (int j = 0; j < 8; j++) a[j] = ws->u.t8[blk * 64 + j * 8 + k];
+			a[0] = (short)(a[0] + 32);
+			idct8_1d(a);
+			int x = (blk & 1) * 8 + k, y0 = (blk >> 1) * 8;
+#pragma unroll
+			for (int j = 0; j < 8; j++) ws->res[(y0 + j) * 16 + x] = (short)(a[j] >> 6);
+		}
+		__syncwarp();
+	} else if (lane < 16) {
+		int b = lane;
+		bool on = (coded >> b) & 1, dcov = i16 && (coded & CODED_Y_DC);
+		if (on || dcov) {
+			int idx = __popc(coded & ((1u << b) - 1));
+			int bx = blk_x(b), by = blk_y(b);
+			idct4x4(cf_luma + idx * 16, on, sr->scaling4x4[inter * 3], qpy, i16, ws->dc[by * 4 + bx], ws->res + by * 4 * 16 + bx * 4, 16);
+		}
+	}
+	/* --- chroma AC (+DC) --- */
+	if (lane >= 16 && lane < 24) {
+		int j = lane - 16, pl = j >> 2, i = j & 3;
+		bool on = (coded >> (16 + j)) & 1;
+		if (on || any_cdc) {
+			int idx = __popc((coded >> 16) & ((1u << j) - 1) & 0xff);
+			idct4x4(cf + idx * 16, on, sr->scaling4x4[1 + pl + inter * 3], r->qp[1 + pl], true, ws->dc[16 + pl * 4 + i], ws->res + 256 + pl * 64 + (i >> 1) * 4 * 8 + (i & 1) * 4, 8);
+		}
+	}
+	__syncwarp();
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* intra prediction                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+#define YT(x, y) ws->ytile[((y) + 1) * YT_STRIDE + 16 + (x)]     /* x in -1..23, y in -1..15 */
+#define CT(pl, x, y) ws->ctile[pl][((y) + 1) * CT_STRIDE + 8 + (x)]
+
+/* predicted sample (x,y) of a 4x4 block whose top-left tile coordinate is (X0,Y0) */
+__device__ __forceinline__ int pred4x4(const WarpSmem *ws, int X0, int Y0, int imode, int x, int y) {
+	int mode = imode & 15, un = imode >> 4;
+	bool hasA = !(un & 1), hasB = !(un & 2), hasC = !(un & 4);
+#define T(i) ((i) < 0 ? (int)YT(X0 - 1, Y0 - 1) : (int)YT(X0 + (((i) > 3 && !hasC) ? 3 : (i)), Y0 - 1))
+#define L(i) ((i) < 0 ? (int)YT(X0 - 1, Y0 - 1) : (int)YT(X0 - 1, Y0 + (i)))
+	switch (mode) {
+	case 0: return T(x);
+	case 1: return L(y);
+	case 2:
+		if (hasA && hasB) return (T(0) + T(1) + T(2) + T(3) + L(0) + L(1) + L(2) + L(3) + 4) >> 3;
+		if (hasA) return (L(0) + L(1) + L(2) + L(3) + 2) >> 2;
+		if (hasB) return (T(0) + T(1) + T(2) + T(3) + 2) >> 2;
+		return 128;
+	case 3: return (x == 3 && y == 3) ? (T(6) + 3 * T(7) + 2) >> 2 : (T(x + y) + 2 * T(x + y + 1) + T(x + y + 2) + 2) >> 2;
+	case 4:
+		if (x > y) return (T(x - y - 2) + 2 * T(x - y - 1) + T(x - y) + 2) >> 2;
+		if (x < y) return (L(y - x - 2) + 2 * L(y - x - 1) + L(y - x) + 2) >> 2;
+		return (T(0) + 2 * T(-1) + L(0) + 2) >> 2;
+	case 5: {
+		int z = 2 * x - y;
+		if (z >= 0 && !(z & 1)) return (T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 1) >> 1;
+		if (z > 0) return (T(x - (y >> 1) - 2) + 2 * T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 2) >> 2;
+		if (z == -1) return (L(0) + 2 * L(-1) + T(0) + 2) >> 2;
+		return (L(y - 1) + 2 * L(y - 2) + L(y - 3) + 2) >> 2; }
+	case 6: {
+		int z = 2 * y - x;
+		if (z >= 0 && !(z & 1)) return (L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 1) >> 1;
+		if (z > 0) return (L(y - (x >> 1) - 2) + 2 * L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 2) >> 2;
+		if (z == -1) return (L(0) + 2 * L(-1) + T(0) + 2) >> 2;
+		return (T(x - 1) + 2 * T(x - 2) + T(x - 3) + 2) >> 2; }
+	case 7:
+		if (!(y & 1)) return (T(x + (y >> 1)) + T(x + (y >> 1) + 1) + 1) >> 1;
+		return (T(x + (y >> 1)) + 2 * T(x + (y >> 1) + 1) + T(x + (y >> 1) + 2) + 2) >> 2;
+	default: {
+		int z = x + 2 * y;
+		if (z > 5) return L(3);
+		if (z == 5) return (L(2) + 3 * L(3) + 2) >> 2;
+		if (!(z & 1)) return (L(y + (x >> 1)) + L(y + (x >> 1) + 1) + 1) >> 1;
+		return (L(y + (x >> 1)) + 2 * L(y + (x >> 1) + 1) + L(y + (x >> 1) + 2) + 2) >> 2; }
+	}
+#undef T
+#undef L
+}
+
+/* Intra 8x8: filtered reference samples in ws->u.edge[0][1+x] (top, x=-1..15) and edge[1][1+y] (left, y=-1..7) */
+__device__ void intra8x8_edges(WarpSmem *ws, int X0, int Y0, int un, int lane) {
+	bool hasA = !(un & 1), hasB = !(un & 2), hasC = !(un & 4), hasD = !(un & 8);
+#define RT(i) ((i) < 0 ? (int)YT(X0 - 1, Y0 - 1) : (int)YT(X0 + (((i) > 7 && !hasC) ? 7 : (i)), Y0 - 1))
+#define RL(i) ((i) < 0 ? (int)YT(X0 - 1, Y0 - 1) : (int)YT(X0 - 1, Y0 + (i)))
+	if (lane < 16) {   /* top x = lane */
+		int x = lane, v = 128;
+		if (hasB) {
+			if (x == 0) v = hasD ? (RT(-1) + 2 * RT(0) + RT(1) + 2) >> 2 : (3 * RT(0) + RT(1) + 2) >> 2;
+			else if (x == 15) v = (RT(14) + 3 * RT(15) + 2) >> 2;
+			else v = (RT(x - 1) + 2 * RT(x) + RT(x + 1) + 2) >> 2;
+		}
+		ws->u.edge[0][1 + x] = v;
+	} else if (lane < 24) {   /* left y = lane - 16 */
+		int y = lane - 16, v = 128;
+		if (hasA) {
+			if (y == 0) v = hasD ? (RL(-1) + 2 * RL(0) + RL(1) + 2) >> 2 : (3 * RL(0) + RL(1) + 2) >> 2;
+			else if (y == 7) v = (RL(6) + 3 * RL(7) + 2) >> 2;
+			else v = (RL(y - 1) + 2 * RL(y) + RL(y + 1) + 2) >> 2;
+		}
+		ws->u.edge[1][1 + y] = v;
+	} else if (lane == 24) {
+		int v = hasD ? RT(-1) : 128;
+		if (hasD) {
+			if (hasA && hasB) v = (RT(0) + 2 * RT(-1) + RL(0) + 2) >> 2;
+			else if (hasB) v = (3 * RT(-1) + RT(0) + 2) >> 2;
+			else if (hasA) v = (3 * RT(-1) + RL(0) + 2) >> 2;
+		}
+		ws->u.edge[0][0] = v; ws->u.edge[1][0] = v;
+	}
+#undef RT
+#undef RL
+	__syncwarp();
+}
+__device__ __forceinline__ int pred8x8(const WarpSmem *ws, int imode, int x, int y) {
+	int mode = imode & 15, un = imode >> 4;
+	bool hasA = !(un & 1), hasB = !(un & 2);
+#define T(i) ws->u.edge[0][1 + (i)]
+#define L(i) ws->u.edge[1][1 + (i)]
+	switch (mode) {
+	case 0: return T(x);
+	case 1: return L(y);
+	case 2: {
+		int st = 0, sl = 0;
+#pragma unroll
+		for (int k = 0; k < 8; k++) { st += T(k); sl += L(k); }
+		return (hasA && hasB) ? (st + sl + 8) >> 4 : hasA ? (sl + 4) >> 3 : hasB ? (st + 4) >> 3 : 128; }
+	case 3: return (x == 7 && y == 7) ? (T(14) + 3 * T(15) + 2) >> 2 : (T(x + y) + 2 * T(x + y + 1) + T(x + y + 2) + 2) >> 2;
+	case 4:
+		if (x > y) return (T(x - y - 2) + 2 * T(x - y - 1) + T(x - y) + 2) >> 2;
+		if (x < y) return (L(y - x - 2) + 2 * L(y - x - 1) + L(y - x) + 2) >> 2;
+		return (T(0) + 2 * T(-1) + L(0) + 2) >> 2;
+	case 5: {
+		int z = 2 * x - y;
+		if (z >= 0 && !(z & 1)) return (T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 1) >> 1;
+		if (z > 0) return (T(x - (y >> 1) - 2) + 2 * T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 2) >> 2;
+		if (z == -1) return (L(0) + 2 * L(-1) + T(0) + 2) >> 2;
+		return (L(y - 2 * x - 1) + 2 * L(y - 2 * x - 2) + L(y - 2 * x - 3) + 2) >> 2; }
+	case 6: {
+		int z = 2 * y - x;
+		if (z >= 0 && !(z & 1)) return (L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 1) >> 1;
+		if (z > 0) return (L(y - (x >> 1) - 2) + 2 * L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 2) >> 2;
+		if (z == -1) return (L(0) + 2 * L(-1) + T(0) + 2) >> 2;
+		return (T(x - 2 * y - 1) + 2 * T(x - 2 * y - 2) + T(x - 2 * y - 3) + 2) >> 2; }
+	case 7:
+		if (!(y & 1)) return (T(x + (y >> 1)) + T(x + (y >> 1) + 1) + 1) >> 1;
+		return (T(x + (y >> 1)) + 2 * T(x + (y >> 1) + 1) + T(x + (y >> 1) + 2) + 2) >> 2;
+	default: {
+		int z = x + 2 * y;
+		if (z > 13) return L(7);
+		if (z == 13) return (L(6) + 3 * L(7) + 2) >> 2;
+		if (!(z & 1)) return (L(y + (x >> 1)) + L(y + (x >> 1) + 1) + 1) >> 1;
+		return (L(y + (x >> 1)) + 2 * L(y + (x >> 1) + 1) + L(y + (x >> 1) + 2) + 2) >> 2; }
+	}
+#undef T
+#undef L
+}
+
+__device__ void intra_luma(WarpSmem *ws, const E264MbRec *r, int lane) {
+	if (r->kind == MBK_I4x4) {
+		for (int b = 0; b < 16; b++) {
+			int X0 = blk_x(b) * 4, Y0 = blk_y(b) * 4;
+			if (lane < 16) {
+				int x = lane & 3, y = lane >> 2;
+				int v = pred4x4(ws, X0, Y0, r->modes[b], x, y);
+				v = clip255((short)(v + ws->res[(Y0 + y) * 16 + X0 + x]));
+				YT(X0 + x, Y0 + y) = (uint8_t)v;   /* reads above touch only samples outside the block */
+			}
+			__syncwarp();
+		}
+	} else if (r->kind == MBK_I8x8) {
+		for (int i = 0; i < 4; i++) {
+			int X0 = (i & 1) * 8, Y0 = (i >> 1) * 8, im = r->modes[i];
+			intra8x8_edges(ws, X0, Y0, im >> 4, lane);
+			int x = lane & 7, y = lane >> 3;
+			int v0 = pred8x8(ws, im, x, y), v1 = pred8x8(ws, im, x, y + 4);
+			v0 = clip255((short)(v0 + ws->res[(Y0 + y) * 16 + X0 + x]));
+			v1 = clip255((short)(v1 + ws->res[(Y0 + y + 4) * 16 + X0 + x]));
+			__syncwarp();
+			YT(X0 + x, Y0 + y) = (uint8_t)v0; YT(X0 + x, Y0 + y + 4) = (uint8_t)v1;
+			__syncwarp();
+		}
+	} else {   /* Intra16x16 */
+		int mode = r->i16_mode & 15, un = r->i16_mode >> 4;
+		bool hasA = !(un & 1), hasB = !(un & 2);
+		int a = 0, b = 0, c = 0, dc = 128;
+		if (mode == 3) {
+			int H = 0, V = 0;
+#pragma unroll
+			for (int k = 0; k < 8; k++) { H += (k + 1) * ((int)YT(8 + k, -1) - (int)YT(6 - k, -1)); V += (k + 1) * ((int)YT(-1, 8 + k) - (int)YT(-1, 6 - k)); }
+			a = 16 * ((int)YT(-1, 15) + (int)YT(15, -1)); b = (5 * H + 32) >> 6; c = (5 * V + 32) >> 6;
+		} else if (mode == 2) {
+			int st = 0, sl = 0;
+#pragma unroll
+			for (int k = 0; k < 16; k++) { st += YT(k, -1); sl += YT(-1, k); }
+			dc = (hasA && hasB) ? (st + sl + 16) >> 5 : hasA ? (sl + 8) >> 4 : hasB ? (st + 8) >> 4 : 128;
+		}
+		int vals[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			int p = lane + 32 * k, x = p & 15, y = p >> 4;
+			int v = mode == 0 ? (hasB ? (int)YT(x, -1) : 128) : mode == 1 ? (hasA ? (int)YT(-1, y) : 128) : mode == 2 ? dc : clip255((a + b * (x - 7) + c * (y - 7) + 16) >> 5);
+			vals[k] = clip255((short)(v + ws->res[p]));
+		}
+		__syncwarp();
+#pragma unroll
+		for (int k = 0; k < 8; k++) { int p = lane + 32 * k; YT(p & 15, p >> 4) = (uint8_t)vals[k]; }
+		__syncwarp();
+	}
+}
+
+__device__ void intra_chroma(WarpSmem *ws, const E264MbRec *r, int lane) {
+	int mode = r->chroma_mode & 15, un = r->chroma_mode >> 4;
+	bool hasA = !(un & 1), hasB = !(un & 2);
+	int vals[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		int p = lane + 32 * k, pl = p >> 6, x = p & 7, y = (p >> 3) & 7, v;
+#define TC(i) (hasB ? (int)CT(pl, i, -1) : 128)
+#define LC(i) (hasA ? (int)CT(pl, -1, i) : 128)
+		if (mode == 0) {
+			int bx = x >> 2, by = y >> 2, st = 0, sl = 0;
+#pragma unroll
+			for (int q = 0; q < 4; q++) { st += TC(bx * 4 + q); sl += LC(by * 4 + q); }
+			if (bx == by) v = (hasA && hasB) ? (st + sl + 4) >> 3 : hasA ? (sl + 2) >> 2 : hasB ? (st + 2) >> 2 : 128;
+			else if (bx == 1) v = hasB ? (st + 2) >> 2 : hasA ? (sl + 2) >> 2 : 128;
+			else v = hasA ? (sl + 2) >> 2 : hasB ? (st + 2) >> 2 : 128;
+		} else if (mode == 1) v = LC(y);
+		else if (mode == 2) v = TC(x);
+		else {
+			int H = 0, V = 0, corner = CT(pl, -1, -1);
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				H += (q + 1) * ((int)CT(pl, 4 + q, -1) - (q == 3 ? corner : (int)CT(pl, 2 - q, -1)));
+				V += (q + 1) * ((int)CT(pl, -1, 4 + q) - (q == 3 ? corner : (int)CT(pl, -1, 2 - q)));
+			}
+			int a = 16 * ((int)CT(pl, -1, 7) + (int)CT(pl, 7, -1)), b = (34 * H + 32) >> 6, c = (34 * V + 32) >> 6;
+			v = clip255((a + b * (x - 3) + c * (y - 3) + 16) >> 5);
+		}
+#undef TC
+#undef LC
+		vals[k] = clip255((short)(v + ws->res[256 + pl * 64 + y * 8 + x]));
+	}
+	__syncwarp();
+#pragma unroll
+	for (int k = 0; k < 4; k++) { int p = lane + 32 * k; CT(p >> 6, p & 7, (p >> 3) & 7) = (uint8_t)vals[k]; }
+	__syncwarp();
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* inter prediction                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+__device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
+
+/* luma sample at window position (x,y) (window origin = integer position - 2), fraction (fx,fy) — 8.4.2.2.1 */
+__device__ __forceinline__ int mc_luma_sample(const uint8_t *w, int x, int y, int fx, int fy) {
+#define P(dx, dy) ((int)w[(y + 2 + (dy)) * WIN_STRIDE + x + 2 + (dx)])
+#define B1(dx, dy) tap6(P((dx) - 2, dy), P((dx) - 1, dy), P(dx, dy), P((dx) + 1, dy), P((dx) + 2, dy), P((dx) + 3, dy))
+#define H1(dx, dy) tap6(P(dx, (dy) - 2), P(dx, (dy) - 1), P(dx, dy), P(dx, (dy) + 1), P(dx, (dy) + 2), P(dx, (dy) + 3))
+	int G = P(0, 0);
+	if (!fx && !fy) return G;
+	if (!fy) { int b = clip255((B1(0, 0) + 16) >> 5); return fx == 2 ? b : (((fx == 1 ? G : P(1, 0)) + b + 1) >> 1); }
+	if (!fx) { int h = clip255((H1(0, 0) + 16) >> 5); return fy == 2 ? h : (((fy == 1 ? G : P(0, 1)) + h + 1) >> 1); }
+	if (fx == 2 || fy == 2) {
+		int j = clip255((tap6(B1(0, -2), B1(0, -1), B1(0, 0), B1(0, 1), B1(0, 2), B1(0, 3)) + 512) >> 10);
+		if (fx == 2 && fy == 2) return j;
+		if (fx == 2) { int bs = clip255((B1(0, fy == 1 ? 0 : 1) + 16) >> 5); return (bs + j + 1) >> 1; }
+		int hm = clip255((H1(fx == 1 ? 0 : 1, 0) + 16) >> 5); return (hm + j + 1) >> 1;
+	}
+	int bs = clip255((B1(0, fy == 1 ? 0 : 1) + 16) >> 5), hm = clip255((H1(fx == 1 ? 0 : 1, 0) + 16) >> 5);
+	return (bs + hm + 1) >> 1;
+#undef P
+#undef B1
+#undef H1
+}
+
+__device__ __forceinline__ int wp_uni(int p, int w, int o, int logwd) { return clip255((logwd >= 1 ? ((p * w + (1 << (logwd - 1))) >> logwd) : p * w) + o); }
+__device__ __forceinline__ int wp_bi(int p0, int p1, int w0, int w1, int o0, int o1, int logwd) { return clip255(((p0 * w0 + p1 * w1 + (1 << logwd)) >> (logwd + 1)) + ((o0 + o1 + 1) >> 1)); }
+
+/* combine the prediction `p` of list `l` for a sample of 8x8 block i8 / plane pl with what the tile holds (list 0 pass) */
+__device__ __forceinline__ int weight_sample(const E264MbRec *r, const E264SliceRec *sr, int l, int i8, int pl, int p, int q) {
+	int r0 = r->ref_idx[0][i8], r1 = r->ref_idx[1][i8];
+	int mode = sr->wp_mode, logwd = pl ? sr->chroma_log2_wd : sr->luma_log2_wd;
+	if (l == 1 && r0 >= 0) {   /* second pass of a bi-predicted block: q = list-0 prediction */
+		if (mode == WP_EXPLICIT) return wp_bi(q, p, sr->wp_w[0][r0 & 15][pl], sr->wp_w[1][r1 & 15][pl], sr->wp_o[0][r0 & 15][pl], sr->wp_o[1][r1 & 15][pl], logwd);
+		if (mode == WP_IMPLICIT) { int w1 = sr->implicit_w1[r0 & 15][r1 & 15]; return wp_bi(q, p, 64 - w1, w1, 0, 0, 5); }
+		return (q + p + 1) >> 1;
+	}
+	if (l == 0 && r1 >= 0) return p;   /* first pass of a bi-predicted block: stored unweighted */
+	if (mode == WP_EXPLICIT) { int ri = (l ? r1 : r0) & 15; return wp_uni(p, sr->wp_w[l][ri][pl], sr->wp_o[l][ri][pl], logwd); }
+	return p;
+}
+
+/* motion-compensate the rectangle (x0,y0,w,h) (luma units, inside the MB) of list l */
+__device__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int l, int x0, int y0, int w, int h, int lane) {
+	int z0 = blk_z(x0 >> 2, y0 >> 2);
+	int mvx = r->mv[l][z0][0], mvy = r->mv[l][z0][1];
+	int slot = r->ref_pic[l][z0 >> 2];
+	if (slot < 0 || slot >= J.n_slots) slot = J.dst_slot;
+	const uint8_t *ref = J.frames + (size_t)slot * J.frame_bytes;
+	const int W = J.w_mbs * 16, H = J.h_mbs * 16;
+	uint8_t *win = ws->u.win;
+	/* luma window */
+	{
+		int X0 = mbx * 16 + x0 + (mvx >> 2) - 2, Y0 = mby * 16 + y0 + (mvy >> 2) - 2;
+		int ww = w + 5, hh = h + 5;
+		for (int row = 0; row < hh; row++) {
+			if (lane < ww) {
+				int xx = min(max(X0 + lane, 0), W - 1), yy = min(max(Y0 + row, 0), H - 1);
+				win[row * WIN_STRIDE + lane] = __ldg(ref + (size_t)yy * J.stride_y + xx);
+			}
+		}
+	}
+	/* chroma windows */
+	int cw = w >> 1, ch = h >> 1;
+	{
+		int X0 = mbx * 8 + (x0 >> 1) + (mvx >> 3), Y0 = mby * 8 + (y0 >> 1) + (mvy >> 3);
+		int ww = cw + 1, hh = ch + 1;
+		for (int row = 0; row < hh; row++) {
+			int pl = lane >> 4, c = lane & 15;
+			if (c < ww) {
+				int xx = min(max(X0 + c, 0), (W >> 1) - 1), yy = min(max(Y0 + row, 0), (H >> 1) - 1);
+				win[21 * WIN_STRIDE + pl * 108 + row * 12 + c] = __ldg(ref + J.plane_y + pl * (J.stride_c >> 1) + (size_t)yy * J.stride_c + xx);
+			}
+		}
+	}
+	__syncwarp();
+	int fx = mvx & 3, fy = mvy & 3;
+	for (int p = lane; p < w * h; p += 32) {
+		int x = p % w, y = p / w;
+		int v = mc_luma_sample(win, x, y, fx, fy);
+		int X = x0 + x, Y = y0 + y, i8 = (Y >> 3) * 2 + (X >> 3);
+		YT(X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 0, v, YT(X, Y));
+	}
+	int cfx = mvx & 7, cfy = mvy & 7;
+	for (int p = lane; p < 2 * cw * ch; p += 32) {
+		int pl = p / (cw * ch), q = p - pl * cw * ch, x = q % cw, y = q / cw;
+		const uint8_t *cwn = win + 21 * WIN_STRIDE + pl * 108;
+		int A = cwn[y * 12 + x], B = cwn[y * 12 + x + 1], C = cwn[(y + 1) * 12 + x], D = cwn[(y + 1) * 12 + x + 1];
+		int v = ((8 - cfx) * (8 - cfy) * A + cfx * (8 - cfy) * B + (8 - cfx) * cfy * C + cfx * cfy * D + 32) >> 6;
+		int X = (x0 >> 1) + x, Y = (y0 >> 1) + y, i8 = (Y >> 2) * 2 + (X >> 2);
+		CT(pl, X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 1 + pl, v, CT(pl, X, Y));
+	}
+	__syncwarp();
+}
+
+__device__ void inter_predict(WarpSmem *ws, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int lane) {
+	for (int l = 0; l < 2; l++) {
+		/* is the whole macroblock one 16x16 partition for this list? */
+		int z = lane & 15;
+		bool same = r->mv[l][z][0] == r->mv[l][0][0] && r->mv[l][z][1] == r->mv[l][0][1] && r->ref_idx[l][z >> 2] == r->ref_idx[l][0] && r->ref_idx[l ^ 1][z >> 2] == r->ref_idx[l ^ 1][0];
+		if (__all_sync(0xffffffffu, same)) {
+			if (r->ref_idx[l][0] >= 0) mc_rect(ws, J, r, sr, mbx, mby, l, 0, 0, 16, 16, lane);
+			continue;
+		}
+		for (int i8 = 0; i8 < 4; i8++) {
+			if (r->ref_idx[l][i8] < 0) continue;
+			int zb = i8 * 4, x0 = (i8 & 1) * 8, y0 = (i8 >> 1) * 8;
+			bool s8 = true;
+			for (int k = 1; k < 4; k++) s8 = s8 && r->mv[l][zb + k][0] == r->mv[l][zb][0] && r->mv[l][zb + k][1] == r->mv[l][zb][1];
+			if (s8) mc_rect(ws, J, r, sr, mbx, mby, l, x0, y0, 8, 8, lane);
+			else for (int k = 0; k < 4; k++) mc_rect(ws, J, r, sr, mbx, mby, l, x0 + (k & 1) * 4, y0 + (k >> 1) * 4, 4, 4, lane);
+		}
+	}
+	/* add the residual */
+#pragma unroll
+	for (int k = 0; k < 8; k++) { int p = lane + 32 * k, x = p & 15, y = p >> 4; YT(x, y) = (uint8_t)clip255((short)((int)YT(x, y) + ws->res[p])); }
+#pragma unroll
+	for (int k = 0; k < 4; k++) { int p = lane + 32 * k, pl = p >> 6, x = p & 7, y = (p >> 3) & 7; CT(pl, x, y) = (uint8_t)clip255((short)((int)CT(pl, x, y) + ws->res[256 + p])); }
+	__syncwarp();
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* reconstruction kernel                                                                        */
+/* ------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_recon_kernel(PicJob J) {
+	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
+	const int lane = threadIdx.x & 31;
+	WarpSmem *ws = &smem[threadIdx.x >> 5];
+	const int nmb = J.w_mbs * J.h_mbs;
+	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
+	for (;;) {
+		unsigned t = 0;
+		if (lane == 0) t = atomicAdd(J.tickets, 1u);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t >= (unsigned)nmb) break;
+		const int mb = (int)t, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
+		if (lane < 12) ws->rec4[lane] = __ldg((const uint4 *)(J.recs + mb) + lane);
+		__syncwarp();
+		const E264MbRec *r = (const E264MbRec *)ws->rec4;
+		const E264SliceRec *sr = J.slices + r->slice_idx;
+		uint8_t *Y = dst + (size_t)(mby * 16) * J.stride_y + mbx * 16;
+		uint8_t *C = dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8;
+		const int kind = r->kind;
+		if (kind == MBK_IPCM) {
+			const uint8_t *s = (const uint8_t *)(J.coefs + r->coef_off);
+			if (lane < 16) *(uint4 *)(Y + (size_t)lane * J.stride_y) = __ldg((const uint4 *)s + lane);
+			else { int j = lane - 16, pl = j >> 3, row = j & 7; *(uint2 *)(C + pl * (J.stride_c >> 1) + (size_t)row * J.stride_c) = __ldg((const uint2 *)(s + 256) + j); }
+		} else {
+			residual_stage(ws, r, sr, J.coefs, lane);
+			if (kind != MBK_INTER) {
+				/* wait for the neighbours, then fetch the samples around the macroblock (L2, bypassing L1) */
+				bool ok = true;
+				if (lane == 0) {   /* A, D, B, C: inter neighbours finish without waiting, so each one is checked */
+					if (mbx > 0) ok = wait_flag(J.flags, mb - 1, J.epoch, J.err);
+					if (ok && mby > 0) {
+						if (mbx > 0) ok = wait_flag(J.flags, mb - J.w_mbs - 1, J.epoch, J.err);
+						if (ok) ok = wait_flag(J.flags, mb - J.w_mbs, J.epoch, J.err);
+						if (ok && mbx < J.w_mbs - 1) ok = wait_flag(J.flags, mb - J.w_mbs + 1, J.epoch, J.err);
+					}
+					__threadfence();
+				}
+				__syncwarp();
+				const bool up = mby > 0, left = mbx > 0;
+				if (up) {
+					int x = lane - 1;   /* -1..30 -> need -1..23 */
+					if (x < 24 && (x >= 0 || left) && (x < 16 || mbx < J.w_mbs - 1)) YT(x, -1) = __ldcg(Y - J.stride_y + x);
+					if (lane < 18) { int pl = lane / 9, cx = lane % 9 - 1; if (cx >= 0 || left) CT(pl, cx, -1) = __ldcg(C + pl * (J.stride_c >> 1) - J.stride_c + cx); }
+				}
+				if (left) {
+					if (lane < 16) YT(-1, lane) = __ldcg(Y + (size_t)lane * J.stride_y - 1);
+					else { int j = lane - 16, pl = j >> 3, row = j & 7; CT(pl, -1, row) = __ldcg(C + pl * (J.stride_c >> 1) + (size_t)row * J.stride_c - 1); }
+				}
+				__syncwarp();
+				intra_luma(ws, r, lane);
+				intra_chroma(ws, r, lane);
+			} else {
+				inter_predict(ws, J, r, sr, mbx, mby, lane);
+			}
+			/* 128-bit row stores of the reconstructed macroblock */
+			if (lane < 16) *(uint4 *)(Y + (size_t)lane * J.stride_y) = *(const uint4 *)&YT(0, lane);
+			else { int j = lane - 16, pl = j >> 3, row = j & 7; *(uint2 *)(C + pl * (J.stride_c >> 1) + (size_t)row * J.stride_c) = *(const uint2 *)&CT(pl, 0, row); }
+		}
+		__syncwarp();
+		if (lane == 0) { __threadfence(); *(volatile unsigned *)(J.flags + mb) = J.epoch; }
+	}
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* deblocking kernel                                                                            */
+/* ------------------------------------------------------------------------------------------ */
+struct __align__(16) DbSmem {
+	uint8_t ypix[20 * 32];        /* rows -4..15, cols -4..15 at [ (r+4)*32 + 12 + (c+4) ] -> sample (0,r) at 16-byte aligned offset 16 */
+	uint8_t cpix[2][10 * 16];     /* rows -2..7, cols -2..7 at [(r+2)*16 + 6 + (c+2)] -> sample (0,r) at offset 8 */
+	int8_t bs[32];             /* [dir][edge][segment] */
+	uint8_t alpha[3][3], beta[3][3];   /* [plane][0 internal, 1 left edge, 2 top edge] */
+	uint8_t ia[3][3];
+};
+#define DY(x, y) ds->ypix[((y) + 4) * 32 + 16 + (x)]
+#define DC_(pl, x, y) ds->cpix[pl][((y) + 2) * 16 + 8 + (x)]
+
+__device__ __forceinline__ int iabs_(int v) { return v < 0 ? -v : v; }
+
+__device__ int bs_pair(const E264MbRec *p, int bp, const E264MbRec *q, int bq, bool mb_edge) {
+	if (p->kind != MBK_INTER || q->kind != MBK_INTER) return mb_edge ? 4 : 3;
+	if (((p->coded >> bp) & 1) || ((q->coded >> bq) & 1)) return 2;
+	int p0 = p->ref_idx[0][bp >> 2] < 0 ? -1 : p->ref_pic[0][bp >> 2], p1 = p->ref_idx[1][bp >> 2] < 0 ? -1 : p->ref_pic[1][bp >> 2];
+	int q0 = q->ref_idx[0][bq >> 2] < 0 ? -1 : q->ref_pic[0][bq >> 2], q1 = q->ref_idx[1][bq >> 2] < 0 ? -1 : q->ref_pic[1][bq >> 2];
+	if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) return 1;
+#define FAR(lp, lq) (iabs_(p->mv[lp][bp][0] - q->mv[lq][bq][0]) >= 4 || iabs_(p->mv[lp][bp][1] - q->mv[lq][bq][1]) >= 4)
+	if (p0 >= 0 && p1 >= 0) {
+		if (p0 != p1) return (p0 == q0) ? (FAR(0, 0) || FAR(1, 1)) : (FAR(0, 1) || FAR(1, 0));
+		return (FAR(0, 0) || FAR(1, 1)) && (FAR(0, 1) || FAR(1, 0));
+	}
+	int lp = p0 >= 0 ? 0 : 1, lq = q0 >= 0 ? 0 : 1;
+	return FAR(lp, lq);
+#undef FAR
+}
+
+__device__ __forceinline__ void filter_luma(uint8_t *pix, int step, int bs, int alpha, int beta, int tc0) {
+	int p0 = pix[-step], p1 = pix[-2 * step], p2 = pix[-3 * step], q0 = pix[0], q1 = pix[step], q2 = pix[2 * step];
+	if (!(iabs_(p0 - q0) < alpha && iabs_(p1 - p0) < beta && iabs_(q1 - q0) < beta)) return;
+	int ap = iabs_(p2 - p0), aq = iabs_(q2 - q0);
+	if (bs < 4) {
+		int tc = tc0 + (ap < beta) + (aq < beta);
+		int d = min(max((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc), tc);
+		pix[-step] = (uint8_t)clip255(p0 + d); pix[0] = (uint8_t)clip255(q0 - d);
+		if (ap < beta) pix[-2 * step] = (uint8_t)(p1 + min(max((p2 + ((p0 + q0 + 1) >> 1) - (p1 << 1)) >> 1, -tc0), tc0));
+		if (aq < beta) pix[step] = (uint8_t)(q1 + min(max((q2 + ((p0 + q0 + 1) >> 1) - (q1 << 1)) >> 1, -tc0), tc0));
+	} else {
+		bool small = iabs_(p0 - q0) < ((alpha >> 2) + 2);
+		if (ap < beta && small) {
+			int p3 = pix[-4 * step];
+			pix[-step] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+			pix[-2 * step] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
+			pix[-3 * step] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+		} else pix[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+		if (aq < beta && small) {
+			int q3 = pix[3 * step];
+			pix[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+			pix[step] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
+			pix[2 * step] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
+		} else pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+	}
+}
+__device__ __forceinline__ void filter_chroma(uint8_t *pix, int step, int bs, int alpha, int beta, int tc0) {
+	int p0 = pix[-step], p1 = pix[-2 * step], q0 = pix[0], q1 = pix[step];
+	if (!(iabs_(p0 - q0) < alpha && iabs_(p1 - p0) < beta && iabs_(q1 - q0) < beta)) return;
+	if (bs < 4) {
+		int tc = tc0 + 1;
+		int d = min(max((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc), tc);
+		pix[-step] = (uint8_t)clip255(p0 + d); pix[0] = (uint8_t)clip255(q0 - d);
+	} else { pix[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2); pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2); }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_deblock_kernel(PicJob J) {
+	__shared__ DbSmem smem[WARPS_PER_BLOCK];
+	const int lane = threadIdx.x & 31;
+	DbSmem *ds = &smem[threadIdx.x >> 5];
+	const int nmb = J.w_mbs * J.h_mbs;
+	unsigned *flags = J.flags + nmb;
+	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
+	for (;;) {
+		unsigned t = 0;
+		if (lane == 0) t = atomicAdd(J.tickets + 1, 1u);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t >= (unsigned)nmb) break;
+		const int mb = (int)t, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
+		const E264MbRec *q = J.recs + mb;
+		const int qflags = q->flags;
+		if (qflags & MBF_DEBLOCK) {
+			const E264SliceRec *sr = J.slices + q->slice_idx;
+			const bool fl = qflags & MBF_EDGE_L, ft = qflags & MBF_EDGE_T, t8 = qflags & MBF_T8x8;
+			/* boundary strengths: lane = dir*16 + edge*4 + segment */
+			{
+				int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3, bs = 0;
+				const E264MbRec *p = q;
+				bool on = true;
+				if (e == 0) { on = dir ? ft : fl; p = dir ? q - J.w_mbs : q - 1; }
+				if (on) {
+					int qx = dir ? k : e, qy = dir ? e : k;
+					int px_ = dir ? k : (e ? e - 1 : 3), py_ = dir ? (e ? e - 1 : 3) : k;
+					bs = bs_pair(p, blk_z(px_, py_), q, blk_z(qx, qy), e == 0);
+				}
+				ds->bs[lane] = (int8_t)bs;
+			}
+			if (lane < 9) {
+				int pl = lane / 3, kind = lane % 3;
+				const E264MbRec *p = kind == 0 ? q : kind == 1 ? q - 1 : q - J.w_mbs;
+				if ((kind == 1 && !fl) || (kind == 2 && !ft)) p = q;
+				int qpav = (p->qp[pl] + q->qp[pl] + 1) >> 1;
+				int ia = min(max(qpav + sr->filter_offset_a, 0), 51), ib = min(max(qpav + sr->filter_offset_b, 0), 51);
+				ds->alpha[pl][kind] = h264_alpha[ia]; ds->beta[pl][kind] = h264_beta[ib]; ds->ia[pl][kind] = (uint8_t)ia;
+			}
+			/* dependencies: left neighbour and top-right (or top) neighbour fully deblocked */
+			bool ok = true;
+			if (lane == 0) {
+				if (mbx > 0) ok = wait_flag(flags, mb - 1, J.epoch, J.err);
+				if (ok && mby > 0) ok = wait_flag(flags, mb - J.w_mbs, J.epoch, J.err);
+				if (ok && mby > 0 && mbx < J.w_mbs - 1) ok = wait_flag(flags, mb - J.w_mbs + 1, J.epoch, J.err);
+				__threadfence();
+			}
+			__syncwarp();
+			uint8_t *Y = dst + (size_t)(mby * 16) * J.stride_y + mbx * 16;
+			uint8_t *C = dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8;
+			/* load 20x20 luma (+ 2 x 10x10 chroma) around the macroblock */
+			for (int i = lane; i < 20 * 5; i += 32) {
+				int row = i / 5 - 4, seg = i % 5 - 1;   /* 4-byte segments: -1 (cols -4..-1), 0..3 */
+				if ((row >= 0 || mby > 0) && (seg >= 0 || mbx > 0))
+					*(uint32_t *)&DY(seg * 4, row) = __ldcg((const uint32_t *)(Y + (ptrdiff_t)row * J.stride_y + seg * 4));
+			}
+			for (int i = lane; i < 2 * 10 * 5; i += 32) {
+				int pl = i / 50, j = i % 50, row = j / 5 - 2, seg = j % 5 - 1;   /* 2-byte segments: -1 (cols -2,-1), 0..3 */
+				if ((row >= 0 || mby > 0) && (seg >= 0 || mbx > 0))
+					*(uint16_t *)&DC_(pl, seg * 2, row) = __ldcg((const uint16_t *)(C + pl * (J.stride_c >> 1) + (ptrdiff_t)row * J.stride_c + seg * 2));
+			}
+			__syncwarp();
+			for (int dir = 0; dir < 2; dir++) {
+				for (int e = 0; e < 4; e++) {
+					int kind = e ? 0 : 1 + dir;
+					if (lane < 16) {
+						if (!(t8 && (e & 1))) {
+							int b = ds->bs[dir * 16 + e * 4 + (lane >> 2)];
+							if (b) {
+								uint8_t *pix = dir ? &DY(lane, e * 4) : &DY(e * 4, lane);
+								filter_luma(pix, dir ? 32 : 1, b, ds->alpha[0][kind], ds->beta[0][kind], b < 4 ? h264_tc0[ds->ia[0][kind]][b - 1] : 0);
+							}
+						}
+					} else if (!(e & 1)) {
+						int j = lane - 16, pl = j >> 3, k = j & 7;
+						int b = ds->bs[dir * 16 + e * 4 + (k >> 1)];
+						if (b) {
+							uint8_t *pix = dir ? &DC_(pl, k, e * 2) : &DC_(pl, e * 2, k);
+							filter_chroma(pix, dir ? 16 : 1, b, ds->alpha[1 + pl][kind], ds->beta[1 + pl][kind], b < 4 ? h264_tc0[ds->ia[1 + pl][kind]][b - 1] : 0);
+						}
+					}
+					__syncwarp();
+				}
+			}
+			/* write back: the macroblock, 3 columns of the left neighbour, 3 rows of the top neighbour (1 for chroma) */
+			if (lane < 16) *(uint4 *)(Y + (size_t)lane * J.stride_y) = *(const uint4 *)&DY(0, lane);
+			else { int j = lane - 16, pl = j >> 3, row = j & 7; *(uint2 *)(C + pl * (J.stride_c >> 1) + (size_t)row * J.stride_c) = *(const uint2 *)&DC_(pl, 0, row); }
+			if (fl) {
+				if (lane < 16) { uint8_t *d = Y + (size_t)lane * J.stride_y; d[-3] = DY(-3, lane); d[-2] = DY(-2, lane); d[-1] = DY(-1, lane); }
+				else { int j = lane - 16, pl = j >> 3, row = j & 7; C[pl * (J.stride_c >> 1) + (size_t)row * J.stride_c - 1] = DC_(pl, -1, row); }
+			}
+			if (ft) {
+				if (lane < 3) *(uint4 *)(Y - (size_t)(lane + 1) * J.stride_y) = *(const uint4 *)&DY(0, -1 - lane);
+				else if (lane < 5) { int pl = lane - 3; *(uint2 *)(C + pl * (J.stride_c >> 1) - J.stride_c) = *(const uint2 *)&DC_(pl, 0, -1); }
+			}
+		}
+		__syncwarp();
+		if (lane == 0) { __threadfence(); *(volatile unsigned *)(flags + mb) = J.epoch; }
+	}
+}
