@@ -6,7 +6,7 @@ NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xco
 CFLAGS := -std=gnu11 -O3 -fPIC -Wall -Wno-unused-function -Wno-unused-variable -Wno-unused-but-set-variable
 LIB := edge264_b200/libedge264_b200.so
 
-all: $(LIB) tools/gen264 tools/b200_decode oracle
+all: $(LIB) tools/gen264 tools/b200_decode tools/libe264bench.so oracle
 
 $(CSRC)/recon.o: $(CSRC)/recon.cu $(CSRC)/recon_kernels.cuh $(wildcard $(CSRC)/*.h) include/e264b_recon.h
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(CSRC)/recon.ptxas.log || (cat $(CSRC)/recon.ptxas.log; false)
@@ -20,8 +20,10 @@ tools/gen264: tools/gen264.c $(wildcard $(CSRC)/*.h)
 	$(CC) $(CFLAGS) -O2 -o $@ $<
 tools/b200_decode: tools/e264_decode.c $(LIB)
 	$(CC) -O2 -std=gnu11 -Iinclude $< -o $@ -Wl,-rpath,'$$ORIGIN/../edge264_b200' -Ledge264_b200 -ledge264_b200
+tools/libe264bench.so: tools/e264_bench.c $(LIB)
+	$(CC) -O2 -std=gnu11 -fPIC -shared -Iinclude $< -o $@ -Wl,-rpath,'$$ORIGIN/../edge264_b200' -Ledge264_b200 -ledge264_b200 -pthread
 oracle:
 	$(MAKE) -C oracle all
 clean:
-	rm -f $(CSRC)/*.o $(LIB) tools/gen264 tools/b200_decode
+	rm -f $(CSRC)/*.o $(LIB) tools/gen264 tools/b200_decode tools/libe264bench.so
 .PHONY: all oracle clean

@@ -148,6 +148,7 @@ struct Edge264Decoder {
 	int prev_ref_frame_num, prev_poc_msb, prev_poc_lsb, prev_frame_num_offset, prev_frame_num, prev_has_mmco5;
 	int last_idr_pic_id, last_poc_lsb, last_delta_poc0;
 	int frame_num_offset;
+	int q_prev_ref_frame_num, q_cur_frame_num;   /* reference-style absolute frame numbers, only used to number FrameIds like it */
 	int32_t next_uid;
 	int mmco5_seen;
 	SliceHeader sh;                    /* header of the slice being parsed */

@@ -358,6 +358,8 @@ static void apply_marking(Edge264Decoder *d) {
 	}
 	cur->ref = cur_long ? 2 : 1;
 	d->prev_ref_frame_num = cur->frame_num;
+	d->q_prev_ref_frame_num = d->q_cur_frame_num;
+	for (int k = 0; k < h->n_mmco; k++) if (h->mmco[k].op == 5) d->q_prev_ref_frame_num = 0;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -397,6 +399,7 @@ static int configure_sequence(Edge264Decoder *d, const SPS *s) {
 	o->frame_crop_offsets[0] = (int16_t)s->crop[2]; o->frame_crop_offsets[1] = (int16_t)s->crop[1];
 	o->frame_crop_offsets[2] = (int16_t)s->crop[3]; o->frame_crop_offsets[3] = (int16_t)s->crop[0];
 	d->configured = 1;
+	d->q_prev_ref_frame_num = -1;
 	d->prev_ref_frame_num = -1; d->prev_poc_msb = d->prev_poc_lsb = 0;
 	return 0;
 }
@@ -616,6 +619,19 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 		}
 		Pic *cp = &d->pics[slot];
 		memset(cp, 0, sizeof(*cp));
+		{   /* FrameId numbering: the reference keeps an absolute FrameNum across IDRs, so an IDR after other
+		     * pictures looks like a frame_num gap and non-existing frames take FrameIds (headers.c:1059,1095-1139) */
+			int q = d->q_prev_ref_frame_num;
+			int qfn = q + 1 + (((idr ? 0 : h->frame_num) - q - 1) & mask);
+			int gap = qfn - q;
+			if (gap > 1) {
+				int nlong = 0;
+				for (int i = 0; i < d->n_slots; i++) if (d->pics[i].in_use && d->pics[i].ref == 2) nlong++;
+				int room = s->max_num_ref_frames - nlong;
+				d->next_uid += (gap - 1 < room ? gap - 1 : room) > 0 ? (gap - 1 < room ? gap - 1 : room) : 0;
+			}
+			d->q_cur_frame_num = qfn;
+		}
 		cp->in_use = 1; cp->frame_num = frame_num_abs; cp->poc = poc; cp->poc_top = poc_top; cp->uid = d->next_uid++; cp->host_buf = hbuf;
 		d->hb[hbuf].state = 1; d->hb[hbuf].frame_id = cp->uid; d->hb[hbuf].borrowed = 0; d->hb[hbuf].submitted = 0;
 		d->cur = slot; d->cur_idr = idr; d->cur_nal_ref_idc = nal_ref_idc;
@@ -733,7 +749,7 @@ Edge264Decoder *edge264_alloc(int n_threads, Edge264LogCb log_cb, void *log_arg,
 	if (!d) return NULL;
 	d->alloc_cb = (alloc_cb && free_cb) ? alloc_cb : NULL; d->free_cb = free_cb; d->alloc_arg = alloc_arg;
 	d->log_cb = log_cb; d->log_arg = log_arg;
-	d->cur = -1; d->pending_release = -1; d->prev_ref_frame_num = -1;
+	d->cur = -1; d->pending_release = -1; d->prev_ref_frame_num = -1; d->q_prev_ref_frame_num = -1;
 	d->be = e264_default_backend();
 	if (!d->be || d->be->create(&d->be_ctx)) { free(d); return NULL; }
 	return d;
@@ -745,7 +761,7 @@ void edge264_flush(Edge264Decoder *d) {
 	for (int i = 0; i < E264_MAX_SLOTS; i++) { d->pics[i].in_use = 0; d->pics[i].host_buf = -1; }
 	for (int i = 0; i < E264_MAX_HOSTBUFS; i++) if (d->hb[i].state != 3 || !d->hb[i].borrowed) d->hb[i].state = 0;
 	d->outq_n = 0; d->cur = -1; d->pending_release = -1;
-	d->prev_ref_frame_num = -1; d->prev_poc_msb = d->prev_poc_lsb = 0;
+	d->prev_ref_frame_num = -1; d->q_prev_ref_frame_num = -1; d->prev_poc_msb = d->prev_poc_lsb = 0;
 	memset(&d->sps, 0, sizeof(d->sps)); memset(d->pps, 0, sizeof(d->pps));
 	d->configured = 0;
 }
@@ -787,6 +803,7 @@ int edge264_decode_NAL(Edge264Decoder *d, const uint8_t *buf, const uint8_t *end
 				if (d->configured && bump_all(d)) return ENOBUFS;   /* frame format change: drain first (headers.c:2005-2007) */
 				ret = configure_sequence(d, &s);
 				if (ret) return ret;
+				memset(d->pps, 0, sizeof(d->pps));   /* a format change clears the decoder, PPSs included (reference clear_decoder, headers.c:133-141) */
 			}
 			d->sps = s;
 		}

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <mutex>
 #include "recon_kernels.cuh"
 extern "C" {
 #include "dec.h"
@@ -41,7 +42,13 @@ struct E264bDevice {
 	bool keep; std::vector<KeptPic> kept;
 	uint64_t launches, h2d_bytes, d2h_bytes;
 	int sm_count;
+	std::vector<std::pair<void *, size_t>> host_free_list;   /* pinned buffers returned by the decoder, reused by the next one */
 };
+
+/* Device contexts are pooled per process: creating pinned staging and the frame pool costs tens of
+ * milliseconds, a decoder for the next clip of the same geometry reuses everything. */
+static std::mutex g_pool_mu;
+static std::vector<E264bDevice *> g_pool;
 
 static void free_geometry(E264bDevice *c) {
 	cudaStreamSynchronize(c->stream);
@@ -70,8 +77,19 @@ extern "C" int e264b_create(E264bDevice **out) {
 	int dev = e ? atoi(e) : 0;
 	if (dev < 0 || dev >= n) dev = 0;
 	CK(cudaSetDevice(dev));
+	{
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		for (size_t i = 0; i < g_pool.size(); i++) if (g_pool[i]->dev == dev) {
+			E264bDevice *c = g_pool[i]; g_pool.erase(g_pool.begin() + i);
+			const char *k = getenv("E264B_KEEP"); c->keep = k && atoi(k) != 0;
+			c->launches = c->h2d_bytes = c->d2h_bytes = 0;
+			*out = c; return 0;
+		}
+	}
 	E264bDevice *c = new E264bDevice();
-	memset((void *)c, 0, offsetof(E264bDevice, kept));
+	c->dev = 0; c->stream = 0; memset(&c->g, 0, sizeof(c->g)); c->n_slots = 0; c->nmb = 0; c->coef_cap = 0; c->d_frames = NULL;
+	memset(c->h_recs, 0, sizeof(c->h_recs)); memset(c->rec_busy, 0, sizeof(c->rec_busy)); memset(c->st, 0, sizeof(c->st)); c->stage = 0; c->d_sync = NULL; c->epoch = 0; c->tick_seq = 0;
+	c->launches = c->h2d_bytes = c->d2h_bytes = 0;
 	c->dev = dev;
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (int i = 0; i < E264_MAX_SLOTS; i++) CK(cudaEventCreateWithFlags(&c->rec_up[i], cudaEventDisableTiming));
@@ -84,10 +102,20 @@ extern "C" int e264b_create(E264bDevice **out) {
 	return 0;
 }
 
+static void drop_kept(E264bDevice *c) { for (auto &k : c->kept) { cudaFree(k.d_recs); cudaFree(k.d_coefs); cudaFree(k.d_slices); } c->kept.clear(); }
+
 extern "C" void e264b_destroy(E264bDevice *c) {
 	if (!c) return;
 	cudaSetDevice(c->dev);
+	cudaStreamSynchronize(c->stream);
+	drop_kept(c);
+	{
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		if (g_pool.size() < 256) { g_pool.push_back(c); return; }
+	}
 	free_geometry(c);
+	for (auto &h : c->host_free_list) cudaFreeHost(h.first);
+	c->host_free_list.clear();
 	for (int i = 0; i < E264_MAX_SLOTS; i++) cudaEventDestroy(c->rec_up[i]);
 	for (int i = 0; i < NSTAGE; i++) cudaEventDestroy(c->st[i].done);
 	for (int i = 0; i < NTICK; i++) cudaEventDestroy(c->tick_ev[i]);
@@ -97,7 +125,18 @@ extern "C" void e264b_destroy(E264bDevice *c) {
 
 extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots) {
 	CK(cudaSetDevice(c->dev));
+	if (c->d_frames && c->n_slots == n_slots && !memcmp(&c->g, g, sizeof(*g))) {   /* pooled context of the same geometry */
+		CK(cudaStreamSynchronize(c->stream));
+		drop_kept(c);
+		CK(cudaMemsetAsync(c->d_sync, 0, (4 + 2 * c->nmb) * sizeof(unsigned), c->stream));
+		for (int i = 0; i < NSTAGE; i++) c->st[i].busy = false;
+		for (int i = 0; i < E264_MAX_SLOTS; i++) c->rec_busy[i] = false;
+		c->epoch = 0; c->stage = 0;
+		return 0;
+	}
 	free_geometry(c);
+	for (auto &h : c->host_free_list) cudaFreeHost(h.first);
+	c->host_free_list.clear();
 	c->g = *g; c->n_slots = n_slots; c->nmb = (size_t)g->width_mbs * g->height_mbs;
 	c->coef_cap = (uint32_t)(c->nmb * 408);
 	size_t pool = (size_t)g->frame_bytes * n_slots;
@@ -122,10 +161,16 @@ extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots
 extern "C" void *e264b_host_alloc(E264bDevice *c, size_t bytes) {
 	void *p = NULL;
 	cudaSetDevice(c->dev);
-	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return NULL;
+	for (size_t i = 0; i < c->host_free_list.size(); i++) if (c->host_free_list[i].second == bytes) { p = c->host_free_list[i].first; c->host_free_list.erase(c->host_free_list.begin() + i); return p; }
+	if (cudaHostAlloc(&p, bytes + 16, cudaHostAllocDefault) != cudaSuccess) return NULL;
+	((size_t *)((uint8_t *)p + bytes))[0] = bytes;   /* size tag behind the buffer for host_free */
 	return p;
 }
-extern "C" void e264b_host_free(E264bDevice *c, void *p) { cudaSetDevice(c->dev); cudaStreamSynchronize(c->stream); cudaFreeHost(p); }
+extern "C" void e264b_host_free(E264bDevice *c, void *p) {
+	/* all decoder mirrors of one geometry have the same size: keep them for the next decoder */
+	size_t bytes = (size_t)c->g.frame_bytes + 64;
+	c->host_free_list.push_back(std::make_pair(p, bytes));
+}
 
 extern "C" int e264b_acquire_staging(E264bDevice *c, int slot, E264MbRec **recs, int16_t **coefs, uint32_t *cap, E264SliceRec **slices) {
 	CK(cudaSetDevice(c->dev));

@@ -1,0 +1,53 @@
+import os, subprocess, sys, hashlib
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+# (name, width_mbs, height_mbs, generator arguments) — small pictures so the CPU checkers finish in seconds
+STREAMS = [
+    ("i_cabac_4x4",      6, 5, "-n 3 -s 1 --gop I --deblock 1 --pcm 0 --t8x8 0"),
+    ("i_cabac_8x8_dbk",  9, 7, "-n 3 -s 7 --gop I --deblock 0 --t8x8 50 --pcm 30"),
+    ("i_cavlc_slices",   9, 7, "-n 3 -s 9 --gop I --deblock 2 --t8x8 50 --slices 4 --cavlc"),
+    ("i_scaling",        9, 7, "-n 3 -s 8 --gop I --deblock 0 --t8x8 60 --scaling 3 --slices 3"),
+    ("p_refs_wp",        9, 7, "-n 8 -s 12 --gop IP --deblock 0 --refs 4 --wp 1"),
+    ("p_cavlc",          9, 7, "-n 8 -s 21 --gop IP --deblock 0 --refs 3 --cavlc"),
+    ("b_default",        9, 7, "-n 10 -s 13 --gop IPB --deblock 0"),
+    ("b_explicit",       9, 7, "-n 10 -s 15 --gop IPB --deblock 0 --wp 1"),
+    ("b_implicit_temporal", 9, 7, "-n 10 -s 16 --gop IPB --deblock 0 --wp 2 --temporal"),
+    ("b_scaling_mv",     9, 7, "-n 10 -s 17 --gop IPB --deblock 0 --scaling 3 --refs 4 --mvrange 60 --slices 2"),
+    ("b_cavlc_all",      11, 6, "-n 10 -s 18 --gop IPB --deblock 0 --wp 2 --temporal --slices 3 --cavlc"),
+    # 1-macroblock-wide pictures: intra only — the reference's edge emulation cannot clamp both sides of one
+    # 16-byte load (edge264_inter.c:1205-1206), so its inter output on 16-pixel-wide pictures is not the standard's
+    ("ragged_1x1_intra", 1, 1, "-n 4 -s 19 --gop I --deblock 0"),
+    ("ragged_1xN_intra", 1, 9, "-n 4 -s 20 --gop I --deblock 0 --cavlc"),
+    ("ragged_2xN",       2, 9, "-n 6 -s 20 --gop IPB --deblock 0 --wp 1"),
+    ("wide_33x2",        33, 2, "-n 6 -s 22 --gop IPB --deblock 0 --wp 2"),
+]
+
+
+@pytest.fixture(scope="session")
+def workdir(tmp_path_factory):
+    return str(tmp_path_factory.mktemp("streams"))
+
+
+def make_stream(workdir, name, w, h, args):
+    path = os.path.join(workdir, name + ".264")
+    if not os.path.exists(path):
+        gen = os.path.join(ROOT, "tools", "gen264")
+        subprocess.run([gen, "-o", path, "-W", str(w), "-H", str(h)] + args.split(), check=True, stderr=subprocess.DEVNULL, timeout=120)
+    return path
+
+
+def md5_frames(frames):
+    return [hashlib.md5(f[3]).hexdigest() for f in frames]
+
+
+def have(backend):
+    from edge264_b200 import _LIBS
+    return os.path.exists(_LIBS[backend])

@@ -1,0 +1,64 @@
+"""GPU parity proper: the sm_100a kernels behind the edge264 C API against the oracle, the compiled
+reference (when oracle/_ref travelled) and the golden digests — bit-exact, every frame."""
+import json, os, subprocess
+import pytest
+from conftest import ROOT, STREAMS, make_stream, md5_frames, have
+from edge264_b200 import decode_bytes
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "streams.json")))
+
+
+@pytest.mark.parametrize("name,w,h,args", STREAMS, ids=[s[0] for s in STREAMS])
+def test_gpu_matches_oracle_and_golden(workdir, name, w, h, args):
+    data = open(make_stream(workdir, name, w, h, args), "rb").read()
+    gpu, codes = decode_bytes(data, "gpu")
+    assert md5_frames(gpu) == GOLD[name]["md5"]
+    port, pcodes = decode_bytes(data, "port")
+    assert md5_frames(gpu) == md5_frames(port) and codes == pcodes
+    assert [f[0] for f in gpu] == [f[0] for f in port]
+
+
+FULL = [
+    ("1080p_intra", 120, 68, "-n 4 -s 31 --gop I --deblock 0 --t8x8 50 --density 40"),
+    ("1080p_ipb", 120, 68, "-n 13 -s 32 --gop IPB --deblock 0 --t8x8 50 --density 52 --wp 2"),
+    ("2160p_scaling", 240, 135, "-n 7 -s 33 --gop IPB --deblock 0 --t8x8 70 --scaling 3 --density 40 --qp 30"),
+]
+
+
+@pytest.mark.parametrize("name,w,h,args", FULL, ids=[s[0] for s in FULL])
+def test_full_size_against_reference(workdir, name, w, h, args):
+    """BASELINE.json sizes: compared with the compiled reference decoder (the oracle port is too slow here)."""
+    if not have("ref"):
+        pytest.skip("oracle/_ref missing")
+    path = make_stream(workdir, name, w, h, args)
+    ref = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_decode"), path, "-q"], capture_output=True, text=True, timeout=600).stdout.strip().splitlines()[-1]
+    gpu = subprocess.run([os.path.join(ROOT, "tools", "b200_decode"), path, "-q"], capture_output=True, text=True, timeout=600).stdout.strip().splitlines()[-1]
+    assert ref == gpu and ref.startswith("frames")
+
+
+def test_replay_reproduces_decode(workdir):
+    """Size-independent property: re-running the kept device records (bench.py's kernel-only path)
+    leaves every frame slot with exactly the pixels the live decode produced."""
+    import ctypes
+    os.environ["E264B_KEEP"] = "1"
+    try:
+        path = make_stream(workdir, "replay", 20, 12, "-n 9 -s 41 --gop IPB --deblock 0 --wp 1")
+        bench = ctypes.CDLL(os.path.join(ROOT, "tools", "libe264bench.so"))
+        core = ctypes.CDLL(os.path.join(ROOT, "edge264_b200", "libedge264_b200.so"))
+        bench.e264bench_run.restype = ctypes.c_double
+        core.e264b_of_decoder.restype = ctypes.c_void_p; core.e264b_of_decoder.argtypes = [ctypes.c_void_p]
+        core.e264b_slot_hash.restype = ctypes.c_uint64; core.e264b_slot_hash.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        data = open(path, "rb").read()
+        bufs = (ctypes.c_char_p * 1)(data); sizes = (ctypes.c_size_t * 1)(len(data))
+        frames = (ctypes.c_long * 1)(); sums = (ctypes.c_uint64 * 1)(); decs = (ctypes.c_void_p * 1)()
+        bench.e264bench_run(bufs, sizes, 1, 1, 1, frames, sums, decs)
+        dev = core.e264b_of_decoder(decs[0])
+        before = [core.e264b_slot_hash(dev, s) for s in range(4)]
+        devs = (ctypes.c_void_p * 1)(dev); ms = ctypes.c_float(); nl = ctypes.c_uint64()
+        assert core.e264b_replay(devs, 1, 2, ctypes.byref(ms), None, ctypes.byref(nl)) == 0
+        assert [core.e264b_slot_hash(dev, s) for s in range(4)] == before
+        assert nl.value == 2 * 2 * frames[0] and core.e264b_error_flag(dev) == 0
+        bench.e264bench_free(decs, 1)
+    finally:
+        os.environ["E264B_KEEP"] = "0"
