@@ -188,6 +188,12 @@ static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, const E264MbRec *r
 	J.frame_bytes = pd->frame_bytes; J.w_mbs = pd->width_mbs; J.h_mbs = pd->height_mbs;
 	J.stride_y = pd->stride_y; J.stride_c = pd->stride_c; J.plane_y = pd->plane_y; J.dst_slot = pd->dst_slot; J.n_slots = c->n_slots;
 	J.tickets = c->d_sync; J.err = c->d_sync + 2; J.flags = c->d_sync + 4;
+	J.rows_mode = pd->n_intra * 2 > pd->width_mbs * pd->height_mbs;   /* intra pictures: wavefront of row warps */
+	if (c->epoch >= (1u << 20)) {   /* row progress counters encode epoch * 2048 + count: restart before it wraps */
+		cudaStreamSynchronize(c->stream);
+		cudaMemsetAsync(c->d_sync, 0, (4 + 2 * c->nmb) * sizeof(unsigned), c->stream);
+		c->epoch = 0;
+	}
 	J.epoch = ++c->epoch;
 	return J;
 }
@@ -197,9 +203,13 @@ static int launch_picture(E264bDevice *c, const PicJob &J, int any_deblock) {
 	int cap = c->sm_count * 8;
 	if (blocks > cap) blocks = cap;
 	CK(cudaMemsetAsync(c->d_sync, 0, 2 * sizeof(unsigned), c->stream));
+	if (J.rows_mode) blocks = (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
 	e264_recon_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
 	c->launches++;
-	if (any_deblock) { e264_deblock_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++; }
+	if (any_deblock) {   /* one warp per macroblock row */
+		int rb = (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+		e264_deblock_kernel<<<rb, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++;
+	}
 	CK(cudaGetLastError());
 	return 0;
 }

@@ -26,6 +26,7 @@ struct PicJob {
 	unsigned epoch;
 	unsigned *tickets;    /* [2] zeroed before the picture */
 	unsigned *err;
+	int rows_mode;
 };
 
 #define WARPS_PER_BLOCK 4
@@ -569,6 +570,72 @@ __device__ void inter_predict(WarpSmem *ws, const PicJob &J, const E264MbRec *r,
 /* ------------------------------------------------------------------------------------------ */
 /* reconstruction kernel                                                                        */
 /* ------------------------------------------------------------------------------------------ */
+/* Reconstruct one macroblock.  rows_mode: the calling warp walks a whole row, so A and D are its own
+ * previous macroblock (samples carried over in shared memory) and only C (or B at the row's end) is waited for. */
+__device__ void recon_mb(WarpSmem *ws, const PicJob &J, uint8_t *dst, int mb, int mbx, int mby, int lane, bool rows_mode) {
+	if (lane < 12) ws->rec4[lane] = __ldg((const uint4 *)(J.recs + mb) + lane);
+	__syncwarp();
+	const E264MbRec *r = (const E264MbRec *)ws->rec4;
+	const E264SliceRec *sr = J.slices + r->slice_idx;
+	uint8_t *Y = dst + (size_t)(mby * 16) * J.stride_y + mbx * 16;
+	uint8_t *C = dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8;
+	const int kind = r->kind, cpl = J.stride_c >> 1;
+	if (kind == MBK_IPCM) {
+		const uint8_t *s = (const uint8_t *)(J.coefs + r->coef_off);
+		if (lane < 16) *(uint4 *)&YT(0, lane) = __ldg((const uint4 *)s + lane);
+		else { int j = lane - 16; *(uint2 *)&CT(j >> 3, 0, j & 7) = __ldg((const uint2 *)(s + 256) + j); }
+		__syncwarp();
+	} else {
+		residual_stage(ws, r, sr, J.coefs, lane);
+		if (kind != MBK_INTER) {
+			bool ok = true;
+			if (lane == 0) {
+				if (!rows_mode) {   /* A, D, B, C: inter neighbours finish without waiting, so each one is checked */
+					if (mbx > 0) ok = wait_flag(J.flags, mb - 1, J.epoch, J.err);
+					if (ok && mby > 0 && mbx > 0) ok = wait_flag(J.flags, mb - J.w_mbs - 1, J.epoch, J.err);
+					if (ok && mby > 0) ok = wait_flag(J.flags, mb - J.w_mbs, J.epoch, J.err);
+				}
+				if (ok && mby > 0) ok = wait_flag(J.flags, mbx < J.w_mbs - 1 ? mb - J.w_mbs + 1 : mb - J.w_mbs, J.epoch, J.err);
+				__threadfence();
+			}
+			__syncwarp();
+			const bool up = mby > 0, left = mbx > 0, carried = rows_mode && left;
+			if (up) {
+				int x = lane - 1;   /* -1..23 */
+				if (x < 24 && (x >= 0 ? true : (left && !carried)) && (x < 16 || mbx < J.w_mbs - 1)) YT(x, -1) = __ldcg(Y - J.stride_y + x);
+				if (lane < 18) { int pl = lane / 9, cx = lane % 9 - 1; if (cx >= 0 || (left && !carried)) CT(pl, cx, -1) = __ldcg(C + pl * cpl - J.stride_c + cx); }
+			}
+			if (left && !carried) {
+				if (lane < 16) YT(-1, lane) = __ldcg(Y + (size_t)lane * J.stride_y - 1);
+				else { int j = lane - 16, pl = j >> 3, row = j & 7; CT(pl, -1, row) = __ldcg(C + pl * cpl + (size_t)row * J.stride_c - 1); }
+			}
+			__syncwarp();
+			intra_luma(ws, r, lane);
+			intra_chroma(ws, r, lane);
+		} else {
+			inter_predict(ws, J, r, sr, mbx, mby, lane);
+		}
+	}
+	/* 128-bit row stores of the reconstructed macroblock */
+	if (lane < 16) *(uint4 *)(Y + (size_t)lane * J.stride_y) = *(const uint4 *)&YT(0, lane);
+	else { int j = lane - 16, pl = j >> 3, row = j & 7; *(uint2 *)(C + pl * cpl + (size_t)row * J.stride_c) = *(const uint2 *)&CT(pl, 0, row); }
+	__syncwarp();
+	if (rows_mode) {   /* right-most column (and the sample above it) become the next macroblock's left neighbour / corner */
+		uint8_t v = 0;
+		if (lane < 17) v = YT(15, lane - 1);
+		else if (lane < 26) v = CT(0, 7, lane - 18);
+		uint8_t v2 = lane < 9 ? CT(1, 7, lane - 1) : 0;
+		__syncwarp();
+		if (lane < 17) YT(-1, lane - 1) = v;
+		else if (lane < 26) CT(0, -1, lane - 18) = v;
+		if (lane < 9) CT(1, -1, lane - 1) = v2;
+	}
+	if (lane == 0) { __threadfence(); *(volatile unsigned *)(J.flags + mb) = J.epoch; }
+	__syncwarp();
+}
+
+/* tickets hand out macroblocks (J.rows_mode == 0: mostly-inter pictures, everything independent runs in
+ * parallel) or whole rows (rows_mode == 1: intra pictures, a 2:1 wavefront of row warps) */
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_recon_kernel(PicJob J) {
 	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
 	const int lane = threadIdx.x & 31;
@@ -579,56 +646,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_recon_kernel(PicJob
 		unsigned t = 0;
 		if (lane == 0) t = atomicAdd(J.tickets, 1u);
 		t = __shfl_sync(0xffffffffu, t, 0);
-		if (t >= (unsigned)nmb) break;
-		const int mb = (int)t, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
-		if (lane < 12) ws->rec4[lane] = __ldg((const uint4 *)(J.recs + mb) + lane);
-		__syncwarp();
-		const E264MbRec *r = (const E264MbRec *)ws->rec4;
-		const E264SliceRec *sr = J.slices + r->slice_idx;
-		uint8_t *Y = dst + (size_t)(mby * 16) * J.stride_y + mbx * 16;
-		uint8_t *C = dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8;
-		const int kind = r->kind;
-		if (kind == MBK_IPCM) {
-			const uint8_t *s = (const uint8_t *)(J.coefs + r->coef_off);
-			if (lane < 16) *(uint4 *)(Y + (size_t)lane * J.stride_y) = __ldg((const uint4 *)s + lane);
-			else { int j = lane - 16, pl = j >> 3, row = j & 7; *(uint2 *)(C + pl * (J.stride_c >> 1) + (size_t)row * J.stride_c) = __ldg((const uint2 *)(s + 256) + j); }
+		if (J.rows_mode) {
+			if (t >= (unsigned)J.h_mbs) break;
+			for (int mbx = 0; mbx < J.w_mbs; mbx++) recon_mb(ws, J, dst, (int)t * J.w_mbs + mbx, mbx, (int)t, lane, true);
 		} else {
-			residual_stage(ws, r, sr, J.coefs, lane);
-			if (kind != MBK_INTER) {
-				/* wait for the neighbours, then fetch the samples around the macroblock (L2, bypassing L1) */
-				bool ok = true;
-				if (lane == 0) {   /* A, D, B, C: inter neighbours finish without waiting, so each one is checked */
-					if (mbx > 0) ok = wait_flag(J.flags, mb - 1, J.epoch, J.err);
-					if (ok && mby > 0) {
-						if (mbx > 0) ok = wait_flag(J.flags, mb - J.w_mbs - 1, J.epoch, J.err);
-						if (ok) ok = wait_flag(J.flags, mb - J.w_mbs, J.epoch, J.err);
-						if (ok && mbx < J.w_mbs - 1) ok = wait_flag(J.flags, mb - J.w_mbs + 1, J.epoch, J.err);
-					}
-					__threadfence();
-				}
-				__syncwarp();
-				const bool up = mby > 0, left = mbx > 0;
-				if (up) {
-					int x = lane - 1;   /* -1..30 -> need -1..23 */
-					if (x < 24 && (x >= 0 || left) && (x < 16 || mbx < J.w_mbs - 1)) YT(x, -1) = __ldcg(Y - J.stride_y + x);
-					if (lane < 18) { int pl = lane / 9, cx = lane % 9 - 1; if (cx >= 0 || left) CT(pl, cx, -1) = __ldcg(C + pl * (J.stride_c >> 1) - J.stride_c + cx); }
-				}
-				if (left) {
-					if (lane < 16) YT(-1, lane) = __ldcg(Y + (size_t)lane * J.stride_y - 1);
-					else { int j = lane - 16, pl = j >> 3, row = j & 7; CT(pl, -1, row) = __ldcg(C + pl * (J.stride_c >> 1) + (size_t)row * J.stride_c - 1); }
-				}
-				__syncwarp();
-				intra_luma(ws, r, lane);
-				intra_chroma(ws, r, lane);
-			} else {
-				inter_predict(ws, J, r, sr, mbx, mby, lane);
-			}
-			/* 128-bit row stores of the reconstructed macroblock */
-			if (lane < 16) *(uint4 *)(Y + (size_t)lane * J.stride_y) = *(const uint4 *)&YT(0, lane);
-			else { int j = lane - 16, pl = j >> 3, row = j & 7; *(uint2 *)(C + pl * (J.stride_c >> 1) + (size_t)row * J.stride_c) = *(const uint2 *)&CT(pl, 0, row); }
+			if (t >= (unsigned)nmb) break;
+			recon_mb(ws, J, dst, (int)t, (int)t % J.w_mbs, (int)t / J.w_mbs, lane, false);
 		}
-		__syncwarp();
-		if (lane == 0) { __threadfence(); *(volatile unsigned *)(J.flags + mb) = J.epoch; }
 	}
 }
 
@@ -699,103 +723,118 @@ __device__ __forceinline__ void filter_chroma(uint8_t *pix, int step, int bs, in
 	} else { pix[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2); pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2); }
 }
 
+/* One warp per macroblock ROW: the warp walks its row left to right, so the left neighbour's samples
+ * stay in shared memory and only the row above is a cross-warp dependency, published as a per-row
+ * progress counter (value = epoch * 2048 + macroblocks finished).  Row y may process macroblock x once
+ * row y-1 has finished x+1 (its left-edge filter touches columns 13..15 of macroblock x above us). */
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_deblock_kernel(PicJob J) {
 	__shared__ DbSmem smem[WARPS_PER_BLOCK];
 	const int lane = threadIdx.x & 31;
 	DbSmem *ds = &smem[threadIdx.x >> 5];
-	const int nmb = J.w_mbs * J.h_mbs;
-	unsigned *flags = J.flags + nmb;
+	const int nmb = J.w_mbs * J.h_mbs, W = J.w_mbs;
+	volatile unsigned *progress = J.flags + nmb;
+	const unsigned base = J.epoch * 2048u;
 	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
+	const int cpl = J.stride_c >> 1;
 	for (;;) {
 		unsigned t = 0;
 		if (lane == 0) t = atomicAdd(J.tickets + 1, 1u);
 		t = __shfl_sync(0xffffffffu, t, 0);
-		if (t >= (unsigned)nmb) break;
-		const int mb = (int)t, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
-		const E264MbRec *q = J.recs + mb;
-		const int qflags = q->flags;
-		if (qflags & MBF_DEBLOCK) {
-			const E264SliceRec *sr = J.slices + q->slice_idx;
-			const bool fl = qflags & MBF_EDGE_L, ft = qflags & MBF_EDGE_T, t8 = qflags & MBF_T8x8;
-			/* boundary strengths: lane = dir*16 + edge*4 + segment */
-			{
-				int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3, bs = 0;
-				const E264MbRec *p = q;
-				bool on = true;
-				if (e == 0) { on = dir ? ft : fl; p = dir ? q - J.w_mbs : q - 1; }
-				if (on) {
-					int qx = dir ? k : e, qy = dir ? e : k;
-					int px_ = dir ? k : (e ? e - 1 : 3), py_ = dir ? (e ? e - 1 : 3) : k;
-					bs = bs_pair(p, blk_z(px_, py_), q, blk_z(qx, qy), e == 0);
+		if (t >= (unsigned)J.h_mbs) break;
+		const int mby = (int)t;
+		uint8_t *Yrow = dst + (size_t)(mby * 16) * J.stride_y;
+		uint8_t *Crow = dst + J.plane_y + (size_t)(mby * 8) * J.stride_c;
+		/* prefetch the first macroblock of the row */
+		uint4 nl = make_uint4(0, 0, 0, 0); uint2 nc = make_uint2(0, 0);
+		if (lane < 16) nl = *(const uint4 *)(Yrow + (size_t)lane * J.stride_y);
+		else { int j = lane - 16; nc = *(const uint2 *)(Crow + (j >> 3) * cpl + (size_t)(j & 7) * J.stride_c); }
+		for (int mbx = 0; mbx < W; mbx++) {
+			const int mb = mby * W + mbx;
+			const E264MbRec *q = J.recs + mb;
+			const int qflags = q->flags;
+			uint8_t *Y = Yrow + mbx * 16, *C = Crow + mbx * 8;
+			/* current macroblock into the tile; columns -4..-1 were left there by the previous iteration */
+			if (lane < 16) *(uint4 *)&DY(0, lane) = nl;
+			else { int j = lane - 16; *(uint2 *)&DC_(j >> 3, 0, j & 7) = nc; }
+			if (mbx + 1 < W) {   /* prefetch the next one (written by the reconstruction kernel only) */
+				if (lane < 16) nl = *(const uint4 *)(Y + 16 + (size_t)lane * J.stride_y);
+				else { int j = lane - 16; nc = *(const uint2 *)(C + 8 + (j >> 3) * cpl + (size_t)(j & 7) * J.stride_c); }
+			}
+			if (qflags & MBF_DEBLOCK) {
+				const E264SliceRec *sr = J.slices + q->slice_idx;
+				const bool fl = qflags & MBF_EDGE_L, ft = qflags & MBF_EDGE_T, t8 = qflags & MBF_T8x8;
+				{
+					int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3, bs = 0;
+					const E264MbRec *p = q;
+					bool on = true;
+					if (e == 0) { on = dir ? ft : fl; p = dir ? q - W : q - 1; }
+					if (on) {
+						int qx = dir ? k : e, qy = dir ? e : k;
+						int px_ = dir ? k : (e ? e - 1 : 3), py_ = dir ? (e ? e - 1 : 3) : k;
+						bs = bs_pair(p, blk_z(px_, py_), q, blk_z(qx, qy), e == 0);
+					}
+					ds->bs[lane] = (int8_t)bs;
 				}
-				ds->bs[lane] = (int8_t)bs;
-			}
-			if (lane < 9) {
-				int pl = lane / 3, kind = lane % 3;
-				const E264MbRec *p = kind == 0 ? q : kind == 1 ? q - 1 : q - J.w_mbs;
-				if ((kind == 1 && !fl) || (kind == 2 && !ft)) p = q;
-				int qpav = (p->qp[pl] + q->qp[pl] + 1) >> 1;
-				int ia = min(max(qpav + sr->filter_offset_a, 0), 51), ib = min(max(qpav + sr->filter_offset_b, 0), 51);
-				ds->alpha[pl][kind] = h264_alpha[ia]; ds->beta[pl][kind] = h264_beta[ib]; ds->ia[pl][kind] = (uint8_t)ia;
-			}
-			/* dependencies: left neighbour and top-right (or top) neighbour fully deblocked */
-			bool ok = true;
-			if (lane == 0) {
-				if (mbx > 0) ok = wait_flag(flags, mb - 1, J.epoch, J.err);
-				if (ok && mby > 0) ok = wait_flag(flags, mb - J.w_mbs, J.epoch, J.err);
-				if (ok && mby > 0 && mbx < J.w_mbs - 1) ok = wait_flag(flags, mb - J.w_mbs + 1, J.epoch, J.err);
-				__threadfence();
-			}
-			__syncwarp();
-			uint8_t *Y = dst + (size_t)(mby * 16) * J.stride_y + mbx * 16;
-			uint8_t *C = dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8;
-			/* load 20x20 luma (+ 2 x 10x10 chroma) around the macroblock */
-			for (int i = lane; i < 20 * 5; i += 32) {
-				int row = i / 5 - 4, seg = i % 5 - 1;   /* 4-byte segments: -1 (cols -4..-1), 0..3 */
-				if ((row >= 0 || mby > 0) && (seg >= 0 || mbx > 0))
-					*(uint32_t *)&DY(seg * 4, row) = __ldcg((const uint32_t *)(Y + (ptrdiff_t)row * J.stride_y + seg * 4));
-			}
-			for (int i = lane; i < 2 * 10 * 5; i += 32) {
-				int pl = i / 50, j = i % 50, row = j / 5 - 2, seg = j % 5 - 1;   /* 2-byte segments: -1 (cols -2,-1), 0..3 */
-				if ((row >= 0 || mby > 0) && (seg >= 0 || mbx > 0))
-					*(uint16_t *)&DC_(pl, seg * 2, row) = __ldcg((const uint16_t *)(C + pl * (J.stride_c >> 1) + (ptrdiff_t)row * J.stride_c + seg * 2));
-			}
-			__syncwarp();
-			for (int dir = 0; dir < 2; dir++) {
-				for (int e = 0; e < 4; e++) {
-					int kind = e ? 0 : 1 + dir;
-					if (lane < 16) {
-						if (!(t8 && (e & 1))) {
-							int b = ds->bs[dir * 16 + e * 4 + (lane >> 2)];
-							if (b) {
-								uint8_t *pix = dir ? &DY(lane, e * 4) : &DY(e * 4, lane);
-								filter_luma(pix, dir ? 32 : 1, b, ds->alpha[0][kind], ds->beta[0][kind], b < 4 ? h264_tc0[ds->ia[0][kind]][b - 1] : 0);
-							}
-						}
-					} else if (!(e & 1)) {
-						int j = lane - 16, pl = j >> 3, k = j & 7;
-						int b = ds->bs[dir * 16 + e * 4 + (k >> 1)];
-						if (b) {
-							uint8_t *pix = dir ? &DC_(pl, k, e * 2) : &DC_(pl, e * 2, k);
-							filter_chroma(pix, dir ? 16 : 1, b, ds->alpha[1 + pl][kind], ds->beta[1 + pl][kind], b < 4 ? h264_tc0[ds->ia[1 + pl][kind]][b - 1] : 0);
-						}
+				if (lane < 9) {
+					int pl = lane / 3, kind = lane % 3;
+					const E264MbRec *p = kind == 0 ? q : kind == 1 ? q - 1 : q - W;
+					if ((kind == 1 && !fl) || (kind == 2 && !ft)) p = q;
+					int qpav = (p->qp[pl] + q->qp[pl] + 1) >> 1;
+					int ia = min(max(qpav + sr->filter_offset_a, 0), 51), ib = min(max(qpav + sr->filter_offset_b, 0), 51);
+					ds->alpha[pl][kind] = h264_alpha[ia]; ds->beta[pl][kind] = h264_beta[ib]; ds->ia[pl][kind] = (uint8_t)ia;
+				}
+				if (ft) {
+					/* the row above must have finished macroblock mbx+1 (or its whole row) */
+					if (lane == 0) {
+						unsigned need = base + (unsigned)min(mbx + 2, W), spins = 0;
+						while ((int)(progress[mby - 1] - need) < 0) { __nanosleep(32); if (++spins > (1u << 24)) { atomicExch(J.err, 1u); break; } }
+						__threadfence();
 					}
 					__syncwarp();
+					if (lane < 4) *(uint4 *)&DY(0, lane - 4) = __ldcg((const uint4 *)(Y - (size_t)(4 - lane) * J.stride_y));
+					else if (lane < 8) { int j = lane - 4, pl = j >> 1, r = (j & 1) - 2; *(uint2 *)&DC_(pl, 0, r) = __ldcg((const uint2 *)(C + pl * cpl + (ptrdiff_t)r * J.stride_c)); }
+				}
+				__syncwarp();
+				for (int dir = 0; dir < 2; dir++) {
+					for (int e = 0; e < 4; e++) {
+						int kind = e ? 0 : 1 + dir;
+						if (lane < 16) {
+							if (!(t8 && (e & 1))) {
+								int b = ds->bs[dir * 16 + e * 4 + (lane >> 2)];
+								if (b) {
+									uint8_t *pix = dir ? &DY(lane, e * 4) : &DY(e * 4, lane);
+									filter_luma(pix, dir ? 32 : 1, b, ds->alpha[0][kind], ds->beta[0][kind], b < 4 ? h264_tc0[ds->ia[0][kind]][b - 1] : 0);
+								}
+							}
+						} else if (!(e & 1)) {
+							int j = lane - 16, pl = j >> 3, k = j & 7;
+							int b = ds->bs[dir * 16 + e * 4 + (k >> 1)];
+							if (b) {
+								uint8_t *pix = dir ? &DC_(pl, k, e * 2) : &DC_(pl, e * 2, k);
+								filter_chroma(pix, dir ? 16 : 1, b, ds->alpha[1 + pl][kind], ds->beta[1 + pl][kind], b < 4 ? h264_tc0[ds->ia[1 + pl][kind]][b - 1] : 0);
+							}
+						}
+						__syncwarp();
+					}
+				}
+				/* write back: the macroblock, 3 columns of the left neighbour, 3 rows (1 for chroma) of the top neighbour */
+				if (lane < 16) *(uint4 *)(Y + (size_t)lane * J.stride_y) = *(const uint4 *)&DY(0, lane);
+				else { int j = lane - 16, pl = j >> 3, row = j & 7; *(uint2 *)(C + pl * cpl + (size_t)row * J.stride_c) = *(const uint2 *)&DC_(pl, 0, row); }
+				if (fl) {
+					if (lane < 16) { uint8_t *d = Y + (size_t)lane * J.stride_y; d[-3] = DY(-3, lane); d[-2] = DY(-2, lane); d[-1] = DY(-1, lane); }
+					else { int j = lane - 16, pl = j >> 3, row = j & 7; C[pl * cpl + (size_t)row * J.stride_c - 1] = DC_(pl, -1, row); }
+				}
+				if (ft) {
+					if (lane < 3) *(uint4 *)(Y - (size_t)(lane + 1) * J.stride_y) = *(const uint4 *)&DY(0, -1 - lane);
+					else if (lane < 5) { int pl = lane - 3; *(uint2 *)(C + pl * cpl - J.stride_c) = *(const uint2 *)&DC_(pl, 0, -1); }
 				}
 			}
-			/* write back: the macroblock, 3 columns of the left neighbour, 3 rows of the top neighbour (1 for chroma) */
-			if (lane < 16) *(uint4 *)(Y + (size_t)lane * J.stride_y) = *(const uint4 *)&DY(0, lane);
-			else { int j = lane - 16, pl = j >> 3, row = j & 7; *(uint2 *)(C + pl * (J.stride_c >> 1) + (size_t)row * J.stride_c) = *(const uint2 *)&DC_(pl, 0, row); }
-			if (fl) {
-				if (lane < 16) { uint8_t *d = Y + (size_t)lane * J.stride_y; d[-3] = DY(-3, lane); d[-2] = DY(-2, lane); d[-1] = DY(-1, lane); }
-				else { int j = lane - 16, pl = j >> 3, row = j & 7; C[pl * (J.stride_c >> 1) + (size_t)row * J.stride_c - 1] = DC_(pl, -1, row); }
-			}
-			if (ft) {
-				if (lane < 3) *(uint4 *)(Y - (size_t)(lane + 1) * J.stride_y) = *(const uint4 *)&DY(0, -1 - lane);
-				else if (lane < 5) { int pl = lane - 3; *(uint2 *)(C + pl * (J.stride_c >> 1) - J.stride_c) = *(const uint2 *)&DC_(pl, 0, -1); }
-			}
+			__syncwarp();
+			/* carry the last 4 (2) columns over as the next macroblock's left neighbour */
+			if (lane < 16) *(uint32_t *)&DY(-4, lane) = *(const uint32_t *)&DY(12, lane);
+			else { int j = lane - 16; *(uint16_t *)&DC_(j >> 3, -2, j & 7) = *(const uint16_t *)&DC_(j >> 3, 6, j & 7); }
+			if (lane == 0) { __threadfence(); progress[mby] = base + (unsigned)mbx + 1u; }
+			__syncwarp();
 		}
-		__syncwarp();
-		if (lane == 0) { __threadfence(); *(volatile unsigned *)(flags + mb) = J.epoch; }
 	}
 }
