@@ -12,21 +12,30 @@
 #include "h264_vlc_tables.h"
 #include "bits.h"
 
+/* Decoder registers: codIOffset sits at a FIXED position (bits 62..54 of `val`, one bit of headroom for
+ * bypass doubling) followed by `avail` valid look-ahead bits, so the MPS/LPS comparison needs only a
+ * constant shift; renormalisation is one count-leading-zeros and the LPS/MPS selection is branch-free. */
 typedef struct CabacDec {
 	uint64_t val;
 	uint32_t range;
-	int nbits;
+	int avail;
 	const uint8_t *p, *start, *end;   /* buffer must carry >= 16 readable slack bytes after `end` */
 	uint8_t state[1024];
 } CabacDec;
+#define CABAC_POS 54
 
 static uint8_t cabac_next_mps[128], cabac_next_lps[128];
+static uint8_t cabac_trans[256];      /* [0..127] state after an MPS, [128..255] after an LPS */
+static uint8_t cabac_lps4[4 * 128];   /* rangeTabLPS indexed by qCodIRangeIdx * 128 + packed state */
 static int cabac_tables_ready;
 static void cabac_build_tables(void) {
 	if (cabac_tables_ready) return;
 	for (int s = 0; s < 64; s++) for (int m = 0; m < 2; m++) {
 		cabac_next_mps[s * 2 + m] = (uint8_t)((s < 62 ? s + 1 : s) * 2 + m);
 		cabac_next_lps[s * 2 + m] = (uint8_t)(h264_trans_lps[s] * 2 + (s == 0 ? !m : m));
+		cabac_trans[s * 2 + m] = cabac_next_mps[s * 2 + m];
+		cabac_trans[128 + s * 2 + m] = cabac_next_lps[s * 2 + m];
+		for (int q = 0; q < 4; q++) cabac_lps4[q * 128 + s * 2 + m] = h264_range_lps[s][q];
 	}
 	cabac_tables_ready = 1;
 }
@@ -42,60 +51,80 @@ static void cabac_init_states(uint8_t *state, int col, int slice_qp) {
 	}
 }
 
-static inline void cabac_refill(CabacDec *c) {
-	if (c->nbits < 16) {
-		uint32_t w; memcpy(&w, c->p, 4); c->p += 4;
-		c->val = (c->val << 32) | __builtin_bswap32(w);
-		c->nbits += 32;
+/* the four hot fields, kept in locals by the residual parser */
+typedef struct CabacRegs { uint64_t val; uint32_t range; int avail; const uint8_t *p; } CabacRegs;
+static inline CabacRegs cabac_regs_load(const CabacDec *c) { CabacRegs r = {c->val, c->range, c->avail, c->p}; return r; }
+static inline void cabac_regs_store(CabacDec *c, const CabacRegs *r) { c->val = r->val; c->range = r->range; c->avail = r->avail; c->p = r->p; }
+
+static inline void cabac_r_refill(CabacRegs *r) {
+	if (r->avail <= CABAC_POS - 32) {
+		uint32_t w; memcpy(&w, r->p, 4); r->p += 4;
+		r->val |= (uint64_t)__builtin_bswap32(w) << (CABAC_POS - 32 - r->avail);
+		r->avail += 32;
 	}
 }
+static inline int cabac_r_bin(CabacRegs *r, uint8_t *state, int ctx) {
+	cabac_r_refill(r);
+	uint32_t s = state[ctx];
+	uint32_t lps = cabac_lps4[((r->range & 0xC0) << 1) + s];
+	uint32_t rmps = r->range - lps;
+	uint64_t scaled = (uint64_t)rmps << CABAC_POS;
+	uint64_t m = (uint64_t)0 - (uint64_t)(r->val >= scaled);     /* all ones on the LPS path */
+	r->val -= scaled & m;
+	uint32_t range = rmps + ((lps - rmps) & (uint32_t)m);
+	state[ctx] = cabac_trans[s + ((uint32_t)m & 128)];
+	int n = __builtin_clz(range) - 23;
+	r->range = range << n; r->val <<= n; r->avail -= n;
+	return (int)((s ^ (uint32_t)m) & 1);
+}
+static inline int cabac_r_bypass(CabacRegs *r) {
+	cabac_r_refill(r);
+	r->val <<= 1; r->avail--;
+	uint64_t scaled = (uint64_t)r->range << CABAC_POS;
+	uint64_t m = (uint64_t)0 - (uint64_t)(r->val >= scaled);
+	r->val -= scaled & m;
+	return (int)(m & 1);
+}
+
 /* 9.3.1.2: p must be byte aligned */
 static inline void cabac_dec_start(CabacDec *c, const uint8_t *p, const uint8_t *end) {
 	c->start = c->p = p; c->end = end;
-	c->val = 0; c->nbits = -9; c->range = 510;
-	cabac_refill(c);
+	c->val = 0; c->avail = -9; c->range = 510;
+	/* first 32 bits: 9 into codIOffset, 23 look-ahead */
+	uint32_t w; memcpy(&w, c->p, 4); c->p += 4;
+	c->val = (uint64_t)__builtin_bswap32(w) << (CABAC_POS + 9 - 32);
+	c->avail = 23;
 }
 static inline int cabac_bin(CabacDec *c, int ctx) {
-	cabac_refill(c);
-	uint32_t s = c->state[ctx];
-	uint32_t lps = h264_range_lps[s >> 1][(c->range >> 6) & 3];
-	uint32_t rmps = c->range - lps;
-	uint64_t scaled = (uint64_t)rmps << c->nbits;
-	if (c->val < scaled) {
-		c->state[ctx] = cabac_next_mps[s];
-		int sh = rmps < 256;
-		c->range = rmps << sh; c->nbits -= sh;
-		return s & 1;
-	}
-	c->val -= scaled;
-	c->state[ctx] = cabac_next_lps[s];
-	int n = __builtin_clz(lps) - 23;
-	c->range = lps << n; c->nbits -= n;
-	return (s & 1) ^ 1;
+	CabacRegs r = cabac_regs_load(c);
+	int b = cabac_r_bin(&r, c->state, ctx);
+	cabac_regs_store(c, &r);
+	return b;
 }
 static inline int cabac_bypass(CabacDec *c) {
-	cabac_refill(c);
-	c->nbits--;
-	uint64_t scaled = (uint64_t)c->range << c->nbits;
-	if (c->val >= scaled) { c->val -= scaled; return 1; }
-	return 0;
+	CabacRegs r = cabac_regs_load(c);
+	int b = cabac_r_bypass(&r);
+	cabac_regs_store(c, &r);
+	return b;
 }
 static inline int cabac_terminate(CabacDec *c) {
-	cabac_refill(c);
-	c->range -= 2;
-	uint64_t scaled = (uint64_t)c->range << c->nbits;
-	if (c->val >= scaled) return 1;
-	if (c->range < 256) { c->range <<= 1; c->nbits--; }
-	return 0;
+	CabacRegs r = cabac_regs_load(c);
+	cabac_r_refill(&r);
+	r.range -= 2;
+	uint64_t scaled = (uint64_t)r.range << CABAC_POS;
+	int bin = r.val >= scaled;
+	if (!bin && r.range < 256) { r.range <<= 1; r.val <<= 1; r.avail--; }
+	cabac_regs_store(c, &r);
+	return bin;
 }
 /* after cabac_terminate()==1: byte position of the first byte after the (aligned) end of the
  * arithmetic code word, i.e. where pcm samples start (7.3.5 pcm_alignment_zero_bit) */
 static inline const uint8_t *cabac_dec_aligned_pos(const CabacDec *c) {
-	int64_t bits = (int64_t)(c->p - c->start) * 8 - c->nbits;   /* consumed into codIOffset, incl. the stop bit */
+	int64_t bits = (int64_t)(c->p - c->start) * 8 - c->avail;   /* consumed into codIOffset, incl. the stop bit */
 	return c->start + ((bits + 7) >> 3);
 }
 static inline int cabac_dec_overrun(const CabacDec *c) {
-	return (int64_t)(c->p - c->end) * 8 - c->nbits > 16;  /* consumed clearly past the end of the RBSP */
+	return (int64_t)(c->p - c->end) * 8 - c->avail > 16;  /* consumed clearly past the end of the RBSP */
 }
 
 /* ---------------- encoder (generator only) ---------------- */

@@ -189,6 +189,7 @@ static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, const E264MbRec *r
 	J.stride_y = pd->stride_y; J.stride_c = pd->stride_c; J.plane_y = pd->plane_y; J.dst_slot = pd->dst_slot; J.n_slots = c->n_slots;
 	J.tickets = c->d_sync; J.err = c->d_sync + 2; J.flags = c->d_sync + 4;
 	J.rows_mode = pd->n_intra * 2 > pd->width_mbs * pd->height_mbs;   /* intra pictures: wavefront of row warps */
+	{ static int force = -2; if (force == -2) { const char *e = getenv("E264B_ROWS"); force = e ? atoi(e) : -1; } if (force >= 0) J.rows_mode = force; }
 	if (c->epoch >= (1u << 20)) {   /* row progress counters encode epoch * 2048 + count: restart before it wraps */
 		cudaStreamSynchronize(c->stream);
 		cudaMemsetAsync(c->d_sync, 0, (4 + 2 * c->nmb) * sizeof(unsigned), c->stream);

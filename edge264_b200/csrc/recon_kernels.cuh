@@ -488,8 +488,13 @@ __device__ __forceinline__ int weight_sample(const E264MbRec *r, const E264Slice
 	return p;
 }
 
-/* motion-compensate the rectangle (x0,y0,w,h) (luma units, inside the MB) of list l */
-__device__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int l, int x0, int y0, int w, int h, int lane) {
+/* motion-compensate the SxS square at (x0,y0) (luma units, inside the MB) of list l.
+ * All reference samples of the (S+5)^2 luma window and the two (S/2+1)^2 chroma windows are requested
+ * before any is consumed (independent loads, fully unrolled), so one L2 round trip covers the window. */
+template <int S>
+__device__ __forceinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int l, int x0, int y0, int lane) {
+	constexpr int WW = S + 5, NL = WW * WW, CW = S / 2, CWW = CW + 1, NC = 2 * CWW * CWW;
+	constexpr int ITL = (NL + 31) / 32, ITC = (NC + 31) / 32;
 	int z0 = blk_z(x0 >> 2, y0 >> 2);
 	int mvx = r->mv[l][z0][0], mvy = r->mv[l][z0][1];
 	int slot = r->ref_pic[l][z0 >> 2];
@@ -497,46 +502,55 @@ __device__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264MbRec *r, const
 	const uint8_t *ref = J.frames + (size_t)slot * J.frame_bytes;
 	const int W = J.w_mbs * 16, H = J.h_mbs * 16;
 	uint8_t *win = ws->u.win;
-	/* luma window */
-	{
-		int X0 = mbx * 16 + x0 + (mvx >> 2) - 2, Y0 = mby * 16 + y0 + (mvy >> 2) - 2;
-		int ww = w + 5, hh = h + 5;
-		for (int row = 0; row < hh; row++) {
-			if (lane < ww) {
-				int xx = min(max(X0 + lane, 0), W - 1), yy = min(max(Y0 + row, 0), H - 1);
-				win[row * WIN_STRIDE + lane] = __ldg(ref + (size_t)yy * J.stride_y + xx);
-			}
+	const int X0 = mbx * 16 + x0 + (mvx >> 2) - 2, Y0 = mby * 16 + y0 + (mvy >> 2) - 2;
+	const int CX0 = mbx * 8 + (x0 >> 1) + (mvx >> 3), CY0 = mby * 8 + (y0 >> 1) + (mvy >> 3);
+	uint8_t vl[ITL], vc[ITC];
+#pragma unroll
+	for (int k = 0; k < ITL; k++) {
+		int i = lane + 32 * k;
+		if (i < NL) {
+			int row = i / WW, col = i - row * WW;
+			int xx = min(max(X0 + col, 0), W - 1), yy = min(max(Y0 + row, 0), H - 1);
+			vl[k] = __ldg(ref + (size_t)yy * J.stride_y + xx);
 		}
 	}
-	/* chroma windows */
-	int cw = w >> 1, ch = h >> 1;
-	{
-		int X0 = mbx * 8 + (x0 >> 1) + (mvx >> 3), Y0 = mby * 8 + (y0 >> 1) + (mvy >> 3);
-		int ww = cw + 1, hh = ch + 1;
-		for (int row = 0; row < hh; row++) {
-			int pl = lane >> 4, c = lane & 15;
-			if (c < ww) {
-				int xx = min(max(X0 + c, 0), (W >> 1) - 1), yy = min(max(Y0 + row, 0), (H >> 1) - 1);
-				win[21 * WIN_STRIDE + pl * 108 + row * 12 + c] = __ldg(ref + J.plane_y + pl * (J.stride_c >> 1) + (size_t)yy * J.stride_c + xx);
-			}
+#pragma unroll
+	for (int k = 0; k < ITC; k++) {
+		int i = lane + 32 * k;
+		if (i < NC) {
+			int pl = i / (CWW * CWW), j = i - pl * CWW * CWW, row = j / CWW, col = j - row * CWW;
+			int xx = min(max(CX0 + col, 0), (W >> 1) - 1), yy = min(max(CY0 + row, 0), (H >> 1) - 1);
+			vc[k] = __ldg(ref + J.plane_y + pl * (J.stride_c >> 1) + (size_t)yy * J.stride_c + xx);
 		}
 	}
+#pragma unroll
+	for (int k = 0; k < ITL; k++) { int i = lane + 32 * k; if (i < NL) { int row = i / WW, col = i - row * WW; win[row * WIN_STRIDE + col] = vl[k]; } }
+#pragma unroll
+	for (int k = 0; k < ITC; k++) { int i = lane + 32 * k; if (i < NC) { int pl = i / (CWW * CWW), j = i - pl * CWW * CWW, row = j / CWW, col = j - row * CWW; win[21 * WIN_STRIDE + pl * 108 + row * 12 + col] = vc[k]; } }
 	__syncwarp();
-	int fx = mvx & 3, fy = mvy & 3;
-	for (int p = lane; p < w * h; p += 32) {
-		int x = p % w, y = p / w;
-		int v = mc_luma_sample(win, x, y, fx, fy);
-		int X = x0 + x, Y = y0 + y, i8 = (Y >> 3) * 2 + (X >> 3);
-		YT(X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 0, v, YT(X, Y));
+	const int fx = mvx & 3, fy = mvy & 3;
+#pragma unroll
+	for (int k = 0; k < (S * S + 31) / 32; k++) {
+		int p = lane + 32 * k;
+		if (p < S * S) {
+			int x = p % S, y = p / S;
+			int v = mc_luma_sample(win, x, y, fx, fy);
+			int X = x0 + x, Y = y0 + y, i8 = (Y >> 3) * 2 + (X >> 3);
+			YT(X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 0, v, YT(X, Y));
+		}
 	}
-	int cfx = mvx & 7, cfy = mvy & 7;
-	for (int p = lane; p < 2 * cw * ch; p += 32) {
-		int pl = p / (cw * ch), q = p - pl * cw * ch, x = q % cw, y = q / cw;
-		const uint8_t *cwn = win + 21 * WIN_STRIDE + pl * 108;
-		int A = cwn[y * 12 + x], B = cwn[y * 12 + x + 1], C = cwn[(y + 1) * 12 + x], D = cwn[(y + 1) * 12 + x + 1];
-		int v = ((8 - cfx) * (8 - cfy) * A + cfx * (8 - cfy) * B + (8 - cfx) * cfy * C + cfx * cfy * D + 32) >> 6;
-		int X = (x0 >> 1) + x, Y = (y0 >> 1) + y, i8 = (Y >> 2) * 2 + (X >> 2);
-		CT(pl, X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 1 + pl, v, CT(pl, X, Y));
+	const int cfx = mvx & 7, cfy = mvy & 7;
+#pragma unroll
+	for (int k = 0; k < (2 * CW * CW + 31) / 32; k++) {
+		int p = lane + 32 * k;
+		if (p < 2 * CW * CW) {
+			int pl = p / (CW * CW), q = p - pl * CW * CW, x = q % CW, y = q / CW;
+			const uint8_t *cwn = win + 21 * WIN_STRIDE + pl * 108;
+			int A = cwn[y * 12 + x], B = cwn[y * 12 + x + 1], C = cwn[(y + 1) * 12 + x], D = cwn[(y + 1) * 12 + x + 1];
+			int v = ((8 - cfx) * (8 - cfy) * A + cfx * (8 - cfy) * B + (8 - cfx) * cfy * C + cfx * cfy * D + 32) >> 6;
+			int X = (x0 >> 1) + x, Y = (y0 >> 1) + y, i8 = (Y >> 2) * 2 + (X >> 2);
+			CT(pl, X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 1 + pl, v, CT(pl, X, Y));
+		}
 	}
 	__syncwarp();
 }
@@ -547,7 +561,7 @@ __device__ void inter_predict(WarpSmem *ws, const PicJob &J, const E264MbRec *r,
 		int z = lane & 15;
 		bool same = r->mv[l][z][0] == r->mv[l][0][0] && r->mv[l][z][1] == r->mv[l][0][1] && r->ref_idx[l][z >> 2] == r->ref_idx[l][0] && r->ref_idx[l ^ 1][z >> 2] == r->ref_idx[l ^ 1][0];
 		if (__all_sync(0xffffffffu, same)) {
-			if (r->ref_idx[l][0] >= 0) mc_rect(ws, J, r, sr, mbx, mby, l, 0, 0, 16, 16, lane);
+			if (r->ref_idx[l][0] >= 0) mc_rect<16>(ws, J, r, sr, mbx, mby, l, 0, 0, lane);
 			continue;
 		}
 		for (int i8 = 0; i8 < 4; i8++) {
@@ -555,8 +569,8 @@ __device__ void inter_predict(WarpSmem *ws, const PicJob &J, const E264MbRec *r,
 			int zb = i8 * 4, x0 = (i8 & 1) * 8, y0 = (i8 >> 1) * 8;
 			bool s8 = true;
 			for (int k = 1; k < 4; k++) s8 = s8 && r->mv[l][zb + k][0] == r->mv[l][zb][0] && r->mv[l][zb + k][1] == r->mv[l][zb][1];
-			if (s8) mc_rect(ws, J, r, sr, mbx, mby, l, x0, y0, 8, 8, lane);
-			else for (int k = 0; k < 4; k++) mc_rect(ws, J, r, sr, mbx, mby, l, x0 + (k & 1) * 4, y0 + (k >> 1) * 4, 4, 4, lane);
+			if (s8) mc_rect<8>(ws, J, r, sr, mbx, mby, l, x0, y0, lane);
+			else for (int k = 0; k < 4; k++) mc_rect<4>(ws, J, r, sr, mbx, mby, l, x0 + (k & 1) * 4, y0 + (k >> 1) * 4, lane);
 		}
 	}
 	/* add the residual */
@@ -602,8 +616,8 @@ __device__ void recon_mb(WarpSmem *ws, const PicJob &J, uint8_t *dst, int mb, in
 			const bool up = mby > 0, left = mbx > 0, carried = rows_mode && left;
 			if (up) {
 				int x = lane - 1;   /* -1..23 */
-				if (x < 24 && (x >= 0 ? true : (left && !carried)) && (x < 16 || mbx < J.w_mbs - 1)) YT(x, -1) = __ldcg(Y - J.stride_y + x);
-				if (lane < 18) { int pl = lane / 9, cx = lane % 9 - 1; if (cx >= 0 || (left && !carried)) CT(pl, cx, -1) = __ldcg(C + pl * cpl - J.stride_c + cx); }
+				if (x < 24 && (x >= 0 || left) && (x < 16 || mbx < J.w_mbs - 1)) YT(x, -1) = __ldcg(Y - J.stride_y + x);   /* the corner is always fetched: the previous macroblock may not have loaded its top row (PCM, inter) */
+				if (lane < 18) { int pl = lane / 9, cx = lane % 9 - 1; if (cx >= 0 || left) CT(pl, cx, -1) = __ldcg(C + pl * cpl - J.stride_c + cx); }
 			}
 			if (left && !carried) {
 				if (lane < 16) YT(-1, lane) = __ldcg(Y + (size_t)lane * J.stride_y - 1);
@@ -620,15 +634,15 @@ __device__ void recon_mb(WarpSmem *ws, const PicJob &J, uint8_t *dst, int mb, in
 	if (lane < 16) *(uint4 *)(Y + (size_t)lane * J.stride_y) = *(const uint4 *)&YT(0, lane);
 	else { int j = lane - 16, pl = j >> 3, row = j & 7; *(uint2 *)(C + pl * cpl + (size_t)row * J.stride_c) = *(const uint2 *)&CT(pl, 0, row); }
 	__syncwarp();
-	if (rows_mode) {   /* right-most column (and the sample above it) become the next macroblock's left neighbour / corner */
+	if (rows_mode) {   /* right-most column becomes the next macroblock's left neighbour */
 		uint8_t v = 0;
-		if (lane < 17) v = YT(15, lane - 1);
-		else if (lane < 26) v = CT(0, 7, lane - 18);
-		uint8_t v2 = lane < 9 ? CT(1, 7, lane - 1) : 0;
+		if (lane < 16) v = YT(15, lane);
+		else if (lane < 24) v = CT(0, 7, lane - 16);
+		uint8_t v2 = lane < 8 ? CT(1, 7, lane) : 0;
 		__syncwarp();
-		if (lane < 17) YT(-1, lane - 1) = v;
-		else if (lane < 26) CT(0, -1, lane - 18) = v;
-		if (lane < 9) CT(1, -1, lane - 1) = v2;
+		if (lane < 16) YT(-1, lane) = v;
+		else if (lane < 24) CT(0, -1, lane - 16) = v;
+		if (lane < 8) CT(1, -1, lane) = v2;
 	}
 	if (lane == 0) { __threadfence(); *(volatile unsigned *)(J.flags + mb) = J.epoch; }
 	__syncwarp();
@@ -665,6 +679,7 @@ struct __align__(16) DbSmem {
 	int8_t bs[32];             /* [dir][edge][segment] */
 	uint8_t alpha[3][3], beta[3][3];   /* [plane][0 internal, 1 left edge, 2 top edge] */
 	uint8_t ia[3][3];
+	uint4 rq[12], rl[12], rt[12];   /* records of the current, left and top macroblocks (row-walking kernel) */
 };
 #define DY(x, y) ds->ypix[((y) + 4) * 32 + 16 + (x)]
 #define DC_(pl, x, y) ds->cpix[pl][((y) + 2) * 16 + 8 + (x)]
@@ -744,21 +759,46 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_deblock_kernel(PicJ
 		const int mby = (int)t;
 		uint8_t *Yrow = dst + (size_t)(mby * 16) * J.stride_y;
 		uint8_t *Crow = dst + J.plane_y + (size_t)(mby * 8) * J.stride_c;
-		/* prefetch the first macroblock of the row */
+		/* prefetch the first macroblock of the row: samples and records */
 		uint4 nl = make_uint4(0, 0, 0, 0); uint2 nc = make_uint2(0, 0);
 		if (lane < 16) nl = *(const uint4 *)(Yrow + (size_t)lane * J.stride_y);
 		else { int j = lane - 16; nc = *(const uint2 *)(Crow + (j >> 3) * cpl + (size_t)(j & 7) * J.stride_c); }
+		if (lane < 12) ds->rq[lane] = __ldg((const uint4 *)(J.recs + mby * W) + lane);
+		else if (lane < 24 && mby > 0) ds->rt[lane - 12] = __ldg((const uint4 *)(J.recs + (mby - 1) * W) + lane - 12);
+		uint4 tl = make_uint4(0, 0, 0, 0); uint2 tc = make_uint2(0, 0); bool have_top = false;
+		__syncwarp();
 		for (int mbx = 0; mbx < W; mbx++) {
 			const int mb = mby * W + mbx;
-			const E264MbRec *q = J.recs + mb;
+			const E264MbRec *q = (const E264MbRec *)ds->rq, *pL = (const E264MbRec *)ds->rl, *pT = (const E264MbRec *)ds->rt;
 			const int qflags = q->flags;
 			uint8_t *Y = Yrow + mbx * 16, *C = Crow + mbx * 8;
 			/* current macroblock into the tile; columns -4..-1 were left there by the previous iteration */
 			if (lane < 16) *(uint4 *)&DY(0, lane) = nl;
 			else { int j = lane - 16; *(uint2 *)&DC_(j >> 3, 0, j & 7) = nc; }
-			if (mbx + 1 < W) {   /* prefetch the next one (written by the reconstruction kernel only) */
+			if (have_top) {
+				if (lane < 4) *(uint4 *)&DY(0, lane - 4) = tl;
+				else if (lane < 8) { int j = lane - 4; *(uint2 *)&DC_(j >> 1, 0, (j & 1) - 2) = tc; }
+			}
+			const bool had_top = have_top;
+			/* software pipeline: everything the NEXT macroblock needs is requested now */
+			uint4 nrec = make_uint4(0, 0, 0, 0);
+			have_top = false;
+			if (mbx + 1 < W) {
 				if (lane < 16) nl = *(const uint4 *)(Y + 16 + (size_t)lane * J.stride_y);
 				else { int j = lane - 16; nc = *(const uint2 *)(C + 8 + (j >> 3) * cpl + (size_t)(j & 7) * J.stride_c); }
+				if (lane < 12) nrec = __ldg((const uint4 *)(J.recs + mb + 1) + lane);
+				else if (lane < 24 && mby > 0) nrec = __ldg((const uint4 *)(J.recs + mb + 1 - W) + lane - 12);
+				if (mby > 0) {
+					unsigned need = base + (unsigned)min(mbx + 3, W);
+					int okp = 0;
+					if (lane == 0) { okp = (int)(progress[mby - 1] - need) >= 0; if (okp) __threadfence(); }
+					okp = __shfl_sync(0xffffffffu, okp, 0);
+					if (okp) {
+						have_top = true;
+						if (lane < 4) tl = __ldcg((const uint4 *)(Y + 16 - (size_t)(4 - lane) * J.stride_y));
+						else if (lane < 8) { int j = lane - 4, pl = j >> 1, r = (j & 1) - 2; tc = __ldcg((const uint2 *)(C + 8 + pl * cpl + (ptrdiff_t)r * J.stride_c)); }
+					}
+				}
 			}
 			if (qflags & MBF_DEBLOCK) {
 				const E264SliceRec *sr = J.slices + q->slice_idx;
@@ -767,7 +807,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_deblock_kernel(PicJ
 					int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3, bs = 0;
 					const E264MbRec *p = q;
 					bool on = true;
-					if (e == 0) { on = dir ? ft : fl; p = dir ? q - W : q - 1; }
+					if (e == 0) { on = dir ? ft : fl; p = dir ? pT : pL; }
 					if (on) {
 						int qx = dir ? k : e, qy = dir ? e : k;
 						int px_ = dir ? k : (e ? e - 1 : 3), py_ = dir ? (e ? e - 1 : 3) : k;
@@ -777,13 +817,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_deblock_kernel(PicJ
 				}
 				if (lane < 9) {
 					int pl = lane / 3, kind = lane % 3;
-					const E264MbRec *p = kind == 0 ? q : kind == 1 ? q - 1 : q - W;
+					const E264MbRec *p = kind == 0 ? q : kind == 1 ? pL : pT;
 					if ((kind == 1 && !fl) || (kind == 2 && !ft)) p = q;
 					int qpav = (p->qp[pl] + q->qp[pl] + 1) >> 1;
 					int ia = min(max(qpav + sr->filter_offset_a, 0), 51), ib = min(max(qpav + sr->filter_offset_b, 0), 51);
 					ds->alpha[pl][kind] = h264_alpha[ia]; ds->beta[pl][kind] = h264_beta[ib]; ds->ia[pl][kind] = (uint8_t)ia;
 				}
-				if (ft) {
+				if (ft && !had_top) {
 					/* the row above must have finished macroblock mbx+1 (or its whole row) */
 					if (lane == 0) {
 						unsigned need = base + (unsigned)min(mbx + 2, W), spins = 0;
@@ -834,6 +874,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_deblock_kernel(PicJ
 			if (lane < 16) *(uint32_t *)&DY(-4, lane) = *(const uint32_t *)&DY(12, lane);
 			else { int j = lane - 16; *(uint16_t *)&DC_(j >> 3, -2, j & 7) = *(const uint16_t *)&DC_(j >> 3, 6, j & 7); }
 			if (lane == 0) { __threadfence(); progress[mby] = base + (unsigned)mbx + 1u; }
+			/* rotate the record buffers: current -> left, prefetched -> current / top */
+			if (lane < 12) { ds->rl[lane] = ds->rq[lane]; ds->rq[lane] = nrec; }
+			else if (lane < 24) ds->rt[lane - 12] = nrec;
 			__syncwarp();
 		}
 	}

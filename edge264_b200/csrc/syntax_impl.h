@@ -34,6 +34,21 @@
 #define VLC_U(n, v)  ((int)br_u(&s->br, (n)))
 #endif
 
+/* register-resident CABAC state for the residual parser (parser direction only) */
+#ifdef E264_ENCODER
+#define CR_BEGIN
+#define CR_OUT
+#define CR_IN
+#define AE_R(ctx, v)  AE(ctx, v)
+#define AE_BYP_R(v)   AE_BYP(v)
+#else
+#define CR_BEGIN      CabacRegs cr = cabac_regs_load(&s->cd); uint8_t *const cst = s->cd.state;
+#define CR_OUT        cabac_regs_store(&s->cd, &cr);
+#define CR_IN         cr = cabac_regs_load(&s->cd);
+#define AE_R(ctx, v)  cabac_r_bin(&cr, cst, (ctx))
+#define AE_BYP_R(v)   cabac_r_bypass(&cr)
+#endif
+
 enum { SLICE_P = 0, SLICE_B = 1, SLICE_I = 2 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -301,16 +316,17 @@ static int residual_block_cabac(SliceCtx *s, int cat, int cbf_inc, int has_cbf, 
 #ifdef E264_ENCODER
 	for (int k = 0; k < n; k++) if (blk[scan[k]]) last_e = k;
 #endif
-	if (has_cbf && !AE(h264_cat_cbf[cat] + cbf_inc, ENCV(last_e >= 0))) return 0;
+	CR_BEGIN
+	if (has_cbf && !AE_R(h264_cat_cbf[cat] + cbf_inc, ENCV(last_e >= 0))) { CR_OUT return 0; }
 	uint8_t sig[64]; int nsig = 0;
 	int sig_base = h264_cat_sig[cat], last_base = h264_cat_last[cat];
 	int k;
 	for (k = 0; k < n - 1; k++) {
 		int si = cat == 5 ? h264_sig8x8_inc[k] : cat == 3 ? (k < 2 ? k : 2) : k;
-		if (AE(sig_base + si, ENCV(blk[scan[k]] != 0))) {
+		if (AE_R(sig_base + si, ENCV(blk[scan[k]] != 0))) {
 			sig[nsig++] = (uint8_t)k;
 			int li = cat == 5 ? h264_last8x8_inc[k] : cat == 3 ? (k < 2 ? k : 2) : k;
-			if (AE(last_base + li, ENCV(k == last_e))) break;
+			if (AE_R(last_base + li, ENCV(k == last_e))) break;
 		}
 	}
 	if (k == n - 1) sig[nsig++] = (uint8_t)(n - 1);
@@ -319,15 +335,15 @@ static int residual_block_cabac(SliceCtx *s, int cat, int cbf_inc, int has_cbf, 
 		int16_t *dst = blk + scan[sig[i]];
 		int a = ENCV((*dst < 0 ? -*dst : *dst) - 1);
 		int absm1;
-		if (!AE(abs_base + (gt1 ? 0 : (1 + eq1 > 4 ? 4 : 1 + eq1)), ENCV(a > 0))) { absm1 = 0; eq1++; }
+		if (!AE_R(abs_base + (gt1 ? 0 : (1 + eq1 > 4 ? 4 : 1 + eq1)), ENCV(a > 0))) { absm1 = 0; eq1++; }
 		else {
 			int ctx = abs_base + 5 + (gt1 < cap ? gt1 : cap), cnt = 1;
-			while (cnt < 14 && AE(ctx, ENCV(a > cnt))) cnt++;
+			while (cnt < 14 && AE_R(ctx, ENCV(a > cnt))) cnt++;
 			absm1 = cnt;
-			if (cnt == 14) absm1 = 14 + se_egk_bypass(s, 0, ENCV(a - 14));
+			if (cnt == 14) { CR_OUT absm1 = 14 + se_egk_bypass(s, 0, ENCV(a - 14)); CR_IN }
 			gt1++;
 		}
-		int neg = AE_BYP(ENCV(*dst < 0));
+		int neg = AE_BYP_R(ENCV(*dst < 0));
 		int lv = neg ? -(absm1 + 1) : absm1 + 1;
 #ifndef E264_ENCODER
 		*dst = (int16_t)lv;
@@ -335,6 +351,7 @@ static int residual_block_cabac(SliceCtx *s, int cat, int cbf_inc, int has_cbf, 
 		(void)lv;
 #endif
 	}
+	CR_OUT
 	return nsig;
 }
 
