@@ -79,7 +79,7 @@ __device__ __forceinline__ bool wait_flag(const unsigned *flags, int idx, unsign
 /* residual                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
 /* 4x4 inverse transform of 16 levels at c (16-byte aligned) -> residual written to dst[y*dstride+x] */
-__device__ __forceinline__ void idct4x4(const int16_t *c, bool have_levels, const uint8_t *scaling, int qp, bool dc_override, int dc, int16_t *dst, int dstride) {
+__device__ __noinline__ void idct4x4(const int16_t *c, bool have_levels, const uint8_t *scaling, int qp, bool dc_override, int dc, int16_t *dst, int dstride) {
 	int d[16];
 	if (have_levels) {
 		uint4 a = __ldg((const uint4 *)c), b = __ldg((const uint4 *)c + 1);
@@ -128,7 +128,7 @@ __device__ __forceinline__ void idct8_1d(short a[8]) {
 	a[4] = (short)(f6 - f1); a[5] = (short)(f4 - f3); a[6] = (short)(f2 - f5); a[7] = (short)(f0 - f7);
 }
 
-__device__ void residual_stage(WarpSmem *ws, const E264MbRec *r, const E264SliceRec *sr, const int16_t *pool, int lane) {
+__device__ __noinline__ void residual_stage(WarpSmem *ws, const E264MbRec *r, const E264SliceRec *sr, const int16_t *pool, int lane) {
 	/* clear */
 	uint4 z = make_uint4(0, 0, 0, 0);
 	((uint4 *)ws->res)[lane] = z;
@@ -231,7 +231,7 @@ __device__ void residual_stage(WarpSmem *ws, const E264MbRec *r, const E264Slice
 #define CT(pl, x, y) ws->ctile[pl][((y) + 1) * CT_STRIDE + 8 + (x)]
 
 /* predicted sample (x,y) of a 4x4 block whose top-left tile coordinate is (X0,Y0) */
-__device__ __forceinline__ int pred4x4(const WarpSmem *ws, int X0, int Y0, int imode, int x, int y) {
+__device__ __noinline__ int pred4x4(const WarpSmem *ws, int X0, int Y0, int imode, int x, int y) {
 	int mode = imode & 15, un = imode >> 4;
 	bool hasA = !(un & 1), hasB = !(un & 2), hasC = !(un & 4);
 #define T(i) ((i) < 0 ? (int)YT(X0 - 1, Y0 - 1) : (int)YT(X0 + (((i) > 3 && !hasC) ? 3 : (i)), Y0 - 1))
@@ -276,7 +276,7 @@ __device__ __forceinline__ int pred4x4(const WarpSmem *ws, int X0, int Y0, int i
 }
 
 /* Intra 8x8: filtered reference samples in ws->u.edge[0][1+x] (top, x=-1..15) and edge[1][1+y] (left, y=-1..7) */
-__device__ void intra8x8_edges(WarpSmem *ws, int X0, int Y0, int un, int lane) {
+__device__ __noinline__ void intra8x8_edges(WarpSmem *ws, int X0, int Y0, int un, int lane) {
 	bool hasA = !(un & 1), hasB = !(un & 2), hasC = !(un & 4), hasD = !(un & 8);
 #define RT(i) ((i) < 0 ? (int)YT(X0 - 1, Y0 - 1) : (int)YT(X0 + (((i) > 7 && !hasC) ? 7 : (i)), Y0 - 1))
 #define RL(i) ((i) < 0 ? (int)YT(X0 - 1, Y0 - 1) : (int)YT(X0 - 1, Y0 + (i)))
@@ -309,7 +309,7 @@ __device__ void intra8x8_edges(WarpSmem *ws, int X0, int Y0, int un, int lane) {
 #undef RL
 	__syncwarp();
 }
-__device__ __forceinline__ int pred8x8(const WarpSmem *ws, int imode, int x, int y) {
+__device__ __noinline__ int pred8x8(const WarpSmem *ws, int imode, int x, int y) {
 	int mode = imode & 15, un = imode >> 4;
 	bool hasA = !(un & 1), hasB = !(un & 2);
 #define T(i) ws->u.edge[0][1 + (i)]
@@ -353,8 +353,9 @@ __device__ __forceinline__ int pred8x8(const WarpSmem *ws, int imode, int x, int
 #undef L
 }
 
-__device__ void intra_luma(WarpSmem *ws, const E264MbRec *r, int lane) {
+__device__ __noinline__ void intra_luma(WarpSmem *ws, const E264MbRec *r, int lane) {
 	if (r->kind == MBK_I4x4) {
+#pragma unroll 1
 		for (int b = 0; b < 16; b++) {
 			int X0 = blk_x(b) * 4, Y0 = blk_y(b) * 4;
 			if (lane < 16) {
@@ -366,6 +367,7 @@ __device__ void intra_luma(WarpSmem *ws, const E264MbRec *r, int lane) {
 			__syncwarp();
 		}
 	} else if (r->kind == MBK_I8x8) {
+#pragma unroll 1
 		for (int i = 0; i < 4; i++) {
 			int X0 = (i & 1) * 8, Y0 = (i >> 1) * 8, im = r->modes[i];
 			intra8x8_edges(ws, X0, Y0, im >> 4, lane);
@@ -392,26 +394,21 @@ __device__ void intra_luma(WarpSmem *ws, const E264MbRec *r, int lane) {
 			for (int k = 0; k < 16; k++) { st += YT(k, -1); sl += YT(-1, k); }
 			dc = (hasA && hasB) ? (st + sl + 16) >> 5 : hasA ? (sl + 8) >> 4 : hasB ? (st + 8) >> 4 : 128;
 		}
-		int vals[8];
-#pragma unroll
-		for (int k = 0; k < 8; k++) {
+#pragma unroll 1
+		for (int k = 0; k < 8; k++) {   /* reads touch only samples outside the macroblock: no hazard with the writes */
 			int p = lane + 32 * k, x = p & 15, y = p >> 4;
 			int v = mode == 0 ? (hasB ? (int)YT(x, -1) : 128) : mode == 1 ? (hasA ? (int)YT(-1, y) : 128) : mode == 2 ? dc : clip255((a + b * (x - 7) + c * (y - 7) + 16) >> 5);
-			vals[k] = clip255((short)(v + ws->res[p]));
+			YT(x, y) = (uint8_t)clip255((short)(v + ws->res[p]));
 		}
-		__syncwarp();
-#pragma unroll
-		for (int k = 0; k < 8; k++) { int p = lane + 32 * k; YT(p & 15, p >> 4) = (uint8_t)vals[k]; }
 		__syncwarp();
 	}
 }
 
-__device__ void intra_chroma(WarpSmem *ws, const E264MbRec *r, int lane) {
+__device__ __noinline__ void intra_chroma(WarpSmem *ws, const E264MbRec *r, int lane) {
 	int mode = r->chroma_mode & 15, un = r->chroma_mode >> 4;
 	bool hasA = !(un & 1), hasB = !(un & 2);
-	int vals[4];
-#pragma unroll
-	for (int k = 0; k < 4; k++) {
+#pragma unroll 1
+	for (int k = 0; k < 4; k++) {   /* reads touch only the row above / column left of the block */
 		int p = lane + 32 * k, pl = p >> 6, x = p & 7, y = (p >> 3) & 7, v;
 #define TC(i) (hasB ? (int)CT(pl, i, -1) : 128)
 #define LC(i) (hasA ? (int)CT(pl, -1, i) : 128)
@@ -436,11 +433,8 @@ __device__ void intra_chroma(WarpSmem *ws, const E264MbRec *r, int lane) {
 		}
 #undef TC
 #undef LC
-		vals[k] = clip255((short)(v + ws->res[256 + pl * 64 + y * 8 + x]));
+		CT(pl, x, y) = (uint8_t)clip255((short)(v + ws->res[256 + pl * 64 + y * 8 + x]));
 	}
-	__syncwarp();
-#pragma unroll
-	for (int k = 0; k < 4; k++) { int p = lane + 32 * k; CT(p >> 6, p & 7, (p >> 3) & 7) = (uint8_t)vals[k]; }
 	__syncwarp();
 }
 
@@ -449,33 +443,35 @@ __device__ void intra_chroma(WarpSmem *ws, const E264MbRec *r, int lane) {
 /* ------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
 
-/* luma sample at window position (x,y) (window origin = integer position - 2), fraction (fx,fy) — 8.4.2.2.1 */
+/* 8.4.2.2.1 in compact form (code size matters: the whole kernel must stay instruction-cache resident).
+ * mc_half: integer / half-sample value at quarter-sample coordinates (qx,qy) in {0,2,4}^2 relative to G. */
+__device__ __noinline__ int mc_half(const uint8_t *g, int qx, int qy) {
+	const uint8_t *p = g + (qy >> 2) * WIN_STRIDE + (qx >> 2);
+	const bool hx = qx & 2, hy = qy & 2;
+	if (!hx && !hy) return p[0];
+	if (!hy) return clip255((tap6(p[-2], p[-1], p[0], p[1], p[2], p[3]) + 16) >> 5);
+	if (!hx) return clip255((tap6(p[-2 * WIN_STRIDE], p[-WIN_STRIDE], p[0], p[WIN_STRIDE], p[2 * WIN_STRIDE], p[3 * WIN_STRIDE]) + 16) >> 5);
+	int t[6];
+#pragma unroll
+	for (int k = 0; k < 6; k++) { const uint8_t *r = p + (k - 2) * WIN_STRIDE; t[k] = tap6(r[-2], r[-1], r[0], r[1], r[2], r[3]); }
+	return clip255((tap6(t[0], t[1], t[2], t[3], t[4], t[5]) + 512) >> 10);
+}
+/* luma sample at window position (x,y) (window origin = integer position - 2), fraction (fx,fy) */
 __device__ __forceinline__ int mc_luma_sample(const uint8_t *w, int x, int y, int fx, int fy) {
-#define P(dx, dy) ((int)w[(y + 2 + (dy)) * WIN_STRIDE + x + 2 + (dx)])
-#define B1(dx, dy) tap6(P((dx) - 2, dy), P((dx) - 1, dy), P(dx, dy), P((dx) + 1, dy), P((dx) + 2, dy), P((dx) + 3, dy))
-#define H1(dx, dy) tap6(P(dx, (dy) - 2), P(dx, (dy) - 1), P(dx, dy), P(dx, (dy) + 1), P(dx, (dy) + 2), P(dx, (dy) + 3))
-	int G = P(0, 0);
-	if (!fx && !fy) return G;
-	if (!fy) { int b = clip255((B1(0, 0) + 16) >> 5); return fx == 2 ? b : (((fx == 1 ? G : P(1, 0)) + b + 1) >> 1); }
-	if (!fx) { int h = clip255((H1(0, 0) + 16) >> 5); return fy == 2 ? h : (((fy == 1 ? G : P(0, 1)) + h + 1) >> 1); }
-	if (fx == 2 || fy == 2) {
-		int j = clip255((tap6(B1(0, -2), B1(0, -1), B1(0, 0), B1(0, 1), B1(0, 2), B1(0, 3)) + 512) >> 10);
-		if (fx == 2 && fy == 2) return j;
-		if (fx == 2) { int bs = clip255((B1(0, fy == 1 ? 0 : 1) + 16) >> 5); return (bs + j + 1) >> 1; }
-		int hm = clip255((H1(fx == 1 ? 0 : 1, 0) + 16) >> 5); return (hm + j + 1) >> 1;
-	}
-	int bs = clip255((B1(0, fy == 1 ? 0 : 1) + 16) >> 5), hm = clip255((H1(fx == 1 ? 0 : 1, 0) + 16) >> 5);
-	return (bs + hm + 1) >> 1;
-#undef P
-#undef B1
-#undef H1
+	const uint8_t *g = w + (y + 2) * WIN_STRIDE + x + 2;
+	if (!((fx | fy) & 1)) return mc_half(g, fx, fy);
+	int ax, ay, bx, by;
+	if (!(fy & 1)) { ax = fx - 1; ay = fy; bx = fx + 1; by = fy; }
+	else if (!(fx & 1)) { ax = fx; ay = fy - 1; bx = fx; by = fy + 1; }
+	else { ax = 2; ay = fy == 1 ? 0 : 4; bx = fx == 1 ? 0 : 4; by = 2; }
+	return (mc_half(g, ax, ay) + mc_half(g, bx, by) + 1) >> 1;
 }
 
 __device__ __forceinline__ int wp_uni(int p, int w, int o, int logwd) { return clip255((logwd >= 1 ? ((p * w + (1 << (logwd - 1))) >> logwd) : p * w) + o); }
 __device__ __forceinline__ int wp_bi(int p0, int p1, int w0, int w1, int o0, int o1, int logwd) { return clip255(((p0 * w0 + p1 * w1 + (1 << logwd)) >> (logwd + 1)) + ((o0 + o1 + 1) >> 1)); }
 
 /* combine the prediction `p` of list `l` for a sample of 8x8 block i8 / plane pl with what the tile holds (list 0 pass) */
-__device__ __forceinline__ int weight_sample(const E264MbRec *r, const E264SliceRec *sr, int l, int i8, int pl, int p, int q) {
+__device__ __noinline__ int weight_sample(const E264MbRec *r, const E264SliceRec *sr, int l, int i8, int pl, int p, int q) {
 	int r0 = r->ref_idx[0][i8], r1 = r->ref_idx[1][i8];
 	int mode = sr->wp_mode, logwd = pl ? sr->chroma_log2_wd : sr->luma_log2_wd;
 	if (l == 1 && r0 >= 0) {   /* second pass of a bi-predicted block: q = list-0 prediction */
@@ -488,13 +484,11 @@ __device__ __forceinline__ int weight_sample(const E264MbRec *r, const E264Slice
 	return p;
 }
 
-/* motion-compensate the SxS square at (x0,y0) (luma units, inside the MB) of list l.
- * All reference samples of the (S+5)^2 luma window and the two (S/2+1)^2 chroma windows are requested
- * before any is consumed (independent loads, fully unrolled), so one L2 round trip covers the window. */
-template <int S>
-__device__ __forceinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int l, int x0, int y0, int lane) {
-	constexpr int WW = S + 5, NL = WW * WW, CW = S / 2, CWW = CW + 1, NC = 2 * CWW * CWW;
-	constexpr int ITL = (NL + 31) / 32, ITC = (NC + 31) / 32;
+/* motion-compensate the SxS square at (x0,y0) (luma units, inside the MB) of list l.  The window loads
+ * are independent (4 in flight per lane per trip), so a few L2 round trips cover the (S+5)^2 window. */
+__device__ __noinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int l, int x0, int y0, int S, int lane) {
+	const int WW = S + 5, NL = WW * WW, CW = S >> 1, CWW = CW + 1, NC1 = CWW * CWW;
+	const int rw = (65536 + WW - 1) / WW, rcw = (65536 + CWW - 1) / CWW;   /* exact reciprocals for i < 512 */
 	int z0 = blk_z(x0 >> 2, y0 >> 2);
 	int mvx = r->mv[l][z0][0], mvy = r->mv[l][z0][1];
 	int slot = r->ref_pic[l][z0 >> 2];
@@ -504,64 +498,47 @@ __device__ __forceinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E26
 	uint8_t *win = ws->u.win;
 	const int X0 = mbx * 16 + x0 + (mvx >> 2) - 2, Y0 = mby * 16 + y0 + (mvy >> 2) - 2;
 	const int CX0 = mbx * 8 + (x0 >> 1) + (mvx >> 3), CY0 = mby * 8 + (y0 >> 1) + (mvy >> 3);
-	uint8_t vl[ITL], vc[ITC];
-#pragma unroll
-	for (int k = 0; k < ITL; k++) {
-		int i = lane + 32 * k;
-		if (i < NL) {
-			int row = i / WW, col = i - row * WW;
-			int xx = min(max(X0 + col, 0), W - 1), yy = min(max(Y0 + row, 0), H - 1);
-			vl[k] = __ldg(ref + (size_t)yy * J.stride_y + xx);
-		}
+#pragma unroll 4
+	for (int i = lane; i < NL; i += 32) {
+		int row = (i * rw) >> 16, col = i - row * WW;
+		int xx = min(max(X0 + col, 0), W - 1), yy = min(max(Y0 + row, 0), H - 1);
+		win[row * WIN_STRIDE + col] = __ldg(ref + (size_t)yy * J.stride_y + xx);
 	}
-#pragma unroll
-	for (int k = 0; k < ITC; k++) {
-		int i = lane + 32 * k;
-		if (i < NC) {
-			int pl = i / (CWW * CWW), j = i - pl * CWW * CWW, row = j / CWW, col = j - row * CWW;
-			int xx = min(max(CX0 + col, 0), (W >> 1) - 1), yy = min(max(CY0 + row, 0), (H >> 1) - 1);
-			vc[k] = __ldg(ref + J.plane_y + pl * (J.stride_c >> 1) + (size_t)yy * J.stride_c + xx);
-		}
+#pragma unroll 2
+	for (int i = lane; i < 2 * NC1; i += 32) {
+		int pl = i >= NC1, j = i - pl * NC1, row = (j * rcw) >> 16, col = j - row * CWW;
+		int xx = min(max(CX0 + col, 0), (W >> 1) - 1), yy = min(max(CY0 + row, 0), (H >> 1) - 1);
+		win[21 * WIN_STRIDE + pl * 108 + row * 12 + col] = __ldg(ref + J.plane_y + pl * (J.stride_c >> 1) + (size_t)yy * J.stride_c + xx);
 	}
-#pragma unroll
-	for (int k = 0; k < ITL; k++) { int i = lane + 32 * k; if (i < NL) { int row = i / WW, col = i - row * WW; win[row * WIN_STRIDE + col] = vl[k]; } }
-#pragma unroll
-	for (int k = 0; k < ITC; k++) { int i = lane + 32 * k; if (i < NC) { int pl = i / (CWW * CWW), j = i - pl * CWW * CWW, row = j / CWW, col = j - row * CWW; win[21 * WIN_STRIDE + pl * 108 + row * 12 + col] = vc[k]; } }
 	__syncwarp();
-	const int fx = mvx & 3, fy = mvy & 3;
-#pragma unroll
-	for (int k = 0; k < (S * S + 31) / 32; k++) {
-		int p = lane + 32 * k;
-		if (p < S * S) {
-			int x = p % S, y = p / S;
-			int v = mc_luma_sample(win, x, y, fx, fy);
-			int X = x0 + x, Y = y0 + y, i8 = (Y >> 3) * 2 + (X >> 3);
-			YT(X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 0, v, YT(X, Y));
-		}
+	const int fx = mvx & 3, fy = mvy & 3, sh = S == 16 ? 4 : S == 8 ? 3 : 2;
+#pragma unroll 1
+	for (int p = lane; p < S * S; p += 32) {
+		int x = p & (S - 1), y = p >> sh;
+		int v = mc_luma_sample(win, x, y, fx, fy);
+		int X = x0 + x, Y = y0 + y, i8 = (Y >> 3) * 2 + (X >> 3);
+		YT(X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 0, v, YT(X, Y));
 	}
 	const int cfx = mvx & 7, cfy = mvy & 7;
-#pragma unroll
-	for (int k = 0; k < (2 * CW * CW + 31) / 32; k++) {
-		int p = lane + 32 * k;
-		if (p < 2 * CW * CW) {
-			int pl = p / (CW * CW), q = p - pl * CW * CW, x = q % CW, y = q / CW;
-			const uint8_t *cwn = win + 21 * WIN_STRIDE + pl * 108;
-			int A = cwn[y * 12 + x], B = cwn[y * 12 + x + 1], C = cwn[(y + 1) * 12 + x], D = cwn[(y + 1) * 12 + x + 1];
-			int v = ((8 - cfx) * (8 - cfy) * A + cfx * (8 - cfy) * B + (8 - cfx) * cfy * C + cfx * cfy * D + 32) >> 6;
-			int X = (x0 >> 1) + x, Y = (y0 >> 1) + y, i8 = (Y >> 2) * 2 + (X >> 2);
-			CT(pl, X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 1 + pl, v, CT(pl, X, Y));
-		}
+#pragma unroll 1
+	for (int p = lane; p < 2 * CW * CW; p += 32) {
+		int pl = p >= CW * CW, q = p - pl * CW * CW, x = q & (CW - 1), y = q >> (sh - 1);
+		const uint8_t *cwn = win + 21 * WIN_STRIDE + pl * 108;
+		int A = cwn[y * 12 + x], B = cwn[y * 12 + x + 1], C = cwn[(y + 1) * 12 + x], D = cwn[(y + 1) * 12 + x + 1];
+		int v = ((8 - cfx) * (8 - cfy) * A + cfx * (8 - cfy) * B + (8 - cfx) * cfy * C + cfx * cfy * D + 32) >> 6;
+		int X = (x0 >> 1) + x, Y = (y0 >> 1) + y, i8 = (Y >> 2) * 2 + (X >> 2);
+		CT(pl, X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 1 + pl, v, CT(pl, X, Y));
 	}
 	__syncwarp();
 }
 
-__device__ void inter_predict(WarpSmem *ws, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int lane) {
+__device__ __noinline__ void inter_predict(WarpSmem *ws, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int lane) {
 	for (int l = 0; l < 2; l++) {
 		/* is the whole macroblock one 16x16 partition for this list? */
 		int z = lane & 15;
 		bool same = r->mv[l][z][0] == r->mv[l][0][0] && r->mv[l][z][1] == r->mv[l][0][1] && r->ref_idx[l][z >> 2] == r->ref_idx[l][0] && r->ref_idx[l ^ 1][z >> 2] == r->ref_idx[l ^ 1][0];
 		if (__all_sync(0xffffffffu, same)) {
-			if (r->ref_idx[l][0] >= 0) mc_rect<16>(ws, J, r, sr, mbx, mby, l, 0, 0, lane);
+			if (r->ref_idx[l][0] >= 0) mc_rect(ws, J, r, sr, mbx, mby, l, 0, 0, 16, lane);
 			continue;
 		}
 		for (int i8 = 0; i8 < 4; i8++) {
@@ -569,8 +546,8 @@ __device__ void inter_predict(WarpSmem *ws, const PicJob &J, const E264MbRec *r,
 			int zb = i8 * 4, x0 = (i8 & 1) * 8, y0 = (i8 >> 1) * 8;
 			bool s8 = true;
 			for (int k = 1; k < 4; k++) s8 = s8 && r->mv[l][zb + k][0] == r->mv[l][zb][0] && r->mv[l][zb + k][1] == r->mv[l][zb][1];
-			if (s8) mc_rect<8>(ws, J, r, sr, mbx, mby, l, x0, y0, lane);
-			else for (int k = 0; k < 4; k++) mc_rect<4>(ws, J, r, sr, mbx, mby, l, x0 + (k & 1) * 4, y0 + (k >> 1) * 4, lane);
+			if (s8) mc_rect(ws, J, r, sr, mbx, mby, l, x0, y0, 8, lane);
+			else for (int k = 0; k < 4; k++) mc_rect(ws, J, r, sr, mbx, mby, l, x0 + (k & 1) * 4, y0 + (k >> 1) * 4, 4, lane);
 		}
 	}
 	/* add the residual */
