@@ -17,6 +17,8 @@ streams x F frames per GPU.
 """
 import argparse, ctypes, json, os, subprocess, sys, threading, time
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 W_MBS, H_MBS = 120, 68
 MB_PER_FRAME = W_MBS * H_MBS
@@ -24,7 +26,7 @@ MB_PER_FRAME = W_MBS * H_MBS
 
 def gen_args(seed, frames):
     return ["-W", str(W_MBS), "-H", str(H_MBS), "-n", str(frames), "-s", str(seed), "--gop", "IPB", "--idr", "30",
-            "--refs", "2", "--t8x8", "50", "--deblock", "0", "--density", "42", "--qp", "28", "--wp", "0"]
+            "--refs", "2", "--t8x8", "50", "--deblock", "0", "--density", "52", "--qp", "28", "--wp", "0"]
 
 
 def generate_streams(seeds, frames, workdir):
@@ -85,6 +87,17 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons, "samples": len(self.rows)}
 
 
+def usable_cpus():
+    """CPUs this container may actually use: min(affinity, cgroup quota) — the GPU boxes grant 16 of 128."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max": n = min(n, max(1, int(int(q) / int(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
@@ -100,8 +113,7 @@ def reference_arm(args, rank):
     if not os.path.exists(lib):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)"})); return
     ref = BenchLib(lib)
-    cores = os.cpu_count() or 1
-    threads = min(cores, 128)
+    threads = min(usable_cpus(), 128)   # one single-threaded decoder per usable CPU (cgroup quota respected)
     distinct = generate_streams([1000 + i for i in range(min(threads, 16))], args.frames, args.workdir)
     bufs = [distinct[i % len(distinct)] for i in range(threads)]
     for _ in range(args.warmup): ref.run(bufs[:threads], threads)
@@ -142,21 +154,8 @@ def main():
     # rank 0 generates every rank's streams and broadcasts the concatenated Annex-B input over NCCL
     if rank == 0:
         bufs_all = generate_streams([2000 + i for i in range(S * world)], F, args.workdir)
-    if world > 1:
-        if rank == 0:
-            sizes = torch.tensor([len(b) for b in bufs_all], dtype=torch.int64, device="cuda")
-            blob = torch.frombuffer(bytearray(b"".join(bufs_all)), dtype=torch.uint8).cuda()
-            total = torch.tensor([blob.numel()], dtype=torch.int64, device="cuda")
-        else:
-            sizes = torch.zeros(S * world, dtype=torch.int64, device="cuda"); total = torch.zeros(1, dtype=torch.int64, device="cuda")
-        dist.broadcast(sizes, 0); dist.broadcast(total, 0)
-        if rank != 0: blob = torch.empty(int(total.item()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(blob, 0)
-        host = blob.cpu().numpy().tobytes(); offs = [0]
-        for s in sizes.tolist(): offs.append(offs[-1] + s)
-        bufs = [host[offs[rank * S + i]:offs[rank * S + i + 1]] for i in range(S)]
-    else:
-        bufs = bufs_all
+    from edge264_b200.shard import broadcast_streams, max_over_ranks
+    bufs = broadcast_streams(bufs_all if rank == 0 else None, S, world, rank, dist, "cuda")
 
     lib = BenchLib(os.path.join(ROOT, "tools", "libe264bench.so"))
     core = ctypes.CDLL(os.path.join(ROOT, "edge264_b200", "libedge264_b200.so"))
@@ -170,9 +169,7 @@ def main():
     def barrier():
         if dist is not None: dist.barrier()
         torch.cuda.synchronize()
-    def maxreduce(x):
-        if dist is None: return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+    def maxreduce(x): return max_over_ranks(x, dist, "cuda")
 
     # ---- e2e: decode through the C API from host buffers (also fills the kept records for the replay) ----
     for _ in range(max(args.warmup - 1, 0)):
@@ -241,11 +238,11 @@ def main():
         refp = os.path.join(ROOT, "oracle", "_ref", "libe264bench_ref.so")
         if os.path.exists(refp):
             ref = BenchLib(refp)
-            threads = min(os.cpu_count() or 1, 32)
+            threads = min(usable_cpus(), 32)
             rb_ = [bufs[i % S] for i in range(threads)]
             s, fr, rs, _ = ref.run(rb_, threads)
             line["cpu_baseline"] = {"value": sum(fr) / s, "unit": "frames/s", "cores": threads, "kind": "reference",
-                                    "sample": f"{threads} streams x {F} frames, one single-threaded reference decoder per thread, host cores of this box ({os.cpu_count()} logical)",
+                                    "sample": f"{threads} streams x {F} frames, one single-threaded reference decoder per thread, host of this box ({os.cpu_count()} logical CPUs, {usable_cpus()} usable under the cgroup quota)",
                                     "bit_exact_with_gpu": all(rs[i] == sums[i % S] for i in range(threads))}
         else:
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}

@@ -15,12 +15,16 @@
 /* Decoder registers: codIOffset sits at a FIXED position (bits 62..54 of `val`, one bit of headroom for
  * bypass doubling) followed by `avail` valid look-ahead bits, so the MPS/LPS comparison needs only a
  * constant shift; renormalisation is one count-leading-zeros and the LPS/MPS selection is branch-free. */
+/* context states are 16-bit on purpose: byte stores may alias anything, which would force the compiler to
+ * reload range/val/avail after every bin; int16 stores cannot alias them (strict aliasing) */
+typedef int16_t CabacState;
+
 typedef struct CabacDec {
 	uint64_t val;
 	uint32_t range;
 	int avail;
 	const uint8_t *p, *start, *end;   /* buffer must carry >= 16 readable slack bytes after `end` */
-	uint8_t state[1024];
+	CabacState state[1024];
 } CabacDec;
 #define CABAC_POS 54
 
@@ -41,13 +45,13 @@ static void cabac_build_tables(void) {
 }
 
 /* 9.3.1.1 context initialisation; col = 0 for I slices, else 1 + cabac_init_idc */
-static void cabac_init_states(uint8_t *state, int col, int slice_qp) {
+static void cabac_init_states(CabacState *state, int col, int slice_qp) {
 	int qp = slice_qp < 0 ? 0 : slice_qp > 51 ? 51 : slice_qp;
 	for (int i = 0; i < 1024; i++) {
 		int m = h264_cabac_mn[i][col][0], n = h264_cabac_mn[i][col][1];
 		int pre = ((m * qp) >> 4) + n;
 		pre = pre < 1 ? 1 : pre > 126 ? 126 : pre;
-		state[i] = pre <= 63 ? (uint8_t)((63 - pre) << 1) : (uint8_t)(((pre - 64) << 1) | 1);
+		state[i] = pre <= 63 ? (CabacState)((63 - pre) << 1) : (CabacState)(((pre - 64) << 1) | 1);
 	}
 }
 
@@ -63,7 +67,7 @@ static inline void cabac_r_refill(CabacRegs *r) {
 		r->avail += 32;
 	}
 }
-static inline int cabac_r_bin(CabacRegs *r, uint8_t *state, int ctx) {
+static inline int cabac_r_bin(CabacRegs *r, CabacState *state, int ctx) {
 	cabac_r_refill(r);
 	uint32_t s = state[ctx];
 	uint32_t lps = cabac_lps4[((r->range & 0xC0) << 1) + s];
@@ -131,7 +135,7 @@ static inline int cabac_dec_overrun(const CabacDec *c) {
 typedef struct CabacEnc {
 	uint32_t low, range; int outstanding, first;
 	BitWriter *w;
-	uint8_t state[1024];
+	CabacState state[1024];
 } CabacEnc;
 static inline void cabac_enc_start(CabacEnc *e, BitWriter *w) { e->w = w; e->low = 0; e->range = 510; e->outstanding = 0; e->first = 1; }
 static inline void cabac_enc_put(CabacEnc *e, int b) {

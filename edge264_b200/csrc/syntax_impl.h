@@ -42,7 +42,7 @@
 #define AE_R(ctx, v)  AE(ctx, v)
 #define AE_BYP_R(v)   AE_BYP(v)
 #else
-#define CR_BEGIN      CabacRegs cr = cabac_regs_load(&s->cd); uint8_t *const cst = s->cd.state;
+#define CR_BEGIN      CabacRegs cr = cabac_regs_load(&s->cd); CabacState *const cst = s->cd.state;
 #define CR_OUT        cabac_regs_store(&s->cd, &cr);
 #define CR_IN         cr = cabac_regs_load(&s->cd);
 #define AE_R(ctx, v)  cabac_r_bin(&cr, cst, (ctx))
