@@ -310,8 +310,10 @@ static int se_transform_8x8_flag(SliceCtx *s, int v) {
 /* ------------------------------------------------------------------------------------------ */
 /* CABAC residual_block_cabac (7.3.5.3.3): `blk` is the raster block in the pool (pre-zeroed by the
  * parser / pre-filled by the writer); scan[k] maps coefficient k (0..n-1) to its raster slot.
- * has_cbf: whether coded_block_flag is transmitted.  Returns the number of non-zero levels. */
-static int residual_block_cabac(SliceCtx *s, int cat, int cbf_inc, int has_cbf, int16_t *blk, const uint8_t *scan, int n) {
+ * has_cbf: whether coded_block_flag is transmitted.  Returns the number of non-zero levels.
+ * The body is force-inlined with a constant ctxBlockCat so that each category gets its own tight
+ * significance loop (the per-coefficient context selection folds away). */
+static inline __attribute__((always_inline)) int residual_block_cabac_cat(SliceCtx *s, const int cat, int cbf_inc, int has_cbf, int16_t *blk, const uint8_t *scan, const int n) {
 	int last_e = -1;
 #ifdef E264_ENCODER
 	for (int k = 0; k < n; k++) if (blk[scan[k]]) last_e = k;
@@ -319,18 +321,19 @@ static int residual_block_cabac(SliceCtx *s, int cat, int cbf_inc, int has_cbf, 
 	CR_BEGIN
 	if (has_cbf && !AE_R(h264_cat_cbf[cat] + cbf_inc, ENCV(last_e >= 0))) { CR_OUT return 0; }
 	uint8_t sig[64]; int nsig = 0;
-	int sig_base = h264_cat_sig[cat], last_base = h264_cat_last[cat];
+	const int sig_base = h264_cat_sig[cat], last_base = h264_cat_last[cat];
 	int k;
 	for (k = 0; k < n - 1; k++) {
-		int si = cat == 5 ? h264_sig8x8_inc[k] : cat == 3 ? (k < 2 ? k : 2) : k;
+		const int si = cat == 5 ? h264_sig8x8_inc[k] : cat == 3 ? (k < 2 ? k : 2) : k;
 		if (AE_R(sig_base + si, ENCV(blk[scan[k]] != 0))) {
 			sig[nsig++] = (uint8_t)k;
-			int li = cat == 5 ? h264_last8x8_inc[k] : cat == 3 ? (k < 2 ? k : 2) : k;
+			const int li = cat == 5 ? h264_last8x8_inc[k] : cat == 3 ? (k < 2 ? k : 2) : k;
 			if (AE_R(last_base + li, ENCV(k == last_e))) break;
 		}
 	}
 	if (k == n - 1) sig[nsig++] = (uint8_t)(n - 1);
-	int abs_base = h264_cat_abs[cat], gt1 = 0, eq1 = 0, cap = 4 - (cat == 3);
+	const int abs_base = h264_cat_abs[cat], cap = 4 - (cat == 3);
+	int gt1 = 0, eq1 = 0;
 	for (int i = nsig - 1; i >= 0; i--) {
 		int16_t *dst = blk + scan[sig[i]];
 		int a = ENCV((*dst < 0 ? -*dst : *dst) - 1);
@@ -353,6 +356,17 @@ static int residual_block_cabac(SliceCtx *s, int cat, int cbf_inc, int has_cbf, 
 	}
 	CR_OUT
 	return nsig;
+}
+static int residual_block_cabac(SliceCtx *s, int cat, int cbf_inc, int has_cbf, int16_t *blk, const uint8_t *scan, int n) {
+	switch (cat) {
+	case 0: return residual_block_cabac_cat(s, 0, cbf_inc, 1, blk, scan, 16);
+	case 1: return residual_block_cabac_cat(s, 1, cbf_inc, 1, blk, scan, 15);
+	case 2: return residual_block_cabac_cat(s, 2, cbf_inc, 1, blk, scan, 16);
+	case 3: return residual_block_cabac_cat(s, 3, cbf_inc, 1, blk, scan, 4);
+	case 4: return residual_block_cabac_cat(s, 4, cbf_inc, 1, blk, scan, 15);
+	default: return residual_block_cabac_cat(s, 5, cbf_inc, 0, blk, scan, 64);
+	}
+	(void)has_cbf; (void)n;
 }
 
 /* --- CAVLC residual_block_cavlc (7.3.5.3.2, 9.2) --- */
@@ -533,12 +547,16 @@ static int sx_nC_chroma(SliceCtx *s, int pl, int i) {
 }
 /* CABAC coded_block_flag ctxIdxInc helpers (9.3.3.1.1.9): value for an unavailable neighbour */
 static inline int sx_cbf_na(SliceCtx *s) { return s->cur->is_intra; }
+/* z-index of the block left of / above block b inside the same macroblock (valid when x>0 / y>0) */
+static const uint8_t sx_left_z[16]  = {0, 0, 0, 2, 1, 4, 3, 6, 0, 8, 0, 10, 9, 12, 11, 14};
+static const uint8_t sx_above_z[16] = {0, 0, 0, 1, 0, 0, 4, 5, 2, 3, 8, 9, 6, 7, 12, 13};
 static int sx_cbf_inc_luma(SliceCtx *s, int b) {
-	MbInfo *ma, *mb; E264MbRec *r;
-	int x = e264_blk_x(b), y = e264_blk_y(b);
-	int za = sx_locate(s, x - 1, y, &ma, &r), zb = sx_locate(s, x, y - 1, &mb, &r);
-	int a = ma ? (ma->is_pcm ? 1 : (ma->cbf_luma >> za) & 1) : sx_cbf_na(s);
-	int bb = mb ? (mb->is_pcm ? 1 : (mb->cbf_luma >> zb) & 1) : sx_cbf_na(s);
+	const int x = e264_blk_x(b), y = e264_blk_y(b);
+	int a, bb;
+	if (x) a = (s->cur->cbf_luma >> sx_left_z[b]) & 1;
+	else a = s->A ? (s->A->is_pcm ? 1 : (s->A->cbf_luma >> e264_blk_z(3, y)) & 1) : sx_cbf_na(s);
+	if (y) bb = (s->cur->cbf_luma >> sx_above_z[b]) & 1;
+	else bb = s->B ? (s->B->is_pcm ? 1 : (s->B->cbf_luma >> e264_blk_z(x, 3)) & 1) : sx_cbf_na(s);
 	return a + 2 * bb;
 }
 static int sx_cbf_inc_chroma_ac(SliceCtx *s, int pl, int i) {
