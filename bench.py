@@ -105,13 +105,13 @@ def peaks():
         return 6650.0, "fallback"
 
 
-def reference_arm(args, rank):
+def reference_arm(args, rank, emit):
     """CPU reference decoder on all host cores (rank 0 only)."""
     if rank != 0:
         return
     lib = os.path.join(ROOT, "oracle", "_ref", "libe264bench_ref.so")
     if not os.path.exists(lib):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)"})); return
+        emit({"impl": "reference", "unavailable": "oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)"}); return
     ref = BenchLib(lib)
     threads = min(usable_cpus(), 128)   # one single-threaded decoder per usable CPU (cgroup quota respected)
     distinct = generate_streams([1000 + i for i in range(min(threads, 16))], args.frames, args.workdir)
@@ -128,10 +128,14 @@ def reference_arm(args, rank):
             "config": {"workload": f"1080p High CABAC IPB ~30 Mbit/s, {args.frames} frames/stream, {threads} concurrent streams (one single-threaded reference decoder per host thread)", "streams": threads, "frames_per_stream": args.frames},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference", "sample": f"{threads} streams x {args.frames} frames per step, n_threads=0 decoders, one per thread"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) are diverted to stderr
+    real_stdout = os.dup(1); os.dup2(2, 1)
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200"); ap.add_argument("--streams", type=int, default=16); ap.add_argument("--frames", type=int, default=60)
@@ -139,7 +143,7 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        reference_arm(args, rank); return
+        reference_arm(args, rank, emit); return
 
     import torch
     if not torch.cuda.is_available():
@@ -247,7 +251,7 @@ def main():
         else:
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -445,26 +445,33 @@ __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { 
 
 /* 8.4.2.2.1 in compact form (code size matters: the whole kernel must stay instruction-cache resident).
  * mc_half: integer / half-sample value at quarter-sample coordinates (qx,qy) in {0,2,4}^2 relative to G. */
-__device__ __noinline__ int mc_half(const uint8_t *g, int qx, int qy) {
+__device__ __noinline__ int mc_half(const uint8_t *g, int qx, int qy, bool vfirst) {
 	const uint8_t *p = g + (qy >> 2) * WIN_STRIDE + (qx >> 2);
 	const bool hx = qx & 2, hy = qy & 2;
 	if (!hx && !hy) return p[0];
 	if (!hy) return clip255((tap6(p[-2], p[-1], p[0], p[1], p[2], p[3]) + 16) >> 5);
 	if (!hx) return clip255((tap6(p[-2 * WIN_STRIDE], p[-WIN_STRIDE], p[0], p[WIN_STRIDE], p[2 * WIN_STRIDE], p[3 * WIN_STRIDE]) + 16) >> 5);
+	/* centre sample: six first-pass sums (vertical first for the i/k positions, horizontal first for f/j/q)
+	 * combined like the reference does in wrapping int16 (edge264_inter.c:4-9) — equal to (j1+512)>>10 except
+	 * when the inner sum overflows on extreme checkerboards, which must be reproduced for bit-exactness */
 	int t[6];
+	const int sa = vfirst ? 1 : WIN_STRIDE, sb = vfirst ? WIN_STRIDE : 1;   /* sa: step between the six sums, sb: step inside one */
 #pragma unroll
-	for (int k = 0; k < 6; k++) { const uint8_t *r = p + (k - 2) * WIN_STRIDE; t[k] = tap6(r[-2], r[-1], r[0], r[1], r[2], r[3]); }
-	return clip255((tap6(t[0], t[1], t[2], t[3], t[4], t[5]) + 512) >> 10);
+	for (int k = 0; k < 6; k++) { const uint8_t *r = p + (k - 2) * sa; t[k] = tap6(r[-2 * sb], r[-sb], r[0], r[sb], r[2 * sb], r[3 * sb]); }
+	int af = t[0] + t[5], be = t[1] + t[4], cd = t[2] + t[3];
+	int t16 = (short)(((af - be) >> 2) + (cd - be));
+	return clip255(((t16 >> 2) + cd + 32) >> 6);
 }
 /* luma sample at window position (x,y) (window origin = integer position - 2), fraction (fx,fy) */
 __device__ __forceinline__ int mc_luma_sample(const uint8_t *w, int x, int y, int fx, int fy) {
 	const uint8_t *g = w + (y + 2) * WIN_STRIDE + x + 2;
-	if (!((fx | fy) & 1)) return mc_half(g, fx, fy);
+	const bool vfirst = fx & 1;
+	if (!((fx | fy) & 1)) return mc_half(g, fx, fy, vfirst);
 	int ax, ay, bx, by;
 	if (!(fy & 1)) { ax = fx - 1; ay = fy; bx = fx + 1; by = fy; }
 	else if (!(fx & 1)) { ax = fx; ay = fy - 1; bx = fx; by = fy + 1; }
 	else { ax = 2; ay = fy == 1 ? 0 : 4; bx = fx == 1 ? 0 : 4; by = 2; }
-	return (mc_half(g, ax, ay) + mc_half(g, bx, by) + 1) >> 1;
+	return (mc_half(g, ax, ay, vfirst) + mc_half(g, bx, by, vfirst) + 1) >> 1;
 }
 
 __device__ __forceinline__ int wp_uni(int p, int w, int o, int logwd) { return clip255((logwd >= 1 ? ((p * w + (1 << (logwd - 1))) >> logwd) : p * w) + o); }

@@ -2,6 +2,7 @@
  * the decoder's backend interface so that the host parser + record ABI can be validated against the
  * compiled reference decoder without a GPU (tests/test_oracle_vs_ref.py), and so that GPU output can
  * be compared with it picture by picture.  Linked only into oracle/liboracle_dec.so. */
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "../edge264_b200/csrc/dec.h"
@@ -47,6 +48,21 @@ static int port_acquire(void *ctx, int slot, E264MbRec **recs, int16_t **coefs, 
 }
 static int port_submit(void *ctx, const E264PicDesc *pd, uint8_t *host_out, uint64_t *ticket) {
 	PortCtx *c = (PortCtx *)ctx;
+	static int pic_no;
+	const char *dump = getenv("E264_DUMP");   /* "pic,mbx,mby": print that macroblock's record (debugging aid) */
+	if (dump) {
+		int pn, mx, my;
+		if (sscanf(dump, "%d,%d,%d", &pn, &mx, &my) == 3 && pn == pic_no) {
+			const E264MbRec *r = c->recs[pd->dst_slot] + my * pd->width_mbs + mx;
+			fprintf(stderr, "pic %d mb(%d,%d) kind %d flags %02x qp %d %d %d chroma_mode %02x i16 %02x coded %08x\n modes", pn, mx, my, r->kind, r->flags, r->qp[0], r->qp[1], r->qp[2], r->chroma_mode, r->i16_mode, r->coded);
+			for (int i = 0; i < 16; i++) fprintf(stderr, " %02x", r->modes[i]);
+			fprintf(stderr, "\n ref_idx"); for (int i = 0; i < 8; i++) fprintf(stderr, " %d", ((int8_t *)r->ref_idx)[i]);
+			fprintf(stderr, " ref_pic"); for (int i = 0; i < 8; i++) fprintf(stderr, " %d", ((int8_t *)r->ref_pic)[i]);
+			for (int l = 0; l < 2; l++) { fprintf(stderr, "\n mv%d", l); for (int i = 0; i < 16; i++) fprintf(stderr, " (%d,%d)", r->mv[l][i][0], r->mv[l][i][1]); }
+			fprintf(stderr, "\n");
+		}
+	}
+	pic_no++;
 	if (!getenv("E264_NULL_RECON")) port_recon_picture(c->frames, pd, c->recs[pd->dst_slot], c->coefs, c->slices);
 	if (!getenv("E264_NULL_RECON")) memcpy(host_out, c->frames + (size_t)pd->dst_slot * pd->frame_bytes, (size_t)pd->frame_bytes);
 	*ticket = 0;

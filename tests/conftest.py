@@ -27,6 +27,9 @@ STREAMS = [
     ("ragged_1x1_intra", 1, 1, "-n 4 -s 19 --gop I --deblock 0"),
     ("ragged_1xN_intra", 1, 9, "-n 4 -s 20 --gop I --deblock 0 --cavlc"),
     ("ragged_2xN",       2, 9, "-n 6 -s 20 --gop IPB --deblock 0 --wp 1"),
+    # 0/255 checkerboard PCM blocks as motion-compensation sources: reproduces the reference's int16 wrap in the
+    # centre half-sample (edge264_inter.c:4-9), found by bench.py's bit-exactness check
+    ("b_pcm_checker",    10, 8, "-n 12 -s 23 --gop IPB --deblock 0 --pcm 250 --pcm-checker --intra-pct 5 --skip-pct 30 --density 10"),
     ("wide_33x2",        33, 2, "-n 6 -s 22 --gop IPB --deblock 0 --wp 2"),
 ]
 

@@ -31,6 +31,7 @@ typedef struct GenState {
 	int32_t next_uid;
 	MbInfo *mbi; int16_t *pool;
 	int t8x8_mode;          /* PPS transform_8x8_mode_flag */
+	int pcm_checker;
 	int wp_p, wp_b;         /* weighted_pred_flag, weighted_bipred_idc */
 	int log2_max_frame_num, log2_max_poc_lsb;
 	int drift[2];           /* per-picture global motion */
@@ -191,6 +192,12 @@ static void gen_choose_intra(GenState *g, SliceCtx *s, MbSyn *m, int base) {
 	if (g->pcm_pm && rnd(g, 1000) < g->pcm_pm) {
 		m->mb_type = base + 25;
 		int v = rnd(g, 256);
+		if (g->pcm_checker) {   /* 0/255 checkerboards: the most extreme input of the 6-tap filters (int16 corner cases of the reference) */
+			/* period-3 pattern H L H | H L H in both directions: every +tap of (1,-5,20,20,-5,1) on 255, every -tap on 0 */
+			int phx = rnd(g, 3), phy = rnd(g, 3);
+			for (int i = 0; i < 256; i++) m->pcm[i] = (uint8_t)((((((i & 15) + phx) % 3 == 1) == ((((i >> 4) + phy) % 3) == 1)) ? 255 : 0) ^ (rnd(g, 32) ? 0 : rnd(g, 4)));
+			for (int i = 256; i < 384; i++) m->pcm[i] = (uint8_t)((((i & 7) + ((i >> 3) & 7) + phx) & 1) ? 255 : 0);
+		} else
 		for (int i = 0; i < 384; i++) m->pcm[i] = (uint8_t)(rnd(g, 8) ? v + rnd(g, 9) - 4 : rnd(g, 256));
 		return;
 	}
@@ -446,6 +453,7 @@ int main(int argc, char **argv) {
 	g->qp0 = argi(argc, argv, "--qp", 28);
 	g->temporal = argf(argc, argv, "--temporal");
 	g->pcm_pm = argi(argc, argv, "--pcm", 2);
+	g->pcm_checker = argf(argc, argv, "--pcm-checker");
 	g->crop_bottom = argi(argc, argv, "--crop-bottom", (g->H * 16) % 1080 == 8 ? 8 : 0);
 	g->level = argi(argc, argv, "--level", g->W * g->H > 36864 ? 62 : g->W * g->H > 8704 ? 51 : 40);
 	g->mvrange = argi(argc, argv, "--mvrange", 24);
