@@ -78,7 +78,7 @@ class ClockSampler(threading.Thread):
                 if o: self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(1.0)   # each nvidia-smi call costs CPU that the parser threads need under the cgroup quota
     def summary(self):
         if not self.rows: return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())

@@ -92,9 +92,9 @@ extern "C" int e264b_create(E264bDevice **out) {
 	c->launches = c->h2d_bytes = c->d2h_bytes = 0;
 	c->dev = dev;
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	for (int i = 0; i < E264_MAX_SLOTS; i++) CK(cudaEventCreateWithFlags(&c->rec_up[i], cudaEventDisableTiming));
-	for (int i = 0; i < NSTAGE; i++) CK(cudaEventCreateWithFlags(&c->st[i].done, cudaEventDisableTiming));
-	for (int i = 0; i < NTICK; i++) CK(cudaEventCreateWithFlags(&c->tick_ev[i], cudaEventDisableTiming));
+	for (int i = 0; i < E264_MAX_SLOTS; i++) CK(cudaEventCreateWithFlags(&c->rec_up[i], cudaEventDisableTiming | cudaEventBlockingSync));
+	for (int i = 0; i < NSTAGE; i++) CK(cudaEventCreateWithFlags(&c->st[i].done, cudaEventDisableTiming | cudaEventBlockingSync));
+	for (int i = 0; i < NTICK; i++) CK(cudaEventCreateWithFlags(&c->tick_ev[i], cudaEventDisableTiming | cudaEventBlockingSync));   /* waiting threads sleep: host CPUs are the scarce resource */
 	cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
 	const char *k = getenv("E264B_KEEP");
 	c->keep = k && atoi(k) != 0;

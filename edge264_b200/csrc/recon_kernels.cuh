@@ -32,7 +32,9 @@ struct PicJob {
 #define WARPS_PER_BLOCK 4
 #define YT_STRIDE 48     /* luma tile row: [15]=left neighbour, [16..31]=samples, [32..39]=top-right */
 #define CT_STRIDE 16     /* chroma tile row: [7]=left neighbour, [8..15]=samples */
-#define WIN_STRIDE 24
+#define WIN_STRIDE 28   /* luma window row: up to 3 alignment bytes + 21 samples, stored as 7 words */
+#define WIN_STRIDE_W WIN_STRIDE
+#define WIN_C_OFF (21 * WIN_STRIDE)
 
 struct __align__(16) WarpSmem {
 	uint4 rec4[12];                 /* the macroblock record */
@@ -42,7 +44,7 @@ struct __align__(16) WarpSmem {
 	int dc[24];                     /* scaled DC: 16 luma (raster over blocks), 4 Cb, 4 Cr */
 	union {
 		int16_t t8[4 * 64];         /* 8x8 transform transpose buffer */
-		uint8_t win[21 * WIN_STRIDE + 2 * 9 * 12];   /* MC windows: luma, Cb, Cr */
+		uint8_t win[21 * WIN_STRIDE + 2 * 9 * 12 + 4];   /* MC windows: luma, Cb, Cr (chroma rows: 12 bytes = 3 words) */
 		int edge[2][28];            /* intra 8x8 filtered reference samples */
 	} u;
 };
@@ -505,24 +507,48 @@ __device__ __noinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264Mb
 	uint8_t *win = ws->u.win;
 	const int X0 = mbx * 16 + x0 + (mvx >> 2) - 2, Y0 = mby * 16 + y0 + (mvy >> 2) - 2;
 	const int CX0 = mbx * 8 + (x0 >> 1) + (mvx >> 3), CY0 = mby * 8 + (y0 >> 1) + (mvy >> 3);
+	/* Interior windows (the common case) are fetched as ALIGNED 32-bit words and stored as words: the window
+	 * then starts `lo`/`co` bytes into its shared-memory rows.  Windows touching the picture border take the
+	 * byte-wise clamped path (8.4.2.2.1 clamps each coordinate). */
+	int lo = 0, co = 0;
+	const bool interior = X0 >= 4 && Y0 >= 0 && X0 + WW + 4 <= W && Y0 + WW <= H && CX0 >= 4 && CY0 >= 0 && CX0 + CWW + 4 <= (W >> 1) && CY0 + CWW <= (H >> 1);
+	if (interior) {
+		lo = X0 & 3; co = CX0 & 3;
+		const int nwl = (lo + WW + 3) >> 2, nwc = (co + CWW + 3) >> 2;          /* words per row: <= 7 luma, <= 3 chroma */
+		const uint8_t *lbase = ref + (size_t)Y0 * J.stride_y + (X0 & ~3);
+		const int rwl = (65536 + nwl - 1) / nwl;
 #pragma unroll 4
-	for (int i = lane; i < NL; i += 32) {
-		int row = (i * rw) >> 16, col = i - row * WW;
-		int xx = min(max(X0 + col, 0), W - 1), yy = min(max(Y0 + row, 0), H - 1);
-		win[row * WIN_STRIDE + col] = __ldg(ref + (size_t)yy * J.stride_y + xx);
-	}
+		for (int i = lane; i < WW * nwl; i += 32) {
+			int row = (i * rwl) >> 16, wd = i - row * nwl;
+			*(uint32_t *)(win + row * WIN_STRIDE_W + wd * 4) = __ldg((const uint32_t *)(lbase + (size_t)row * J.stride_y) + wd);
+		}
+		const uint8_t *cbase = ref + J.plane_y + (size_t)CY0 * J.stride_c + (CX0 & ~3);
+		const int rwc = (65536 + nwc - 1) / nwc, ncw = CWW * nwc;
 #pragma unroll 2
-	for (int i = lane; i < 2 * NC1; i += 32) {
-		int pl = i >= NC1, j = i - pl * NC1, row = (j * rcw) >> 16, col = j - row * CWW;
-		int xx = min(max(CX0 + col, 0), (W >> 1) - 1), yy = min(max(CY0 + row, 0), (H >> 1) - 1);
-		win[21 * WIN_STRIDE + pl * 108 + row * 12 + col] = __ldg(ref + J.plane_y + pl * (J.stride_c >> 1) + (size_t)yy * J.stride_c + xx);
+		for (int i = lane; i < 2 * ncw; i += 32) {
+			int pl = i >= ncw, j = i - pl * ncw, row = (j * rwc) >> 16, wd = j - row * nwc;
+			*(uint32_t *)(win + WIN_C_OFF + pl * 108 + row * 12 + wd * 4) = __ldg((const uint32_t *)(cbase + pl * (J.stride_c >> 1) + (size_t)row * J.stride_c) + wd);
+		}
+	} else {
+#pragma unroll 4
+		for (int i = lane; i < NL; i += 32) {
+			int row = (i * rw) >> 16, col = i - row * WW;
+			int xx = min(max(X0 + col, 0), W - 1), yy = min(max(Y0 + row, 0), H - 1);
+			win[row * WIN_STRIDE_W + col] = __ldg(ref + (size_t)yy * J.stride_y + xx);
+		}
+#pragma unroll 2
+		for (int i = lane; i < 2 * NC1; i += 32) {
+			int pl = i >= NC1, j = i - pl * NC1, row = (j * rcw) >> 16, col = j - row * CWW;
+			int xx = min(max(CX0 + col, 0), (W >> 1) - 1), yy = min(max(CY0 + row, 0), (H >> 1) - 1);
+			win[WIN_C_OFF + pl * 108 + row * 12 + col] = __ldg(ref + J.plane_y + pl * (J.stride_c >> 1) + (size_t)yy * J.stride_c + xx);
+		}
 	}
 	__syncwarp();
 	const int fx = mvx & 3, fy = mvy & 3, sh = S == 16 ? 4 : S == 8 ? 3 : 2;
 #pragma unroll 1
 	for (int p = lane; p < S * S; p += 32) {
 		int x = p & (S - 1), y = p >> sh;
-		int v = mc_luma_sample(win, x, y, fx, fy);
+		int v = mc_luma_sample(win + lo, x, y, fx, fy);
 		int X = x0 + x, Y = y0 + y, i8 = (Y >> 3) * 2 + (X >> 3);
 		YT(X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 0, v, YT(X, Y));
 	}
@@ -530,7 +556,7 @@ __device__ __noinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264Mb
 #pragma unroll 1
 	for (int p = lane; p < 2 * CW * CW; p += 32) {
 		int pl = p >= CW * CW, q = p - pl * CW * CW, x = q & (CW - 1), y = q >> (sh - 1);
-		const uint8_t *cwn = win + 21 * WIN_STRIDE + pl * 108;
+		const uint8_t *cwn = win + WIN_C_OFF + pl * 108 + co;
 		int A = cwn[y * 12 + x], B = cwn[y * 12 + x + 1], C = cwn[(y + 1) * 12 + x], D = cwn[(y + 1) * 12 + x + 1];
 		int v = ((8 - cfx) * (8 - cfy) * A + cfx * (8 - cfy) * B + (8 - cfx) * cfy * C + cfx * cfy * D + 32) >> 6;
 		int X = (x0 >> 1) + x, Y = (y0 >> 1) + y, i8 = (Y >> 2) * 2 + (X >> 2);
@@ -634,7 +660,7 @@ __device__ void recon_mb(WarpSmem *ws, const PicJob &J, uint8_t *dst, int mb, in
 
 /* tickets hand out macroblocks (J.rows_mode == 0: mostly-inter pictures, everything independent runs in
  * parallel) or whole rows (rows_mode == 1: intra pictures, a 2:1 wavefront of row warps) */
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_recon_kernel(PicJob J) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 5) e264_recon_kernel(PicJob J) {
 	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
 	const int lane = threadIdx.x & 31;
 	WarpSmem *ws = &smem[threadIdx.x >> 5];
