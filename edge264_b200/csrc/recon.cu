@@ -26,6 +26,7 @@ extern "C" {
 
 struct Staging {
 	E264MbRec *d_recs; int16_t *d_coefs, *h_coefs; E264SliceRec *d_slices, *h_slices;
+	int16_t *d_resid;            /* residual of the picture in flight: nmb x 384 int16 */
 	cudaEvent_t done; bool busy;
 };
 struct KeptPic { E264PicDesc pd; E264MbRec *d_recs; int16_t *d_coefs; E264SliceRec *d_slices; };
@@ -36,7 +37,7 @@ struct E264bDevice {
 	uint8_t *d_frames;
 	E264MbRec *h_recs[E264_MAX_SLOTS]; cudaEvent_t rec_up[E264_MAX_SLOTS]; bool rec_busy[E264_MAX_SLOTS];
 	Staging st[NSTAGE]; int stage;
-	unsigned *d_sync;            /* [0..1] tickets, [2] err, then flags[2*nmb] */
+	unsigned *d_sync;            /* [0..2] tickets (inter, deblock, intra), [3] err, then flags[2*nmb] */
 	unsigned epoch;
 	cudaEvent_t tick_ev[NTICK]; uint64_t tick_seq;
 	bool keep; std::vector<KeptPic> kept;
@@ -57,7 +58,7 @@ static void free_geometry(E264bDevice *c) {
 	for (int i = 0; i < E264_MAX_SLOTS; i++) { if (c->h_recs[i]) cudaFreeHost(c->h_recs[i]); c->h_recs[i] = NULL; c->rec_busy[i] = false; }
 	for (int i = 0; i < NSTAGE; i++) {
 		Staging *s = &c->st[i];
-		if (s->d_recs) cudaFree(s->d_recs); if (s->d_coefs) cudaFree(s->d_coefs); if (s->d_slices) cudaFree(s->d_slices);
+		if (s->d_recs) cudaFree(s->d_recs); if (s->d_coefs) cudaFree(s->d_coefs); if (s->d_slices) cudaFree(s->d_slices); if (s->d_resid) cudaFree(s->d_resid); s->d_resid = NULL;
 		if (s->h_coefs) cudaFreeHost(s->h_coefs); if (s->h_slices) cudaFreeHost(s->h_slices);
 		s->d_recs = NULL; s->d_coefs = NULL; s->d_slices = NULL; s->h_coefs = NULL; s->h_slices = NULL; s->busy = false;
 	}
@@ -148,6 +149,7 @@ extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots
 		CK(cudaMalloc(&s->d_recs, c->nmb * sizeof(E264MbRec)));
 		CK(cudaMalloc(&s->d_coefs, (size_t)c->coef_cap * 2 + 64));
 		CK(cudaMalloc(&s->d_slices, E264_MAX_SLICES * sizeof(E264SliceRec)));
+		CK(cudaMalloc(&s->d_resid, c->nmb * 384 * sizeof(int16_t)));
 		CK(cudaHostAlloc(&s->h_coefs, (size_t)c->coef_cap * 2 + 64, cudaHostAllocDefault));
 		CK(cudaHostAlloc(&s->h_slices, E264_MAX_SLICES * sizeof(E264SliceRec), cudaHostAllocDefault));
 	}
@@ -187,8 +189,10 @@ static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, const E264MbRec *r
 	J.recs = recs; J.coefs = coefs; J.slices = slices; J.frames = c->d_frames;
 	J.frame_bytes = pd->frame_bytes; J.w_mbs = pd->width_mbs; J.h_mbs = pd->height_mbs;
 	J.stride_y = pd->stride_y; J.stride_c = pd->stride_c; J.plane_y = pd->plane_y; J.dst_slot = pd->dst_slot; J.n_slots = c->n_slots;
-	J.tickets = c->d_sync; J.err = c->d_sync + 2; J.flags = c->d_sync + 4;
+	J.tickets = c->d_sync; J.err = c->d_sync + 3; J.flags = c->d_sync + 4;
+	J.resid = c->st[c->stage].d_resid;
 	J.rows_mode = pd->n_intra * 2 > pd->width_mbs * pd->height_mbs;   /* intra pictures: wavefront of row warps */
+	{ static int wl = -1; if (wl < 0) { const char *e = getenv("E264B_WORDLOAD"); wl = e ? atoi(e) : 1; } J.word_loads = wl; }
 	{ static int force = -2; if (force == -2) { const char *e = getenv("E264B_ROWS"); force = e ? atoi(e) : -1; } if (force >= 0) J.rows_mode = force; }
 	if (c->epoch >= (1u << 20)) {   /* row progress counters encode epoch * 2048 + count: restart before it wraps */
 		cudaStreamSynchronize(c->stream);
@@ -198,16 +202,26 @@ static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, const E264MbRec *r
 	J.epoch = ++c->epoch;
 	return J;
 }
-static int launch_picture(E264bDevice *c, const PicJob &J, int any_deblock) {
+static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd, int with_deblock) {
 	int nmb = J.w_mbs * J.h_mbs;
 	int blocks = (nmb + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
 	int cap = c->sm_count * 8;
 	if (blocks > cap) blocks = cap;
-	CK(cudaMemsetAsync(c->d_sync, 0, 2 * sizeof(unsigned), c->stream));
-	if (J.rows_mode) blocks = (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-	e264_recon_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
-	c->launches++;
-	if (any_deblock) {   /* one warp per macroblock row */
+	static int minb = -1;
+	if (minb < 0) { const char *e = getenv("E264B_MINB"); minb = e ? atoi(e) : 4; }
+	CK(cudaMemsetAsync(c->d_sync, 0, 3 * sizeof(unsigned), c->stream));
+	if (pd->n_coefs > 0) { e264_residual_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++; }
+	if (pd->n_intra < nmb) {
+		if (minb >= 5) e264_inter_kernel<5><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+		else if (minb == 4) e264_inter_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+		else e264_inter_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+		c->launches++;
+	}
+	if (pd->n_intra > 0) {
+		int ib = J.rows_mode ? (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK : blocks;
+		e264_intra_kernel<<<ib, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++;
+	}
+	if (with_deblock) {   /* one warp per macroblock row */
 		int rb = (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
 		e264_deblock_kernel<<<rb, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++;
 	}
@@ -225,7 +239,7 @@ extern "C" int e264b_submit(E264bDevice *c, const E264PicDesc *pd, uint8_t *host
 	if (sl_bytes) CK(cudaMemcpyAsync(s->d_slices, s->h_slices, sl_bytes, cudaMemcpyHostToDevice, c->stream));
 	c->h2d_bytes += rec_bytes + coef_bytes + sl_bytes;
 	PicJob J = make_job(c, pd, s->d_recs, s->d_coefs, s->d_slices);
-	if (launch_picture(c, J, pd->any_deblock)) return -1;
+	if (launch_picture(c, J, pd, pd->any_deblock)) return -1;
 	if (host_out) { CK(cudaMemcpyAsync(host_out, c->d_frames + (size_t)pd->dst_slot * pd->frame_bytes, (size_t)pd->frame_bytes - 16, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (size_t)pd->frame_bytes - 16; }
 	if (c->keep) {
 		KeptPic k; k.pd = *pd;
@@ -262,7 +276,7 @@ extern "C" int e264b_error_flag(E264bDevice *c) {
 	unsigned v = 0;
 	cudaSetDevice(c->dev);
 	cudaStreamSynchronize(c->stream);
-	cudaMemcpy(&v, c->d_sync + 2, sizeof(v), cudaMemcpyDeviceToHost);
+	cudaMemcpy(&v, c->d_sync + 3, sizeof(v), cudaMemcpyDeviceToHost);
 	return (int)v;
 }
 extern "C" void e264b_stats(E264bDevice *c, uint64_t *launches, uint64_t *h2d, uint64_t *d2h) { if (launches) *launches = c->launches; if (h2d) *h2d = c->h2d_bytes; if (d2h) *d2h = c->d2h_bytes; }
@@ -307,7 +321,7 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, float *ms_total, 
 				for (int i = 0; i < n; i++) {
 					KeptPic &kp = cs[i]->kept[k];
 					PicJob J = make_job(cs[i], &kp.pd, kp.d_recs, kp.d_coefs, kp.d_slices);
-					if (launch_picture(cs[i], J, pass == 0 ? kp.pd.any_deblock : 0)) return -1;
+					if (launch_picture(cs[i], J, &kp.pd, pass == 0 ? kp.pd.any_deblock : 0)) return -1;
 				}
 		for (int i = 1; i < n; i++) { CK(cudaEventRecord(ends[i], cs[i]->stream)); CK(cudaStreamWaitEvent(cs[0]->stream, ends[i], 0)); }
 		CK(cudaEventRecord(stop, cs[0]->stream));

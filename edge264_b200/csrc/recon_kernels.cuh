@@ -27,6 +27,8 @@ struct PicJob {
 	unsigned *tickets;    /* [2] zeroed before the picture */
 	unsigned *err;
 	int rows_mode;
+	int word_loads;
+	int16_t *resid;       /* [nmb][384] residual written by e264_residual_kernel (coded macroblocks only) */
 };
 
 #define WARPS_PER_BLOCK 4
@@ -447,50 +449,16 @@ __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { 
 
 /* 8.4.2.2.1 in compact form (code size matters: the whole kernel must stay instruction-cache resident).
  * mc_half: integer / half-sample value at quarter-sample coordinates (qx,qy) in {0,2,4}^2 relative to G. */
-__device__ __noinline__ int mc_half(const uint8_t *g, int qx, int qy, bool vfirst) {
-	const uint8_t *p = g + (qy >> 2) * WIN_STRIDE + (qx >> 2);
-	const bool hx = qx & 2, hy = qy & 2;
-	if (!hx && !hy) return p[0];
-	if (!hy) return clip255((tap6(p[-2], p[-1], p[0], p[1], p[2], p[3]) + 16) >> 5);
-	if (!hx) return clip255((tap6(p[-2 * WIN_STRIDE], p[-WIN_STRIDE], p[0], p[WIN_STRIDE], p[2 * WIN_STRIDE], p[3 * WIN_STRIDE]) + 16) >> 5);
-	/* centre sample: six first-pass sums (vertical first for the i/k positions, horizontal first for f/j/q)
-	 * combined like the reference does in wrapping int16 (edge264_inter.c:4-9) — equal to (j1+512)>>10 except
-	 * when the inner sum overflows on extreme checkerboards, which must be reproduced for bit-exactness */
-	int t[6];
-	const int sa = vfirst ? 1 : WIN_STRIDE, sb = vfirst ? WIN_STRIDE : 1;   /* sa: step between the six sums, sb: step inside one */
-#pragma unroll
-	for (int k = 0; k < 6; k++) { const uint8_t *r = p + (k - 2) * sa; t[k] = tap6(r[-2 * sb], r[-sb], r[0], r[sb], r[2 * sb], r[3 * sb]); }
-	int af = t[0] + t[5], be = t[1] + t[4], cd = t[2] + t[3];
-	int t16 = (short)(((af - be) >> 2) + (cd - be));
-	return clip255(((t16 >> 2) + cd + 32) >> 6);
-}
-/* luma sample at window position (x,y) (window origin = integer position - 2), fraction (fx,fy) */
-__device__ __forceinline__ int mc_luma_sample(const uint8_t *w, int x, int y, int fx, int fy) {
-	const uint8_t *g = w + (y + 2) * WIN_STRIDE + x + 2;
-	const bool vfirst = fx & 1;
-	if (!((fx | fy) & 1)) return mc_half(g, fx, fy, vfirst);
-	int ax, ay, bx, by;
-	if (!(fy & 1)) { ax = fx - 1; ay = fy; bx = fx + 1; by = fy; }
-	else if (!(fx & 1)) { ax = fx; ay = fy - 1; bx = fx; by = fy + 1; }
-	else { ax = 2; ay = fy == 1 ? 0 : 4; bx = fx == 1 ? 0 : 4; by = 2; }
-	return (mc_half(g, ax, ay, vfirst) + mc_half(g, bx, by, vfirst) + 1) >> 1;
-}
-
 __device__ __forceinline__ int wp_uni(int p, int w, int o, int logwd) { return clip255((logwd >= 1 ? ((p * w + (1 << (logwd - 1))) >> logwd) : p * w) + o); }
 __device__ __forceinline__ int wp_bi(int p0, int p1, int w0, int w1, int o0, int o1, int logwd) { return clip255(((p0 * w0 + p1 * w1 + (1 << logwd)) >> (logwd + 1)) + ((o0 + o1 + 1) >> 1)); }
 
-/* combine the prediction `p` of list `l` for a sample of 8x8 block i8 / plane pl with what the tile holds (list 0 pass) */
-__device__ __noinline__ int weight_sample(const E264MbRec *r, const E264SliceRec *sr, int l, int i8, int pl, int p, int q) {
-	int r0 = r->ref_idx[0][i8], r1 = r->ref_idx[1][i8];
-	int mode = sr->wp_mode, logwd = pl ? sr->chroma_log2_wd : sr->luma_log2_wd;
-	if (l == 1 && r0 >= 0) {   /* second pass of a bi-predicted block: q = list-0 prediction */
-		if (mode == WP_EXPLICIT) return wp_bi(q, p, sr->wp_w[0][r0 & 15][pl], sr->wp_w[1][r1 & 15][pl], sr->wp_o[0][r0 & 15][pl], sr->wp_o[1][r1 & 15][pl], logwd);
-		if (mode == WP_IMPLICIT) { int w1 = sr->implicit_w1[r0 & 15][r1 & 15]; return wp_bi(q, p, 64 - w1, w1, 0, 0, 5); }
-		return (q + p + 1) >> 1;
-	}
-	if (l == 0 && r1 >= 0) return p;   /* first pass of a bi-predicted block: stored unweighted */
-	if (mode == WP_EXPLICIT) { int ri = (l ? r1 : r0) & 15; return wp_uni(p, sr->wp_w[l][ri][pl], sr->wp_o[l][ri][pl], logwd); }
-	return p;
+/* 8.4.2.3 weighted sample prediction of one sample; wm: 0 store, 1 default average, 2 explicit uni, 3 bi (explicit/implicit).
+ * Kept out of line: the kernel must stay within the 32 KB L1.5 instruction cache. */
+__device__ __noinline__ int wblend(int q, int v, int wm, int w0, int w1, int o, int lw) {
+	if (wm == 0) return v;
+	if (wm == 1) return (q + v + 1) >> 1;
+	if (wm == 2) return clip255((lw >= 1 ? ((v * w1 + (1 << (lw - 1))) >> lw) : v * w1) + o);
+	return clip255(((q * w0 + v * w1 + (1 << lw)) >> (lw + 1)) + o);
 }
 
 /* motion-compensate the SxS square at (x0,y0) (luma units, inside the MB) of list l.  The window loads
@@ -511,7 +479,7 @@ __device__ __noinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264Mb
 	 * then starts `lo`/`co` bytes into its shared-memory rows.  Windows touching the picture border take the
 	 * byte-wise clamped path (8.4.2.2.1 clamps each coordinate). */
 	int lo = 0, co = 0;
-	const bool interior = X0 >= 4 && Y0 >= 0 && X0 + WW + 4 <= W && Y0 + WW <= H && CX0 >= 4 && CY0 >= 0 && CX0 + CWW + 4 <= (W >> 1) && CY0 + CWW <= (H >> 1);
+	const bool interior = J.word_loads && X0 >= 4 && Y0 >= 0 && X0 + WW + 4 <= W && Y0 + WW <= H && CX0 >= 4 && CY0 >= 0 && CX0 + CWW + 4 <= (W >> 1) && CY0 + CWW <= (H >> 1);
 	if (interior) {
 		lo = X0 & 3; co = CX0 & 3;
 		const int nwl = (lo + WW + 3) >> 2, nwc = (co + CWW + 3) >> 2;          /* words per row: <= 7 luma, <= 3 chroma */
@@ -530,13 +498,13 @@ __device__ __noinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264Mb
 			*(uint32_t *)(win + WIN_C_OFF + pl * 108 + row * 12 + wd * 4) = __ldg((const uint32_t *)(cbase + pl * (J.stride_c >> 1) + (size_t)row * J.stride_c) + wd);
 		}
 	} else {
-#pragma unroll 4
+#pragma unroll 1
 		for (int i = lane; i < NL; i += 32) {
 			int row = (i * rw) >> 16, col = i - row * WW;
 			int xx = min(max(X0 + col, 0), W - 1), yy = min(max(Y0 + row, 0), H - 1);
 			win[row * WIN_STRIDE_W + col] = __ldg(ref + (size_t)yy * J.stride_y + xx);
 		}
-#pragma unroll 2
+#pragma unroll 1
 		for (int i = lane; i < 2 * NC1; i += 32) {
 			int pl = i >= NC1, j = i - pl * NC1, row = (j * rcw) >> 16, col = j - row * CWW;
 			int xx = min(max(CX0 + col, 0), (W >> 1) - 1), yy = min(max(CY0 + row, 0), (H >> 1) - 1);
@@ -544,24 +512,74 @@ __device__ __noinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264Mb
 		}
 	}
 	__syncwarp();
+	/* weighting of this rectangle is uniform (callers guarantee one 8x8 reference pair per rectangle):
+	 * wm 0 store, 1 default average with the list-0 pass, 2 explicit uni, 3 explicit/implicit bi */
+	const int i8r = ((y0 >> 3) << 1) | (x0 >> 3);
+	const int r0 = r->ref_idx[0][i8r], r1 = r->ref_idx[1][i8r];
+	int wm = 0, w0[3] = {0, 0, 0}, w1[3] = {0, 0, 0}, oo[3] = {0, 0, 0}, lw[3] = {0, 0, 0};
+	if (l == 1 && r0 >= 0) {
+		if (sr->wp_mode == WP_EXPLICIT) {
+			wm = 3;
+			for (int c = 0; c < 3; c++) { w0[c] = sr->wp_w[0][r0 & 15][c]; w1[c] = sr->wp_w[1][r1 & 15][c]; oo[c] = (sr->wp_o[0][r0 & 15][c] + sr->wp_o[1][r1 & 15][c] + 1) >> 1; lw[c] = c ? sr->chroma_log2_wd : sr->luma_log2_wd; }
+		} else if (sr->wp_mode == WP_IMPLICIT) {
+			wm = 3;
+			int iw = sr->implicit_w1[r0 & 15][r1 & 15];
+			for (int c = 0; c < 3; c++) { w0[c] = 64 - iw; w1[c] = iw; oo[c] = 0; lw[c] = 5; }
+		} else wm = 1;
+	} else if (!(l == 0 && r1 >= 0) && sr->wp_mode == WP_EXPLICIT) {
+		wm = 2;
+		int ri = (l ? r1 : r0) & 15;
+		for (int c = 0; c < 3; c++) { w1[c] = sr->wp_w[l][ri][c]; oo[c] = sr->wp_o[l][ri][c]; lw[c] = c ? sr->chroma_log2_wd : sr->luma_log2_wd; }
+	}
+#define WSTORE(dst, v, c) (dst) = (uint8_t)wblend((dst), (v), wm, w0[c], w1[c], oo[c], lw[c])
 	const int fx = mvx & 3, fy = mvy & 3, sh = S == 16 ? 4 : S == 8 ? 3 : 2;
+	const uint8_t *wl = win + lo + 2 * WIN_STRIDE + 2;
+	/* one loop per class of fractional position: the branch is uniform for the rectangle */
+#define HSUM(g) tap6((g)[-2], (g)[-1], (g)[0], (g)[1], (g)[2], (g)[3])
+#define VSUM(g) tap6((g)[-2 * WIN_STRIDE], (g)[-WIN_STRIDE], (g)[0], (g)[WIN_STRIDE], (g)[2 * WIN_STRIDE], (g)[3 * WIN_STRIDE])
+#define LUMA_LOOP(EXPR) _Pragma("unroll 1") for (int p = lane; p < S * S; p += 32) { int x = p & (S - 1), y = p >> sh; const uint8_t *g = wl + y * WIN_STRIDE + x; int v = (EXPR); WSTORE(YT(x0 + x, y0 + y), v, 0); }
+	if (!(fx | fy)) { LUMA_LOOP(g[0]) }
+	else if (!fy) {   /* a, b, c */
+		const int o2 = fx == 3;
+		if (fx == 2) { LUMA_LOOP(clip255((HSUM(g) + 16) >> 5)) } else { LUMA_LOOP((clip255((HSUM(g) + 16) >> 5) + g[o2] + 1) >> 1) }
+	} else if (!fx) {   /* d, h, n */
+		const int o2 = fy == 3 ? WIN_STRIDE : 0;
+		if (fy == 2) { LUMA_LOOP(clip255((VSUM(g) + 16) >> 5)) } else { LUMA_LOOP((clip255((VSUM(g) + 16) >> 5) + g[o2] + 1) >> 1) }
+	} else if ((fx & 1) && (fy & 1)) {   /* e, g, p, r: horizontal half of row y or y+1, vertical half of column x or x+1 */
+		const int ro = fy == 3 ? WIN_STRIDE : 0, cofs = fx == 3;
+		LUMA_LOOP((clip255((HSUM(g + ro) + 16) >> 5) + clip255((VSUM(g + cofs) + 16) >> 5) + 1) >> 1)
+	} else {   /* f, i, j, k, q: centre sample, combined like the reference (see mc_centre) */
+		const bool vfirst = fx & 1;
+		const int sa = vfirst ? 1 : WIN_STRIDE, sb = vfirst ? WIN_STRIDE : 1;
+		const int second = fx == 2 ? (fy == 2 ? 0 : 1) : 2;          /* 0 none (j), 1 horizontal half b/s, 2 vertical half h/m */
+		const int so = fx == 2 ? (fy == 3 ? WIN_STRIDE : 0) : (fx == 3 ? 1 : 0);
 #pragma unroll 1
-	for (int p = lane; p < S * S; p += 32) {
-		int x = p & (S - 1), y = p >> sh;
-		int v = mc_luma_sample(win + lo, x, y, fx, fy);
-		int X = x0 + x, Y = y0 + y, i8 = (Y >> 3) * 2 + (X >> 3);
-		YT(X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 0, v, YT(X, Y));
+		for (int p = lane; p < S * S; p += 32) {
+			int x = p & (S - 1), y = p >> sh; const uint8_t *g = wl + y * WIN_STRIDE + x;
+			int t[6];
+#pragma unroll
+			for (int k = 0; k < 6; k++) { const uint8_t *q = g + (k - 2) * sa; t[k] = tap6(q[-2 * sb], q[-sb], q[0], q[sb], q[2 * sb], q[3 * sb]); }
+			int af = t[0] + t[5], be = t[1] + t[4], cd = t[2] + t[3];
+			int t16 = (short)(((af - be) >> 2) + (cd - be));
+			int v = clip255(((t16 >> 2) + cd + 32) >> 6);
+			if (second == 1) v = (v + clip255((HSUM(g + so) + 16) >> 5) + 1) >> 1;
+			else if (second == 2) v = (v + clip255((VSUM(g + so) + 16) >> 5) + 1) >> 1;
+			WSTORE(YT(x0 + x, y0 + y), v, 0);
+		}
 	}
 	const int cfx = mvx & 7, cfy = mvy & 7;
+	const int cA = (8 - cfx) * (8 - cfy), cB = cfx * (8 - cfy), cC = (8 - cfx) * cfy, cD = cfx * cfy;
 #pragma unroll 1
 	for (int p = lane; p < 2 * CW * CW; p += 32) {
 		int pl = p >= CW * CW, q = p - pl * CW * CW, x = q & (CW - 1), y = q >> (sh - 1);
-		const uint8_t *cwn = win + WIN_C_OFF + pl * 108 + co;
-		int A = cwn[y * 12 + x], B = cwn[y * 12 + x + 1], C = cwn[(y + 1) * 12 + x], D = cwn[(y + 1) * 12 + x + 1];
-		int v = ((8 - cfx) * (8 - cfy) * A + cfx * (8 - cfy) * B + (8 - cfx) * cfy * C + cfx * cfy * D + 32) >> 6;
-		int X = (x0 >> 1) + x, Y = (y0 >> 1) + y, i8 = (Y >> 2) * 2 + (X >> 2);
-		CT(pl, X, Y) = (uint8_t)weight_sample(r, sr, l, i8, 1 + pl, v, CT(pl, X, Y));
+		const uint8_t *cwn = win + WIN_C_OFF + pl * 108 + co + y * 12 + x;
+		int v = (cA * cwn[0] + cB * cwn[1] + cC * cwn[12] + cD * cwn[13] + 32) >> 6;
+		if (pl) WSTORE(CT(1, (x0 >> 1) + x, (y0 >> 1) + y), v, 2); else WSTORE(CT(0, (x0 >> 1) + x, (y0 >> 1) + y), v, 1);
 	}
+#undef LUMA_LOOP
+#undef HSUM
+#undef VSUM
+#undef WSTORE
 	__syncwarp();
 }
 
@@ -594,55 +612,117 @@ __device__ __noinline__ void inter_predict(WarpSmem *ws, const PicJob &J, const 
 /* ------------------------------------------------------------------------------------------ */
 /* reconstruction kernel                                                                        */
 /* ------------------------------------------------------------------------------------------ */
-/* Reconstruct one macroblock.  rows_mode: the calling warp walks a whole row, so A and D are its own
- * previous macroblock (samples carried over in shared memory) and only C (or B at the row's end) is waited for. */
-__device__ void recon_mb(WarpSmem *ws, const PicJob &J, uint8_t *dst, int mb, int mbx, int mby, int lane, bool rows_mode) {
+/* load the macroblock's residual (written by e264_residual_kernel) into ws->res, or clear it */
+__device__ __forceinline__ void fetch_residual(WarpSmem *ws, const PicJob &J, const E264MbRec *r, int mb, int lane) {
+	const uint4 *src = (const uint4 *)(J.resid + (size_t)mb * 384);
+	const bool on = r->coded != 0;
+	uint4 z = make_uint4(0, 0, 0, 0);
+	((uint4 *)ws->res)[lane] = on ? __ldg(src + lane) : z;
+	if (lane < 16) ((uint4 *)ws->res)[32 + lane] = on ? __ldg(src + 32 + lane) : z;
+	__syncwarp();
+}
+
+__device__ __forceinline__ void store_mb(WarpSmem *ws, const PicJob &J, uint8_t *Y, uint8_t *C, int lane) {
+	const int cpl = J.stride_c >> 1;
+	if (lane < 16) *(uint4 *)(Y + (size_t)lane * J.stride_y) = *(const uint4 *)&YT(0, lane);
+	else { int j = lane - 16, pl = j >> 3, row = j & 7; *(uint2 *)(C + pl * cpl + (size_t)row * J.stride_c) = *(const uint2 *)&CT(pl, 0, row); }
+}
+
+/* ---- kernel 1: inverse quantisation + inverse transforms of every coded macroblock (no dependencies) ---- */
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_residual_kernel(PicJob J) {
+	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
+	const int lane = threadIdx.x & 31;
+	WarpSmem *ws = &smem[threadIdx.x >> 5];
+	const int nmb = J.w_mbs * J.h_mbs;
+	for (int mb = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); mb < nmb; mb += gridDim.x * WARPS_PER_BLOCK) {
+		if (lane < 12) ws->rec4[lane] = __ldg((const uint4 *)(J.recs + mb) + lane);
+		__syncwarp();
+		const E264MbRec *r = (const E264MbRec *)ws->rec4;
+		if (r->coded != 0 && r->kind != MBK_IPCM) {
+			residual_stage(ws, r, J.slices + r->slice_idx, J.coefs, lane);
+			uint4 *dst = (uint4 *)(J.resid + (size_t)mb * 384);
+			dst[lane] = ((const uint4 *)ws->res)[lane];
+			if (lane < 16) dst[32 + lane] = ((const uint4 *)ws->res)[32 + lane];
+		}
+		__syncwarp();
+	}
+}
+
+/* ---- kernel 2: inter macroblocks: motion compensation + weighting + residual (no dependencies) ---- */
+template <int MINB>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) e264_inter_kernel(PicJob J) {
+	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
+	const int lane = threadIdx.x & 31;
+	WarpSmem *ws = &smem[threadIdx.x >> 5];
+	const int nmb = J.w_mbs * J.h_mbs;
+	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
+	for (;;) {
+		unsigned t = 0;
+		if (lane == 0) t = atomicAdd(J.tickets, 1u);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t >= (unsigned)nmb) break;
+		const int mb = (int)t, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
+		if (J.recs[mb].kind != MBK_INTER) continue;
+		if (lane < 12) ws->rec4[lane] = __ldg((const uint4 *)(J.recs + mb) + lane);
+		__syncwarp();
+		const E264MbRec *r = (const E264MbRec *)ws->rec4;
+		fetch_residual(ws, J, r, mb, lane);
+		inter_predict(ws, J, r, J.slices + r->slice_idx, mbx, mby, lane);
+		store_mb(ws, J, dst + (size_t)(mby * 16) * J.stride_y + mbx * 16, dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8, lane);
+		if (lane == 0) J.flags[mb] = J.epoch;     /* visible to the intra kernel through the kernel boundary */
+		__syncwarp();
+	}
+}
+
+/* ---- kernel 3: intra (and I_PCM) macroblocks, in dependency order ----
+ * rows_mode == 0 (few intra macroblocks): tickets over macroblocks, each intra one waits for A, D, B, C
+ * (inter neighbours were flagged by kernel 2).  rows_mode == 1 (intra pictures): one warp walks a row, the left
+ * neighbour's column stays in shared memory, only C (or B at the row's end) is waited for. */
+__device__ __forceinline__ void intra_mb(WarpSmem *ws, const PicJob &J, uint8_t *dst, int mb, int mbx, int mby, int lane, bool rows_mode) {
 	if (lane < 12) ws->rec4[lane] = __ldg((const uint4 *)(J.recs + mb) + lane);
 	__syncwarp();
 	const E264MbRec *r = (const E264MbRec *)ws->rec4;
-	const E264SliceRec *sr = J.slices + r->slice_idx;
 	uint8_t *Y = dst + (size_t)(mby * 16) * J.stride_y + mbx * 16;
 	uint8_t *C = dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8;
 	const int kind = r->kind, cpl = J.stride_c >> 1;
-	if (kind == MBK_IPCM) {
+	if (kind == MBK_INTER) {   /* rows mode only: already reconstructed; pick its right column up for the carry */
+		if (lane < 16) YT(15, lane) = __ldcg(Y + (size_t)lane * J.stride_y + 15);
+		else { int j = lane - 16; CT(j >> 3, 7, j & 7) = __ldcg(C + (j >> 3) * cpl + (size_t)(j & 7) * J.stride_c + 7); }
+		__syncwarp();
+	} else if (kind == MBK_IPCM) {
 		const uint8_t *s = (const uint8_t *)(J.coefs + r->coef_off);
 		if (lane < 16) *(uint4 *)&YT(0, lane) = __ldg((const uint4 *)s + lane);
 		else { int j = lane - 16; *(uint2 *)&CT(j >> 3, 0, j & 7) = __ldg((const uint2 *)(s + 256) + j); }
 		__syncwarp();
+		store_mb(ws, J, Y, C, lane);
 	} else {
-		residual_stage(ws, r, sr, J.coefs, lane);
-		if (kind != MBK_INTER) {
-			bool ok = true;
-			if (lane == 0) {
-				if (!rows_mode) {   /* A, D, B, C: inter neighbours finish without waiting, so each one is checked */
-					if (mbx > 0) ok = wait_flag(J.flags, mb - 1, J.epoch, J.err);
-					if (ok && mby > 0 && mbx > 0) ok = wait_flag(J.flags, mb - J.w_mbs - 1, J.epoch, J.err);
-					if (ok && mby > 0) ok = wait_flag(J.flags, mb - J.w_mbs, J.epoch, J.err);
-				}
-				if (ok && mby > 0) ok = wait_flag(J.flags, mbx < J.w_mbs - 1 ? mb - J.w_mbs + 1 : mb - J.w_mbs, J.epoch, J.err);
-				__threadfence();
+		fetch_residual(ws, J, r, mb, lane);
+		bool ok = true;
+		if (lane == 0) {
+			if (!rows_mode) {
+				if (mbx > 0) ok = wait_flag(J.flags, mb - 1, J.epoch, J.err);
+				if (ok && mby > 0 && mbx > 0) ok = wait_flag(J.flags, mb - J.w_mbs - 1, J.epoch, J.err);
+				if (ok && mby > 0) ok = wait_flag(J.flags, mb - J.w_mbs, J.epoch, J.err);
 			}
-			__syncwarp();
-			const bool up = mby > 0, left = mbx > 0, carried = rows_mode && left;
-			if (up) {
-				int x = lane - 1;   /* -1..23 */
-				if (x < 24 && (x >= 0 || left) && (x < 16 || mbx < J.w_mbs - 1)) YT(x, -1) = __ldcg(Y - J.stride_y + x);   /* the corner is always fetched: the previous macroblock may not have loaded its top row (PCM, inter) */
-				if (lane < 18) { int pl = lane / 9, cx = lane % 9 - 1; if (cx >= 0 || left) CT(pl, cx, -1) = __ldcg(C + pl * cpl - J.stride_c + cx); }
-			}
-			if (left && !carried) {
-				if (lane < 16) YT(-1, lane) = __ldcg(Y + (size_t)lane * J.stride_y - 1);
-				else { int j = lane - 16, pl = j >> 3, row = j & 7; CT(pl, -1, row) = __ldcg(C + pl * cpl + (size_t)row * J.stride_c - 1); }
-			}
-			__syncwarp();
-			intra_luma(ws, r, lane);
-			intra_chroma(ws, r, lane);
-		} else {
-			inter_predict(ws, J, r, sr, mbx, mby, lane);
+			if (ok && mby > 0) ok = wait_flag(J.flags, mbx < J.w_mbs - 1 ? mb - J.w_mbs + 1 : mb - J.w_mbs, J.epoch, J.err);
+			__threadfence();
 		}
+		__syncwarp();
+		const bool up = mby > 0, left = mbx > 0, carried = rows_mode && left;
+		if (up) {
+			int x = lane - 1;   /* -1..23; the corner is always fetched (the previous macroblock may not have loaded its top row) */
+			if (x < 24 && (x >= 0 || left) && (x < 16 || mbx < J.w_mbs - 1)) YT(x, -1) = __ldcg(Y - J.stride_y + x);
+			if (lane < 18) { int pl = lane / 9, cx = lane % 9 - 1; if (cx >= 0 || left) CT(pl, cx, -1) = __ldcg(C + pl * cpl - J.stride_c + cx); }
+		}
+		if (left && !carried) {
+			if (lane < 16) YT(-1, lane) = __ldcg(Y + (size_t)lane * J.stride_y - 1);
+			else { int j = lane - 16, pl = j >> 3, row = j & 7; CT(pl, -1, row) = __ldcg(C + pl * cpl + (size_t)row * J.stride_c - 1); }
+		}
+		__syncwarp();
+		intra_luma(ws, r, lane);
+		intra_chroma(ws, r, lane);
+		store_mb(ws, J, Y, C, lane);
 	}
-	/* 128-bit row stores of the reconstructed macroblock */
-	if (lane < 16) *(uint4 *)(Y + (size_t)lane * J.stride_y) = *(const uint4 *)&YT(0, lane);
-	else { int j = lane - 16, pl = j >> 3, row = j & 7; *(uint2 *)(C + pl * cpl + (size_t)row * J.stride_c) = *(const uint2 *)&CT(pl, 0, row); }
 	__syncwarp();
 	if (rows_mode) {   /* right-most column becomes the next macroblock's left neighbour */
 		uint8_t v = 0;
@@ -654,13 +734,11 @@ __device__ void recon_mb(WarpSmem *ws, const PicJob &J, uint8_t *dst, int mb, in
 		else if (lane < 24) CT(0, -1, lane - 16) = v;
 		if (lane < 8) CT(1, -1, lane) = v2;
 	}
-	if (lane == 0) { __threadfence(); *(volatile unsigned *)(J.flags + mb) = J.epoch; }
+	if (kind != MBK_INTER && lane == 0) { __threadfence(); *(volatile unsigned *)(J.flags + mb) = J.epoch; }
 	__syncwarp();
 }
 
-/* tickets hand out macroblocks (J.rows_mode == 0: mostly-inter pictures, everything independent runs in
- * parallel) or whole rows (rows_mode == 1: intra pictures, a 2:1 wavefront of row warps) */
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 5) e264_recon_kernel(PicJob J) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_intra_kernel(PicJob J) {
 	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
 	const int lane = threadIdx.x & 31;
 	WarpSmem *ws = &smem[threadIdx.x >> 5];
@@ -668,14 +746,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 5) e264_recon_kernel(Pic
 	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
 	for (;;) {
 		unsigned t = 0;
-		if (lane == 0) t = atomicAdd(J.tickets, 1u);
+		if (lane == 0) t = atomicAdd(J.tickets + 2, 1u);
 		t = __shfl_sync(0xffffffffu, t, 0);
 		if (J.rows_mode) {
 			if (t >= (unsigned)J.h_mbs) break;
-			for (int mbx = 0; mbx < J.w_mbs; mbx++) recon_mb(ws, J, dst, (int)t * J.w_mbs + mbx, mbx, (int)t, lane, true);
+			for (int mbx = 0; mbx < J.w_mbs; mbx++) intra_mb(ws, J, dst, (int)t * J.w_mbs + mbx, mbx, (int)t, lane, true);
 		} else {
 			if (t >= (unsigned)nmb) break;
-			recon_mb(ws, J, dst, (int)t, (int)t % J.w_mbs, (int)t / J.w_mbs, lane, false);
+			if (J.recs[t].kind == MBK_INTER) continue;
+			intra_mb(ws, J, dst, (int)t, (int)t % J.w_mbs, (int)t / J.w_mbs, lane, false);
 		}
 	}
 }

@@ -58,7 +58,8 @@ def test_replay_reproduces_decode(workdir):
         devs = (ctypes.c_void_p * 1)(dev); ms = ctypes.c_float(); nl = ctypes.c_uint64()
         assert core.e264b_replay(devs, 1, 2, ctypes.byref(ms), None, ctypes.byref(nl)) == 0
         assert [core.e264b_slot_hash(dev, s) for s in range(4)] == before
-        assert nl.value == 2 * 2 * frames[0] and core.e264b_error_flag(dev) == 0
+        # per picture: residual (if coded), inter (if any), intra (if any), deblock -> 2..4 launches, replayed twice
+        assert 2 * 2 * frames[0] <= nl.value <= 2 * 4 * frames[0] and core.e264b_error_flag(dev) == 0
         bench.e264bench_free(decs, 1)
     finally:
         os.environ["E264B_KEEP"] = "0"
