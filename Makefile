@@ -3,7 +3,7 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 CC ?= gcc
 CSRC := edge264_b200/csrc
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wno-unused-function
-CFLAGS := -std=gnu11 -O3 -fPIC -Wall -Wno-unused-function -Wno-unused-variable -Wno-unused-but-set-variable
+CFLAGS := -std=gnu11 -O3 -march=x86-64-v3 -fPIC -Wall -Wno-unused-function -Wno-unused-variable -Wno-unused-but-set-variable
 LIB := edge264_b200/libedge264_b200.so
 
 all: $(LIB) tools/gen264 tools/b200_decode tools/libe264bench.so oracle

@@ -61,7 +61,7 @@ static inline CabacRegs cabac_regs_load(const CabacDec *c) { CabacRegs r = {c->v
 static inline void cabac_regs_store(CabacDec *c, const CabacRegs *r) { c->val = r->val; c->range = r->range; c->avail = r->avail; c->p = r->p; }
 
 static inline void cabac_r_refill(CabacRegs *r) {
-	if (r->avail <= CABAC_POS - 32) {
+	if (__builtin_expect(r->avail <= CABAC_POS - 32, 0)) {
 		uint32_t w; memcpy(&w, r->p, 4); r->p += 4;
 		r->val |= (uint64_t)__builtin_bswap32(w) << (CABAC_POS - 32 - r->avail);
 		r->avail += 32;

@@ -641,7 +641,7 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 		if (d->be->acquire_staging(d->be_ctx, slot, &cp->recs, &d->coefs, &cap, &d->slices)) return ENOMEM;
 		d->coef_cap = cap; d->n_coefs = 0; d->n_slices = 0; d->mbs_done = 0; d->n_intra = 0; d->any_deblock = 0;
 		memset(d->mbi, 0, (size_t)d->w_mbs * d->h_mbs * sizeof(MbInfo));
-		memset(cp->recs, 0, (size_t)d->w_mbs * d->h_mbs * sizeof(E264MbRec));
+		/* records need no clearing: every macroblock of a complete picture rewrites its own (sx_one_mb) */
 		d->slice_counter = 0;
 
 		/* IDR / MMCO5: every earlier picture leaves in output order first (reference headers.c:632, 680) */

@@ -64,20 +64,25 @@ static void sx_mvpred(SliceCtx *s, int list, int x4, int y4, int w4, int ref, in
 	mvp[1] = sx_median(A.mv[1], B.mv[1], C.mv[1]);
 }
 
+/* z-order makes 16x16, 16x8 and 8x8 partitions contiguous runs of the per-4x4 arrays */
 static inline void sx_fill_mv(SliceCtx *s, int list, int x4, int y4, int w4, int h4, int mvx, int mvy) {
-	for (int y = y4; y < y4 + h4; y++) for (int x = x4; x < x4 + w4; x++) {
-		int z = e264_blk_z(x, y);
-		s->rec->mv[list][z][0] = (int16_t)mvx; s->rec->mv[list][z][1] = (int16_t)mvy;
-	}
+	uint32_t v = (uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16);
+	uint32_t *dst = (uint32_t *)s->rec->mv[list];
+	if (w4 == 4 && h4 == 4) { for (int z = 0; z < 16; z++) dst[z] = v; return; }
+	if (w4 == 4 && h4 == 2) { int z0 = y4 * 4; for (int z = z0; z < z0 + 8; z++) dst[z] = v; return; }
+	if (w4 == 2 && h4 == 2) { int z0 = e264_blk_z(x4, y4); dst[z0] = dst[z0 + 1] = dst[z0 + 2] = dst[z0 + 3] = v; return; }
+	for (int y = y4; y < y4 + h4; y++) for (int x = x4; x < x4 + w4; x++) dst[e264_blk_z(x, y)] = v;
 }
 static inline void sx_fill_mvd(SliceCtx *s, int list, int x4, int y4, int w4, int h4, int dx, int dy) {
 	int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
 	if (ax > 255) ax = 255;
 	if (ay > 255) ay = 255;
-	for (int y = y4; y < y4 + h4; y++) for (int x = x4; x < x4 + w4; x++) {
-		int z = e264_blk_z(x, y);
-		s->cur->mvd[list][z][0] = (uint8_t)ax; s->cur->mvd[list][z][1] = (uint8_t)ay;
-	}
+	uint16_t v = (uint16_t)(ax | (ay << 8));
+	uint16_t *dst = (uint16_t *)s->cur->mvd[list];
+	if (w4 == 4 && h4 == 4) { for (int z = 0; z < 16; z++) dst[z] = v; return; }
+	if (w4 == 4 && h4 == 2) { int z0 = y4 * 4; for (int z = z0; z < z0 + 8; z++) dst[z] = v; return; }
+	if (w4 == 2 && h4 == 2) { int z0 = e264_blk_z(x4, y4); dst[z0] = dst[z0 + 1] = dst[z0 + 2] = dst[z0 + 3] = v; return; }
+	for (int y = y4; y < y4 + h4; y++) for (int x = x4; x < x4 + w4; x++) dst[e264_blk_z(x, y)] = v;
 }
 static inline void sx_set_ref(SliceCtx *s, int list, int i8, int ref) {
 	s->rec->ref_idx[list][i8] = (int8_t)ref;

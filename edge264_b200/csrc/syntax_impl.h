@@ -320,22 +320,25 @@ static inline __attribute__((always_inline)) int residual_block_cabac_cat(SliceC
 #endif
 	CR_BEGIN
 	if (has_cbf && !AE_R(h264_cat_cbf[cat] + cbf_inc, ENCV(last_e >= 0))) { CR_OUT return 0; }
-	uint8_t sig[64]; int nsig = 0;
+	uint64_t sigmask = 0;
 	const int sig_base = h264_cat_sig[cat], last_base = h264_cat_last[cat];
 	int k;
 	for (k = 0; k < n - 1; k++) {
 		const int si = cat == 5 ? h264_sig8x8_inc[k] : cat == 3 ? (k < 2 ? k : 2) : k;
 		if (AE_R(sig_base + si, ENCV(blk[scan[k]] != 0))) {
-			sig[nsig++] = (uint8_t)k;
+			sigmask |= (uint64_t)1 << k;
 			const int li = cat == 5 ? h264_last8x8_inc[k] : cat == 3 ? (k < 2 ? k : 2) : k;
 			if (AE_R(last_base + li, ENCV(k == last_e))) break;
 		}
 	}
-	if (k == n - 1) sig[nsig++] = (uint8_t)(n - 1);
+	if (k == n - 1) sigmask |= (uint64_t)1 << (n - 1);
+	const int nsig = __builtin_popcountll(sigmask);
 	const int abs_base = h264_cat_abs[cat], cap = 4 - (cat == 3);
 	int gt1 = 0, eq1 = 0;
-	for (int i = nsig - 1; i >= 0; i--) {
-		int16_t *dst = blk + scan[sig[i]];
+	while (sigmask) {
+		const int pos = 63 - __builtin_clzll(sigmask);
+		sigmask &= ~((uint64_t)1 << pos);
+		int16_t *dst = blk + scan[pos];
 		int a = ENCV((*dst < 0 ? -*dst : *dst) - 1);
 		int absm1;
 		if (!AE_R(abs_base + (gt1 ? 0 : (1 + eq1 > 4 ? 4 : 1 + eq1)), ENCV(a > 0))) { absm1 = 0; eq1++; }

@@ -4,7 +4,8 @@ cd "$(dirname "$0")/.."; mkdir -p gpurun_out; TAG=${1:-r1}
 { echo "nproc $(nproc)"; cat /sys/fs/cgroup/cpu.max 2>/dev/null; lscpu | grep -E "Model name|Socket|Core|Thread" ; nvidia-smi -L; } > gpurun_out/host_$TAG.txt 2>&1
 tools/gen264 -o /tmp/c2.264 -W 120 -H 68 -n 20 -s 2000 --gop IPB --idr 30 --refs 2 --t8x8 50 --deblock 0 --density 52 --qp 28 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_$TAG.csv tools/b200_decode /tmp/c2.264 -q > gpurun_out/ncu_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -s 8 -c 4 -o gpurun_out/prof_$TAG -f tools/b200_decode /tmp/c2.264 -q >> gpurun_out/ncu_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -s 12 -c 8 -o gpurun_out/prof_$TAG -f tools/b200_decode /tmp/c2.264 -q >> gpurun_out/ncu_$TAG.log 2>&1
+if [ -n "$SCALING" ]; then
 python - <<'PY' > gpurun_out/scaling_$1.txt 2>&1
 import ctypes, os, sys, time
 sys.path.insert(0, '.')
@@ -18,4 +19,5 @@ for name, path in (("reference", "oracle/_ref/libe264bench_ref.so"), ("b200", "t
         s, fr, _, d = lib.run(b, th)
         print(name, "threads", th, "fps", round(sum(fr) / s, 1), "per_thread", round(sum(fr) / s / th, 1), flush=True)
 PY
-cat gpurun_out/host_$TAG.txt gpurun_out/scaling_$TAG.txt
+fi
+cat gpurun_out/host_$TAG.txt; [ -n "$SCALING" ] && cat gpurun_out/scaling_$TAG.txt
