@@ -114,9 +114,9 @@ def reference_arm(args, rank, emit):
         emit({"impl": "reference", "unavailable": "oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)"}); return
     ref = BenchLib(lib)
     threads = min(usable_cpus(), 128)   # one single-threaded decoder per usable CPU (cgroup quota respected)
-    distinct = generate_streams([1000 + i for i in range(min(threads, 16))], args.frames, args.workdir)
-    bufs = [distinct[i % len(distinct)] for i in range(threads)]
-    for _ in range(args.warmup): ref.run(bufs[:threads], threads)
+    n_streams = max(args.streams, threads)   # same batch as the GPU arm: S streams, decoded by `threads` workers from a queue
+    bufs = generate_streams([2000 + i for i in range(n_streams)], args.frames, args.workdir)
+    for _ in range(args.warmup): ref.run(bufs, threads)
     t = 0.0; frames = 0
     for _ in range(args.steps):
         s, fr, _, _ = ref.run(bufs, threads)
@@ -125,8 +125,8 @@ def reference_arm(args, rank, emit):
     line = {"metric": "1080p_high_cabac_ipb_decode_fps", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "impl": "reference", "macroblocks_per_s": fps * MB_PER_FRAME,
-            "config": {"workload": f"1080p High CABAC IPB ~30 Mbit/s, {args.frames} frames/stream, {threads} concurrent streams (one single-threaded reference decoder per host thread)", "streams": threads, "frames_per_stream": args.frames},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference", "sample": f"{threads} streams x {args.frames} frames per step, n_threads=0 decoders, one per thread"},
+            "config": {"workload": f"1080p High CABAC IPB ~30 Mbit/s (BASELINE configs[1]), {args.frames} frames/stream, {n_streams} streams decoded by {threads} single-threaded reference decoders at a time", "streams": n_streams, "threads": threads, "frames_per_stream": args.frames},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference", "sample": f"{n_streams} streams x {args.frames} frames per step, n_threads=0 decoders, {threads} worker threads"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -138,7 +138,7 @@ def main():
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1); ap.add_argument("--steps", type=int, default=5); ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200"); ap.add_argument("--streams", type=int, default=16); ap.add_argument("--frames", type=int, default=60)
+    ap.add_argument("--impl", default="b200"); ap.add_argument("--streams", type=int, default=32); ap.add_argument("--frames", type=int, default=60)
     ap.add_argument("--workdir", default=os.environ.get("E264_BENCH_DIR", "/tmp/e264_bench"))
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -234,7 +234,7 @@ def main():
                        "parallelism": f"streams sharded over {world} GPU(s), NCCL broadcast of the input only"},
             "clocks": sampler.summary(), "gpu_launches": int(launches),
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-                    "threads": S, "note": "edge264_decode_NAL/get_frame from host buffers, one parser thread per stream"},
+                    "threads": S, "usable_cpus": usable_cpus(), "note": "edge264_decode_NAL/get_frame from host buffers, one parser thread per stream (threads sleep while get_frame waits for the GPU)"},
             "roofline": roof}
     lib.free(decs)
 
@@ -243,11 +243,11 @@ def main():
         if os.path.exists(refp):
             ref = BenchLib(refp)
             threads = min(usable_cpus(), 32)
-            rb_ = [bufs[i % S] for i in range(threads)]
+            rb_ = bufs[:max(threads, min(S, 2 * threads))]
             s, fr, rs, _ = ref.run(rb_, threads)
             line["cpu_baseline"] = {"value": sum(fr) / s, "unit": "frames/s", "cores": threads, "kind": "reference",
-                                    "sample": f"{threads} streams x {F} frames, one single-threaded reference decoder per thread, host of this box ({os.cpu_count()} logical CPUs, {usable_cpus()} usable under the cgroup quota)",
-                                    "bit_exact_with_gpu": all(rs[i] == sums[i % S] for i in range(threads))}
+                                    "sample": f"{len(rb_)} streams x {F} frames, {threads} single-threaded reference decoders at a time, host of this box ({os.cpu_count()} logical CPUs, {usable_cpus()} usable under the cgroup quota)",
+                                    "bit_exact_with_gpu": all(rs[i] == sums[i] for i in range(len(rb_)))}
         else:
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
     if rank == 0:

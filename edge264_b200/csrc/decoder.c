@@ -17,6 +17,15 @@
 
 int e264_parse_slice_data(SliceCtx *s);   /* slice_dec.c */
 
+/* optional host-side time accounting (E264_HOST_PROFILE=1): where decode_NAL/get_frame spend their time */
+#include <time.h>
+static int prof_on = -1;
+static double prof_t[6]; static long prof_n[6];
+static const char *const prof_names[6] = {"parse_slice_data", "acquire_staging", "submit", "wait", "clear_mbinfo", "headers+dpb"};
+static inline double prof_now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+#define PROF_BEGIN double prof_t0_ = prof_on > 0 ? prof_now() : 0
+#define PROF_END(i) do { if (prof_on > 0) { prof_t[i] += prof_now() - prof_t0_; prof_n[i]++; } } while (0)
+
 /* ------------------------------------------------------------------------------------------ */
 /* start codes (reference edge264.c:87-119: returns a pointer to the 00 00 01 / 00 00 00 01)     */
 /* ------------------------------------------------------------------------------------------ */
@@ -304,7 +313,7 @@ static int finish_picture(Edge264Decoder *d) {
 	int ret = 0;
 	if (p->host_buf >= 0) {
 		uint64_t ticket = 0;
-		if (d->be->submit(d->be_ctx, &pd, d->hb[p->host_buf].p, &ticket)) ret = EIO;
+		{ PROF_BEGIN; if (d->be->submit(d->be_ctx, &pd, d->hb[p->host_buf].p, &ticket)) ret = EIO; PROF_END(2); }
 		d->hb[p->host_buf].ticket = ticket; d->hb[p->host_buf].submitted = 1;
 		if (!p->needed_for_output) p->host_buf = -1;   /* already in the output queue */
 	}
@@ -638,9 +647,9 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 		d->first_sh = *h;
 		for (int i = 0; i < E264_MAX_SLOTS; i++) cp->slot_uid[i] = d->pics[i].in_use ? d->pics[i].uid : -1;
 		uint32_t cap = 0;
-		if (d->be->acquire_staging(d->be_ctx, slot, &cp->recs, &d->coefs, &cap, &d->slices)) return ENOMEM;
+		{ PROF_BEGIN; int ar = d->be->acquire_staging(d->be_ctx, slot, &cp->recs, &d->coefs, &cap, &d->slices); PROF_END(1); if (ar) return ENOMEM; }
 		d->coef_cap = cap; d->n_coefs = 0; d->n_slices = 0; d->mbs_done = 0; d->n_intra = 0; d->any_deblock = 0;
-		memset(d->mbi, 0, (size_t)d->w_mbs * d->h_mbs * sizeof(MbInfo));
+		{ PROF_BEGIN; memset(d->mbi, 0, (size_t)d->w_mbs * d->h_mbs * sizeof(MbInfo)); PROF_END(4); }
 		/* records need no clearing: every macroblock of a complete picture rewrites its own (sx_one_mb) */
 		d->slice_counter = 0;
 
@@ -730,7 +739,7 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 	c->br = *b;
 	c->mbaddr = h->first_mb;
 	c->cabac_init_idc_col = h->slice_type == 2 ? 0 : 1 + h->cabac_init_idc;
-	int n = e264_parse_slice_data(c);
+	int n; { PROF_BEGIN; n = e264_parse_slice_data(c); PROF_END(0); }
 	d->n_coefs = c->n_coefs; d->n_intra += c->n_intra;
 	if (n > 0) d->mbs_done += n;
 	if (c->error) ret = c->error == 2 ? ENOMEM : EBADMSG;
@@ -744,6 +753,7 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 Edge264Decoder *edge264_alloc(int n_threads, Edge264LogCb log_cb, void *log_arg, int log_mbs,
                               Edge264AllocCb alloc_cb, Edge264FreeCb free_cb, void *alloc_arg) {
 	(void)n_threads; (void)log_mbs;
+	if (prof_on < 0) { const char *e = getenv("E264_HOST_PROFILE"); prof_on = e && atoi(e); }
 	if (log_cb) return NULL;   /* like a reference build without the logs variant (edge264.c:217-220) */
 	Edge264Decoder *d = (Edge264Decoder *)calloc(1, sizeof(*d));
 	if (!d) return NULL;
@@ -770,6 +780,7 @@ void edge264_free(Edge264Decoder **pd) {
 	Edge264Decoder *d;
 	if (!pd || !(d = *pd)) return;
 	*pd = NULL;
+	if (prof_on > 0) { for (int i = 0; i < 6; i++) if (prof_n[i]) fprintf(stderr, "host profile: %-18s %8.3f ms total %6ld calls %8.1f us/call\n", prof_names[i], 1e3 * prof_t[i], prof_n[i], 1e6 * prof_t[i] / prof_n[i]); memset(prof_t, 0, sizeof(prof_t)); memset(prof_n, 0, sizeof(prof_n)); }
 	hostbufs_free_all(d);
 	d->be->destroy(d->be_ctx);
 	free(d->mbi); free(d->rbsp); free(d);
@@ -823,7 +834,7 @@ int edge264_get_frame(Edge264Decoder *d, Edge264Frame *out, int borrow) {
 	int hbuf = d->outq[0];
 	HostBuf *hb = &d->hb[hbuf];
 	if (!hb->submitted) return ENOMSG;   /* queued at insertion but still being parsed */
-	if (d->be->wait(d->be_ctx, hb->ticket)) return EIO;
+	{ PROF_BEGIN; int wr = d->be->wait(d->be_ctx, hb->ticket); PROF_END(3); if (wr) return EIO; }
 	memmove(d->outq, d->outq + 1, (size_t)(--d->outq_n) * sizeof(int));
 	*out = d->out_fmt;
 	int top = out->frame_crop_offsets[0], left = out->frame_crop_offsets[3];
