@@ -23,6 +23,9 @@ FULL = [
     ("1080p_intra", 120, 68, "-n 4 -s 31 --gop I --deblock 0 --t8x8 50 --density 40"),
     ("1080p_ipb", 120, 68, "-n 13 -s 32 --gop IPB --deblock 0 --t8x8 50 --density 52 --wp 2"),
     ("2160p_scaling", 240, 135, "-n 7 -s 33 --gop IPB --deblock 0 --t8x8 70 --scaling 3 --density 40 --qp 30"),
+    # BASELINE configs[4]: 7680x4320 level 6.2, B slices with explicit / implicit weighted bi-prediction, every edge filtered
+    ("4320p_wp_explicit", 480, 270, "-n 4 -s 34 --gop IPB --deblock 0 --wp 1 --density 60 --skip-pct 0 --refs 2"),
+    ("4320p_wp_implicit", 480, 270, "-n 4 -s 35 --gop IPB --deblock 0 --wp 2 --density 60 --skip-pct 5 --temporal"),
 ]
 
 
