@@ -384,7 +384,7 @@ static int configure_sequence(Edge264Decoder *d, const SPS *s) {
 	int w = s->width_mbs * 16, h = s->height_mbs * 16;
 	d->w_mbs = s->width_mbs; d->h_mbs = s->height_mbs;
 	d->stride_y = w; if (!(d->stride_y & 2047)) d->stride_y += 16;       /* reference headers.c:2027-2029 */
-	d->stride_c = w; if (!(d->stride_c & 4095)) d->stride_c += 8;        /* headers.c:2035-2037 */
+	d->stride_c = w; if (!(d->stride_c & 4095)) d->stride_c += 16;       /* headers.c:2035-2037 pads by 8; 16 keeps both chroma planes 8-byte aligned for vector stores and TMA */
 	d->plane_y = d->stride_y * h; d->plane_c = d->stride_c * (h >> 1);
 	d->frame_bytes = d->plane_y + d->plane_c + 16;
 	d->n_slots = s->max_num_ref_frames + 2;

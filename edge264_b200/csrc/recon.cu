@@ -9,6 +9,7 @@
  * There is NO CPU fallback: without a CUDA device e264b_create() fails and edge264_alloc() returns NULL.
  */
 #include <cuda_runtime.h>
+#include <cuda.h>            /* CUtensorMap types only: the encoder is resolved at run time, libcuda is not linked */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -35,6 +36,7 @@ struct E264bDevice {
 	int dev; cudaStream_t stream;
 	E264PicDesc g; int n_slots; size_t nmb; uint32_t coef_cap;
 	uint8_t *d_frames;
+	void *d_tmaps;               /* CUtensorMap[n_slots][6] over the frame pool, or NULL when the geometry does not fit TMA's rules */
 	E264MbRec *h_recs[E264_MAX_SLOTS]; cudaEvent_t rec_up[E264_MAX_SLOTS]; bool rec_busy[E264_MAX_SLOTS];
 	Staging st[NSTAGE]; int stage;
 	unsigned *d_sync;            /* [0..2] tickets (inter, deblock, intra), [3] err, then flags[2*nmb] */
@@ -55,6 +57,8 @@ static void free_geometry(E264bDevice *c) {
 	cudaStreamSynchronize(c->stream);
 	if (c->d_frames) cudaFree(c->d_frames);
 	c->d_frames = NULL;
+	if (c->d_tmaps) cudaFree(c->d_tmaps);
+	c->d_tmaps = NULL;
 	for (int i = 0; i < E264_MAX_SLOTS; i++) { if (c->h_recs[i]) cudaFreeHost(c->h_recs[i]); c->h_recs[i] = NULL; c->rec_busy[i] = false; }
 	for (int i = 0; i < NSTAGE; i++) {
 		Staging *s = &c->st[i];
@@ -88,7 +92,7 @@ extern "C" int e264b_create(E264bDevice **out) {
 		}
 	}
 	E264bDevice *c = new E264bDevice();
-	c->dev = 0; c->stream = 0; memset(&c->g, 0, sizeof(c->g)); c->n_slots = 0; c->nmb = 0; c->coef_cap = 0; c->d_frames = NULL;
+	c->dev = 0; c->stream = 0; memset(&c->g, 0, sizeof(c->g)); c->n_slots = 0; c->nmb = 0; c->coef_cap = 0; c->d_frames = NULL; c->d_tmaps = NULL;
 	memset(c->h_recs, 0, sizeof(c->h_recs)); memset(c->rec_busy, 0, sizeof(c->rec_busy)); memset(c->st, 0, sizeof(c->st)); c->stage = 0; c->d_sync = NULL; c->epoch = 0; c->tick_seq = 0;
 	c->launches = c->h2d_bytes = c->d2h_bytes = 0;
 	c->dev = dev;
@@ -124,6 +128,43 @@ extern "C" void e264b_destroy(E264bDevice *c) {
 	delete c;
 }
 
+
+/* Tensor maps for the motion-compensation windows: per frame slot, luma boxes 48 x {21,13,9} over the W x H luma
+ * plane and chroma boxes 32 x {9,5,3} over the Cb|Cr rows (one 2-D tensor: Cr starts stride_c/2 bytes into a row).
+ * Returns 0 and leaves d_tmaps NULL when TMA cannot describe the geometry (tiny pictures, odd strides, old driver):
+ * the kernel then gathers every window with clamped loads. */
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int build_tensor_maps(E264bDevice *c) {
+	const E264PicDesc *g = &c->g;
+	const int W = g->width_mbs * 16, H = g->height_mbs * 16;
+	if (W < 48 || H < 32 || (g->stride_y & 15) || (g->stride_c & 15) || (g->plane_y & 15) || (g->frame_bytes & 15)) return 0;
+	static EncodeTiledFn enc = NULL; static bool tried = false;
+	if (!tried) {
+		tried = true;
+		void *fn = NULL; cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) enc = (EncodeTiledFn)fn;
+		else { cudaGetLastError(); fprintf(stderr, "edge264_b200: cuTensorMapEncodeTiled unavailable, windows fall back to gathered loads\n"); }
+	}
+	if (!enc) return 0;
+	std::vector<CUtensorMap> maps((size_t)c->n_slots * 6);
+	static const cuuint32_t lrows[3] = {21, 13, 9}, crows[3] = {9, 5, 3};
+	for (int s = 0; s < c->n_slots; s++) for (int k = 0; k < 6; k++) {
+		const bool chroma = k >= 3;
+		uint8_t *base = c->d_frames + (size_t)s * g->frame_bytes + (chroma ? g->plane_y : 0);
+		cuuint64_t dims[2] = {(cuuint64_t)(chroma ? (g->stride_c >> 1) + (W >> 1) : W), (cuuint64_t)(chroma ? H >> 1 : H)};
+		cuuint64_t strides[1] = {(cuuint64_t)(chroma ? g->stride_c : g->stride_y)};
+		cuuint32_t box[2] = {chroma ? 32u : 48u, chroma ? crows[k - 3] : lrows[k]};
+		cuuint32_t estr[2] = {1, 1};
+		CUresult r = enc(&maps[(size_t)s * 6 + k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+		                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS) { fprintf(stderr, "edge264_b200: cuTensorMapEncodeTiled failed (%d) for %dx%d, windows fall back to gathered loads\n", (int)r, W, H); return 0; }
+	}
+	CK(cudaMalloc(&c->d_tmaps, maps.size() * sizeof(CUtensorMap)));
+	CK(cudaMemcpy(c->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+	return 0;
+}
+
 extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots) {
 	CK(cudaSetDevice(c->dev));
 	if (c->d_frames && c->n_slots == n_slots && !memcmp(&c->g, g, sizeof(*g))) {   /* pooled context of the same geometry */
@@ -143,6 +184,7 @@ extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots
 	size_t pool = (size_t)g->frame_bytes * n_slots;
 	CK(cudaMalloc(&c->d_frames, pool + 256));
 	CK(cudaMemsetAsync(c->d_frames, 128, pool + 256, c->stream));
+	if (build_tensor_maps(c)) return -1;
 	for (int i = 0; i < n_slots; i++) CK(cudaHostAlloc(&c->h_recs[i], c->nmb * sizeof(E264MbRec), cudaHostAllocDefault));
 	for (int i = 0; i < NSTAGE; i++) {
 		Staging *s = &c->st[i];
@@ -192,7 +234,8 @@ static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, const E264MbRec *r
 	J.tickets = c->d_sync; J.err = c->d_sync + 3; J.flags = c->d_sync + 4;
 	J.resid = c->st[c->stage].d_resid;
 	J.rows_mode = pd->n_intra * 2 > pd->width_mbs * pd->height_mbs;   /* intra pictures: wavefront of row warps */
-	{ static int wl = -1; if (wl < 0) { const char *e = getenv("E264B_WORDLOAD"); wl = e ? atoi(e) : 1; } J.word_loads = wl; }
+	J.word_loads = 0;
+	{ static int tma = -1; if (tma < 0) { const char *e = getenv("E264B_TMA"); tma = e ? atoi(e) : 1; } J.tmaps = tma ? c->d_tmaps : NULL; }
 	{ static int force = -2; if (force == -2) { const char *e = getenv("E264B_ROWS"); force = e ? atoi(e) : -1; } if (force >= 0) J.rows_mode = force; }
 	if (c->epoch >= (1u << 20)) {   /* row progress counters encode epoch * 2048 + count: restart before it wraps */
 		cudaStreamSynchronize(c->stream);

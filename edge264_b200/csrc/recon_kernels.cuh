@@ -27,16 +27,23 @@ struct PicJob {
 	unsigned *tickets;    /* [2] zeroed before the picture */
 	unsigned *err;
 	int rows_mode;
-	int word_loads;
+	int word_loads;       /* unused (kept for ABI of the job struct) */
+	const void *tmaps;    /* CUtensorMap[n_slots][6]: luma boxes 48x{21,13,9}, chroma boxes 32x{9,5,3}; NULL = no TMA */
 	int16_t *resid;       /* [nmb][384] residual written by e264_residual_kernel (coded macroblocks only) */
 };
 
 #define WARPS_PER_BLOCK 4
 #define YT_STRIDE 48     /* luma tile row: [15]=left neighbour, [16..31]=samples, [32..39]=top-right */
 #define CT_STRIDE 16     /* chroma tile row: [7]=left neighbour, [8..15]=samples */
-#define WIN_STRIDE 28   /* luma window row: up to 3 alignment bytes + 21 samples, stored as 7 words */
-#define WIN_STRIDE_W WIN_STRIDE
-#define WIN_C_OFF (21 * WIN_STRIDE)
+/* motion-compensation window buffer (one TMA destination set): luma box 48 x 21 at +0, Cb box 32 x 9 at +1024,
+ * Cr box 32 x 9 at +1408 — every box starts on a 128-byte boundary as cp.async.bulk.tensor requires.  A box must
+ * start on a 16-byte boundary of the picture row (measured: other x coordinates raise an illegal-instruction
+ * fault), so the wanted window begins 0..15 bytes into its shared-memory rows. */
+#define WIN_STRIDE 48
+#define WIN_C_STRIDE 32
+#define WIN_CB_OFF 1024
+#define WIN_CR_OFF 1408
+#define WIN_BYTES 1792
 
 struct __align__(16) WarpSmem {
 	uint4 rec4[12];                 /* the macroblock record */
@@ -46,7 +53,6 @@ struct __align__(16) WarpSmem {
 	int dc[24];                     /* scaled DC: 16 luma (raster over blocks), 4 Cb, 4 Cr */
 	union {
 		int16_t t8[4 * 64];         /* 8x8 transform transpose buffer */
-		uint8_t win[21 * WIN_STRIDE + 2 * 9 * 12 + 4];   /* MC windows: luma, Cb, Cr (chroma rows: 12 bytes = 3 words) */
 		int edge[2][28];            /* intra 8x8 filtered reference samples */
 	} u;
 };
@@ -79,6 +85,26 @@ __device__ __forceinline__ bool wait_flag(const unsigned *flags, int idx, unsign
 	return true;
 }
 
+/* ---- shared-memory barrier + TMA helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP, UTMALDG) ---- */
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+/* bounded wait for the phase with the given parity; false = gave up (caller raises the error flag) */
+__device__ __forceinline__ bool mbar_wait(void *bar, unsigned parity) {
+	unsigned done = 0, spins = 0;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	} while (!done && ++spins < (1u << 22));
+	return done != 0;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* residual                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
@@ -86,7 +112,7 @@ __device__ __forceinline__ bool wait_flag(const unsigned *flags, int idx, unsign
 __device__ __noinline__ void idct4x4(const int16_t *c, bool have_levels, const uint8_t *scaling, int qp, bool dc_override, int dc, int16_t *dst, int dstride) {
 	int d[16];
 	if (have_levels) {
-		uint4 a = __ldg((const uint4 *)c), b = __ldg((const uint4 *)c + 1);
+		uint4 a = *(const uint4 *)c, b = *((const uint4 *)c + 1);   /* c points into the TMA-staged shared copy */
 		int16_t lv[16];
 		*(uint4 *)lv = a; *(uint4 *)(lv + 8) = b;
 		int sh = qp / 6, m = qp - sh * 6;
@@ -132,14 +158,14 @@ __device__ __forceinline__ void idct8_1d(short a[8]) {
 	a[4] = (short)(f6 - f1); a[5] = (short)(f4 - f3); a[6] = (short)(f2 - f5); a[7] = (short)(f0 - f7);
 }
 
-__device__ __noinline__ void residual_stage(WarpSmem *ws, const E264MbRec *r, const E264SliceRec *sr, const int16_t *pool, int lane) {
+/* cf: this macroblock's coefficient run, staged in shared memory by the caller (cp.async.bulk) */
+__device__ __noinline__ void residual_stage(WarpSmem *ws, const E264MbRec *r, const E264SliceRec *sr, const int16_t *cf, int lane) {
 	/* clear */
 	uint4 z = make_uint4(0, 0, 0, 0);
 	((uint4 *)ws->res)[lane] = z;
 	if (lane < 16) ((uint4 *)ws->res)[32 + lane] = z;
 	const unsigned coded = r->coded;
 	const int inter = r->kind == MBK_INTER, i16 = r->kind == MBK_I16x16;
-	const int16_t *cf = pool + r->coef_off;
 	const int qpy = r->qp[0];
 	/* --- DC transforms first --- */
 	if (coded & CODED_Y_DC) {
@@ -150,7 +176,7 @@ __device__ __noinline__ void residual_stage(WarpSmem *ws, const E264MbRec *r, co
 			for (int k = 0; k < 4; k++)
 #pragma unroll
 				for (int l = 0; l < 4; l++) {
-					int v = __ldg(cf + k * 4 + l);
+					int v = cf[k * 4 + l];
 					int s = ((neg[i] >> k) ^ (neg[j] >> l)) & 1;
 					u += s ? -v : v;
 				}
@@ -166,7 +192,7 @@ __device__ __noinline__ void residual_stage(WarpSmem *ws, const E264MbRec *r, co
 	if (lane >= 16 && lane < 24) {
 		int pl = (lane - 16) >> 2, i = lane & 3, v = 0;
 		if (any_cdc) {
-			int a = __ldg(cf + 4 * pl), b = __ldg(cf + 4 * pl + 1), c = __ldg(cf + 4 * pl + 2), d = __ldg(cf + 4 * pl + 3);
+			int a = cf[4 * pl], b = cf[4 * pl + 1], c = cf[4 * pl + 2], d = cf[4 * pl + 3];
 			int f = i == 0 ? a + b + c + d : i == 1 ? a - b + c - d : i == 2 ? a + b - c - d : a - b - c + d;
 			int qpc = r->qp[1 + pl];
 			int ls = (sr->scaling4x4[1 + pl + inter * 3][0] * h264_norm4x4[qpc % 6][0]) << (qpc / 6);
@@ -183,7 +209,7 @@ __device__ __noinline__ void residual_stage(WarpSmem *ws, const E264MbRec *r, co
 		short a[8];
 		if (on) {
 			int idx = __popc(coded & 0x1111 & ((1u << (blk * 4)) - 1));
-			uint4 q = __ldg((const uint4 *)(cf_luma + idx * 64 + k * 8));
+			uint4 q = *(const uint4 *)(cf_luma + idx * 64 + k * 8);
 			short lv[8]; *(uint4 *)lv = q;
 			int div = qpy / 6, m = qpy - div * 6;
 			const uint8_t *sc = sr->scaling8x8[inter] + k * 8;
@@ -461,57 +487,82 @@ __device__ __noinline__ int wblend(int q, int v, int wm, int w0, int w1, int o, 
 	return clip255(((q * w0 + v * w1 + (1 << lw)) >> (lw + 1)) + o);
 }
 
-/* motion-compensate the SxS square at (x0,y0) (luma units, inside the MB) of list l.  The window loads
- * are independent (4 in flight per lane per trip), so a few L2 round trips cover the (S+5)^2 window. */
-__device__ __noinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int l, int x0, int y0, int S, int lane) {
-	const int WW = S + 5, NL = WW * WW, CW = S >> 1, CWW = CW + 1, NC1 = CWW * CWW;
-	const int rw = (65536 + WW - 1) / WW, rcw = (65536 + CWW - 1) / CWW;   /* exact reciprocals for i < 512 */
-	int z0 = blk_z(x0 >> 2, y0 >> 2);
-	int mvx = r->mv[l][z0][0], mvy = r->mv[l][z0][1];
+/* Motion compensation of one macroblock = a list of square rectangles (16, 8 or 4 luma samples wide, one
+ * motion vector and one reference each).  Each rectangle needs a (S+5)^2 luma window and two (S/2+1)^2 chroma
+ * windows of its reference picture.  Windows that lie inside the picture are fetched by the TMA unit
+ * (cp.async.bulk.tensor.2d, one luma and two chroma boxes counted on one mbarrier); windows that touch the
+ * border are gathered sample by sample with clamped coordinates (8.4.2.2.1).  Two window buffers per warp:
+ * the fetch of rectangle i+1 is in flight while rectangle i is filtered. */
+struct McCtx {
+	uint8_t *win[2];
+	unsigned long long *bar[2];
+	unsigned parity[2];
+	bool pending[2];
+	int lo[2], cob[2], cor[2];   /* where the wanted luma / Cb / Cr window starts inside its rows */
+};
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, int y, void *bar) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+	             :: "r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+
+/* rectangle code: bit0 list, bits1-2 size class (0:16 1:8 2:4), bits3-4 x0/4, bits5-6 y0/4 */
+#define RECT(l, sc, x0, y0) ((l) | ((sc) << 1) | (((x0) >> 2) << 3) | (((y0) >> 2) << 5))
+
+__device__ __forceinline__ void mc_issue(WarpSmem *ws, McCtx &mc, int b, const PicJob &J, const E264MbRec *r, int mbx, int mby, int rect, int lane) {
+	const int l = rect & 1, sc = (rect >> 1) & 3, x0 = ((rect >> 3) & 3) << 2, y0 = ((rect >> 5) & 3) << 2, S = 16 >> sc;
+	const int WW = S + 5, CWW = (S >> 1) + 1;
+	const int z0 = blk_z(x0 >> 2, y0 >> 2);
+	const int mvx = r->mv[l][z0][0], mvy = r->mv[l][z0][1];
 	int slot = r->ref_pic[l][z0 >> 2];
 	if (slot < 0 || slot >= J.n_slots) slot = J.dst_slot;
-	const uint8_t *ref = J.frames + (size_t)slot * J.frame_bytes;
 	const int W = J.w_mbs * 16, H = J.h_mbs * 16;
-	uint8_t *win = ws->u.win;
 	const int X0 = mbx * 16 + x0 + (mvx >> 2) - 2, Y0 = mby * 16 + y0 + (mvy >> 2) - 2;
 	const int CX0 = mbx * 8 + (x0 >> 1) + (mvx >> 3), CY0 = mby * 8 + (y0 >> 1) + (mvy >> 3);
-	/* Interior windows (the common case) are fetched as ALIGNED 32-bit words and stored as words: the window
-	 * then starts `lo`/`co` bytes into its shared-memory rows.  Windows touching the picture border take the
-	 * byte-wise clamped path (8.4.2.2.1 clamps each coordinate). */
-	int lo = 0, co = 0;
-	const bool interior = J.word_loads && X0 >= 4 && Y0 >= 0 && X0 + WW + 4 <= W && Y0 + WW <= H && CX0 >= 4 && CY0 >= 0 && CX0 + CWW + 4 <= (W >> 1) && CY0 + CWW <= (H >> 1);
+	uint8_t *win = mc.win[b];
+	const bool interior = J.tmaps != nullptr && X0 >= 0 && Y0 >= 0 && X0 + WW <= W && Y0 + WW <= H && CX0 >= 0 && CY0 >= 0 && CX0 + CWW <= (W >> 1) && CY0 + CWW <= (H >> 1);
+	mc.pending[b] = interior;
+	mc.lo[b] = mc.cob[b] = mc.cor[b] = 0;
 	if (interior) {
-		lo = X0 & 3; co = CX0 & 3;
-		const int nwl = (lo + WW + 3) >> 2, nwc = (co + CWW + 3) >> 2;          /* words per row: <= 7 luma, <= 3 chroma */
-		const uint8_t *lbase = ref + (size_t)Y0 * J.stride_y + (X0 & ~3);
-		const int rwl = (65536 + nwl - 1) / nwl;
-#pragma unroll 4
-		for (int i = lane; i < WW * nwl; i += 32) {
-			int row = (i * rwl) >> 16, wd = i - row * nwl;
-			*(uint32_t *)(win + row * WIN_STRIDE_W + wd * 4) = __ldg((const uint32_t *)(lbase + (size_t)row * J.stride_y) + wd);
-		}
-		const uint8_t *cbase = ref + J.plane_y + (size_t)CY0 * J.stride_c + (CX0 & ~3);
-		const int rwc = (65536 + nwc - 1) / nwc, ncw = CWW * nwc;
-#pragma unroll 2
-		for (int i = lane; i < 2 * ncw; i += 32) {
-			int pl = i >= ncw, j = i - pl * ncw, row = (j * rwc) >> 16, wd = j - row * nwc;
-			*(uint32_t *)(win + WIN_C_OFF + pl * 108 + row * 12 + wd * 4) = __ldg((const uint32_t *)(cbase + pl * (J.stride_c >> 1) + (size_t)row * J.stride_c) + wd);
+		const int crx = CX0 + (J.stride_c >> 1);
+		mc.lo[b] = X0 & 15; mc.cob[b] = CX0 & 15; mc.cor[b] = crx & 15;
+		if (lane == 0) {
+			const char *tm = (const char *)J.tmaps + (size_t)(slot * 6 + sc) * 128;
+			const unsigned bytes = (unsigned)(WIN_STRIDE * WW + 2 * WIN_C_STRIDE * CWW);
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mc.bar[b])), "r"(bytes) : "memory");
+			tma_load_2d(win, tm, X0 & ~15, Y0, mc.bar[b]);
+			tma_load_2d(win + WIN_CB_OFF, tm + 3 * 128, CX0 & ~15, CY0, mc.bar[b]);
+			tma_load_2d(win + WIN_CR_OFF, tm + 3 * 128, crx & ~15, CY0, mc.bar[b]);
 		}
 	} else {
+		const uint8_t *ref = J.frames + (size_t)slot * J.frame_bytes;
+		const int NL = WW * WW, NC1 = CWW * CWW;
+		const int rw = (65536 + WW - 1) / WW, rcw = (65536 + CWW - 1) / CWW;   /* exact reciprocals for i < 512 */
 #pragma unroll 1
 		for (int i = lane; i < NL; i += 32) {
 			int row = (i * rw) >> 16, col = i - row * WW;
 			int xx = min(max(X0 + col, 0), W - 1), yy = min(max(Y0 + row, 0), H - 1);
-			win[row * WIN_STRIDE_W + col] = __ldg(ref + (size_t)yy * J.stride_y + xx);
+			win[row * WIN_STRIDE + col] = __ldg(ref + (size_t)yy * J.stride_y + xx);
 		}
 #pragma unroll 1
 		for (int i = lane; i < 2 * NC1; i += 32) {
 			int pl = i >= NC1, j = i - pl * NC1, row = (j * rcw) >> 16, col = j - row * CWW;
 			int xx = min(max(CX0 + col, 0), (W >> 1) - 1), yy = min(max(CY0 + row, 0), (H >> 1) - 1);
-			win[WIN_C_OFF + pl * 108 + row * 12 + col] = __ldg(ref + J.plane_y + pl * (J.stride_c >> 1) + (size_t)yy * J.stride_c + xx);
+			win[(pl ? WIN_CR_OFF : WIN_CB_OFF) + row * WIN_C_STRIDE + col] = __ldg(ref + J.plane_y + pl * (J.stride_c >> 1) + (size_t)yy * J.stride_c + xx);
 		}
 	}
-	__syncwarp();
+}
+
+/* filter + weight the rectangle whose windows sit in buffer b; false = the TMA never completed */
+__device__ __forceinline__ bool mc_compute(WarpSmem *ws, McCtx &mc, int b, const E264MbRec *r, const E264SliceRec *sr, int rect, int lane) {
+	const int l = rect & 1, sc = (rect >> 1) & 3, x0 = ((rect >> 3) & 3) << 2, y0 = ((rect >> 5) & 3) << 2, S = 16 >> sc;
+	const int CW = S >> 1;
+	const int z0 = blk_z(x0 >> 2, y0 >> 2);
+	const int mvx = r->mv[l][z0][0], mvy = r->mv[l][z0][1];
+	const uint8_t *win = mc.win[b];
+	if (mc.pending[b]) {
+		if (!mbar_wait(mc.bar[b], mc.parity[b])) return false;
+		mc.parity[b] ^= 1; mc.pending[b] = false;
+	} else __syncwarp();
 	/* weighting of this rectangle is uniform (callers guarantee one 8x8 reference pair per rectangle):
 	 * wm 0 store, 1 default average with the list-0 pass, 2 explicit uni, 3 explicit/implicit bi */
 	const int i8r = ((y0 >> 3) << 1) | (x0 >> 3);
@@ -532,8 +583,8 @@ __device__ __noinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264Mb
 		for (int c = 0; c < 3; c++) { w1[c] = sr->wp_w[l][ri][c]; oo[c] = sr->wp_o[l][ri][c]; lw[c] = c ? sr->chroma_log2_wd : sr->luma_log2_wd; }
 	}
 #define WSTORE(dst, v, c) (dst) = (uint8_t)wblend((dst), (v), wm, w0[c], w1[c], oo[c], lw[c])
-	const int fx = mvx & 3, fy = mvy & 3, sh = S == 16 ? 4 : S == 8 ? 3 : 2;
-	const uint8_t *wl = win + lo + 2 * WIN_STRIDE + 2;
+	const int fx = mvx & 3, fy = mvy & 3, sh = 4 - sc;
+	const uint8_t *wl = win + mc.lo[b] + 2 * WIN_STRIDE + 2;
 	/* one loop per class of fractional position: the branch is uniform for the rectangle */
 #define HSUM(g) tap6((g)[-2], (g)[-1], (g)[0], (g)[1], (g)[2], (g)[3])
 #define VSUM(g) tap6((g)[-2 * WIN_STRIDE], (g)[-WIN_STRIDE], (g)[0], (g)[WIN_STRIDE], (g)[2 * WIN_STRIDE], (g)[3 * WIN_STRIDE])
@@ -548,7 +599,7 @@ __device__ __noinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264Mb
 	} else if ((fx & 1) && (fy & 1)) {   /* e, g, p, r: horizontal half of row y or y+1, vertical half of column x or x+1 */
 		const int ro = fy == 3 ? WIN_STRIDE : 0, cofs = fx == 3;
 		LUMA_LOOP((clip255((HSUM(g + ro) + 16) >> 5) + clip255((VSUM(g + cofs) + 16) >> 5) + 1) >> 1)
-	} else {   /* f, i, j, k, q: centre sample, combined like the reference (see mc_centre) */
+	} else {   /* f, i, j, k, q: centre sample, combined like the reference (int16 wrap) */
 		const bool vfirst = fx & 1;
 		const int sa = vfirst ? 1 : WIN_STRIDE, sb = vfirst ? WIN_STRIDE : 1;
 		const int second = fx == 2 ? (fy == 2 ? 0 : 1) : 2;          /* 0 none (j), 1 horizontal half b/s, 2 vertical half h/m */
@@ -572,8 +623,8 @@ __device__ __noinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264Mb
 #pragma unroll 1
 	for (int p = lane; p < 2 * CW * CW; p += 32) {
 		int pl = p >= CW * CW, q = p - pl * CW * CW, x = q & (CW - 1), y = q >> (sh - 1);
-		const uint8_t *cwn = win + WIN_C_OFF + pl * 108 + co + y * 12 + x;
-		int v = (cA * cwn[0] + cB * cwn[1] + cC * cwn[12] + cD * cwn[13] + 32) >> 6;
+		const uint8_t *cwn = win + (pl ? WIN_CR_OFF + mc.cor[b] : WIN_CB_OFF + mc.cob[b]) + y * WIN_C_STRIDE + x;
+		int v = (cA * cwn[0] + cB * cwn[1] + cC * cwn[WIN_C_STRIDE] + cD * cwn[WIN_C_STRIDE + 1] + 32) >> 6;
 		if (pl) WSTORE(CT(1, (x0 >> 1) + x, (y0 >> 1) + y), v, 2); else WSTORE(CT(0, (x0 >> 1) + x, (y0 >> 1) + y), v, 1);
 	}
 #undef LUMA_LOOP
@@ -581,15 +632,17 @@ __device__ __noinline__ void mc_rect(WarpSmem *ws, const PicJob &J, const E264Mb
 #undef VSUM
 #undef WSTORE
 	__syncwarp();
+	return true;
 }
 
-__device__ __noinline__ void inter_predict(WarpSmem *ws, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int lane) {
+/* list the rectangles of this macroblock (list 0 first: list 1 blends with what list 0 stored) */
+__device__ __forceinline__ int mc_rects(const E264MbRec *r, uint8_t *out, int lane) {
+	int n = 0;
 	for (int l = 0; l < 2; l++) {
-		/* is the whole macroblock one 16x16 partition for this list? */
 		int z = lane & 15;
 		bool same = r->mv[l][z][0] == r->mv[l][0][0] && r->mv[l][z][1] == r->mv[l][0][1] && r->ref_idx[l][z >> 2] == r->ref_idx[l][0] && r->ref_idx[l ^ 1][z >> 2] == r->ref_idx[l ^ 1][0];
 		if (__all_sync(0xffffffffu, same)) {
-			if (r->ref_idx[l][0] >= 0) mc_rect(ws, J, r, sr, mbx, mby, l, 0, 0, 16, lane);
+			if (r->ref_idx[l][0] >= 0) { if (lane == 0) out[n] = (uint8_t)RECT(l, 0, 0, 0); n++; }
 			continue;
 		}
 		for (int i8 = 0; i8 < 4; i8++) {
@@ -597,9 +650,20 @@ __device__ __noinline__ void inter_predict(WarpSmem *ws, const PicJob &J, const 
 			int zb = i8 * 4, x0 = (i8 & 1) * 8, y0 = (i8 >> 1) * 8;
 			bool s8 = true;
 			for (int k = 1; k < 4; k++) s8 = s8 && r->mv[l][zb + k][0] == r->mv[l][zb][0] && r->mv[l][zb + k][1] == r->mv[l][zb][1];
-			if (s8) mc_rect(ws, J, r, sr, mbx, mby, l, x0, y0, 8, lane);
-			else for (int k = 0; k < 4; k++) mc_rect(ws, J, r, sr, mbx, mby, l, x0 + (k & 1) * 4, y0 + (k >> 1) * 4, 4, lane);
+			if (s8) { if (lane == 0) out[n] = (uint8_t)RECT(l, 1, x0, y0); n++; }
+			else for (int k = 0; k < 4; k++) { if (lane == 0) out[n] = (uint8_t)RECT(l, 2, x0 + (k & 1) * 4, y0 + (k >> 1) * 4); n++; }
 		}
+	}
+	__syncwarp();
+	return n;
+}
+
+__device__ __noinline__ bool inter_predict(WarpSmem *ws, McCtx &mc, uint8_t *rects, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int lane) {
+	const int n = mc_rects(r, rects, lane);
+#pragma unroll 1
+	for (int i = -1; i < n; i++) {
+		if (i + 1 < n) mc_issue(ws, mc, (i + 1) & 1, J, r, mbx, mby, rects[i + 1], lane);
+		if (i >= 0 && !mc_compute(ws, mc, i & 1, r, sr, rects[i], lane)) return false;
 	}
 	/* add the residual */
 #pragma unroll
@@ -607,6 +671,7 @@ __device__ __noinline__ void inter_predict(WarpSmem *ws, const PicJob &J, const 
 #pragma unroll
 	for (int k = 0; k < 4; k++) { int p = lane + 32 * k, pl = p >> 6, x = p & 7, y = (p >> 3) & 7; CT(pl, x, y) = (uint8_t)clip255((short)((int)CT(pl, x, y) + ws->res[256 + p])); }
 	__syncwarp();
+	return true;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -628,23 +693,70 @@ __device__ __forceinline__ void store_mb(WarpSmem *ws, const PicJob &J, uint8_t 
 	else { int j = lane - 16, pl = j >> 3, row = j & 7; *(uint2 *)(C + pl * cpl + (size_t)row * J.stride_c) = *(const uint2 *)&CT(pl, 0, row); }
 }
 
-/* ---- kernel 1: inverse quantisation + inverse transforms of every coded macroblock (no dependencies) ---- */
+/* ---- kernel 1: inverse quantisation + inverse transforms of every coded macroblock (no dependencies) ----
+ * Each warp owns a two-stage pipeline: while macroblock i is transformed, the coefficient run of its next
+ * macroblock (16..816 bytes, contiguous in the pool, 16-byte aligned) is in flight as one TMA bulk copy
+ * (cp.async.bulk global -> shared, completion counted in bytes on the warp's mbarrier). */
+#define RES_COEF_MAX 416   /* 16 + 256 + 8 + 128 levels, rounded up */
+
+/* number of int16 levels a record owns in the pool (same layout rule as sx_pool_take on the host) */
+__device__ __forceinline__ int rec_coef_count(const E264MbRec *r) {
+	const unsigned coded = r->coded;
+	int n = (coded & CODED_Y_DC) ? 16 : 0;
+	n += (r->flags & MBF_T8x8) ? 64 * __popc(coded & 0x1111) : 16 * __popc(coded & 0xffff);
+	if (coded & (CODED_CB_DC | CODED_CR_DC)) n += 8;
+	n += 16 * __popc((coded >> 16) & 0xff);
+	return n;
+}
+
+struct __align__(16) ResStage {
+	uint4 rec4[12];
+	int16_t coef[RES_COEF_MAX];
+};
+
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_residual_kernel(PicJob J) {
 	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
-	const int lane = threadIdx.x & 31;
-	WarpSmem *ws = &smem[threadIdx.x >> 5];
-	const int nmb = J.w_mbs * J.h_mbs;
-	for (int mb = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); mb < nmb; mb += gridDim.x * WARPS_PER_BLOCK) {
-		if (lane < 12) ws->rec4[lane] = __ldg((const uint4 *)(J.recs + mb) + lane);
+	__shared__ ResStage stage[WARPS_PER_BLOCK][2];
+	__shared__ __align__(8) unsigned long long bars[WARPS_PER_BLOCK][2];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	WarpSmem *ws = &smem[w];
+	const int nmb = J.w_mbs * J.h_mbs, step = gridDim.x * WARPS_PER_BLOCK;
+	if (lane == 0) {
+		mbar_init(&bars[w][0], 1); mbar_init(&bars[w][1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	__syncwarp();
+	/* stage s <- macroblock m: record through the read-only path, coefficient run through TMA */
+	auto issue = [&](int m, int s) -> bool {
+		ResStage *st = &stage[w][s];
+		if (lane < 12) st->rec4[lane] = __ldg((const uint4 *)(J.recs + m) + lane);
 		__syncwarp();
-		const E264MbRec *r = (const E264MbRec *)ws->rec4;
-		if (r->coded != 0 && r->kind != MBK_IPCM) {
-			residual_stage(ws, r, J.slices + r->slice_idx, J.coefs, lane);
+		const E264MbRec *r = (const E264MbRec *)st->rec4;
+		const bool on = r->coded != 0 && r->kind != MBK_IPCM;
+		if (on && lane == 0) tma_bulk_g2s(st->coef, J.coefs + r->coef_off, (unsigned)rec_coef_count(r) * 2u, &bars[w][s]);
+		return on;
+	};
+	int mb = blockIdx.x * WARPS_PER_BLOCK + w;
+	if (mb >= nmb) return;
+	unsigned parity[2] = {0, 0};
+	int s = 0;
+	bool on = issue(mb, 0);
+	for (; mb < nmb; mb += step, s ^= 1) {
+		bool on_next = false;
+		if (mb + step < nmb) on_next = issue(mb + step, s ^ 1);
+		if (on) {
+			ResStage *st = &stage[w][s];
+			if (!mbar_wait(&bars[w][s], parity[s])) { if (lane == 0) atomicExch(J.err, 3u); return; }
+			parity[s] ^= 1;
+			const E264MbRec *r = (const E264MbRec *)st->rec4;
+			residual_stage(ws, r, J.slices + r->slice_idx, st->coef, lane);
 			uint4 *dst = (uint4 *)(J.resid + (size_t)mb * 384);
 			dst[lane] = ((const uint4 *)ws->res)[lane];
 			if (lane < 16) dst[32 + lane] = ((const uint4 *)ws->res)[32 + lane];
 		}
 		__syncwarp();
+		on = on_next;
 	}
 }
 
@@ -652,8 +764,25 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_residual_kernel(Pic
 template <int MINB>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) e264_inter_kernel(PicJob J) {
 	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
-	const int lane = threadIdx.x & 31;
-	WarpSmem *ws = &smem[threadIdx.x >> 5];
+	__shared__ __align__(128) uint8_t wins[WARPS_PER_BLOCK][2][WIN_BYTES];
+	__shared__ __align__(8) unsigned long long bars[WARPS_PER_BLOCK][2];
+	__shared__ uint8_t rects[WARPS_PER_BLOCK][32];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	WarpSmem *ws = &smem[w];
+	McCtx mc;
+	mc.win[0] = wins[w][0]; mc.win[1] = wins[w][1]; mc.bar[0] = &bars[w][0]; mc.bar[1] = &bars[w][1];
+	mc.parity[0] = mc.parity[1] = 0; mc.pending[0] = mc.pending[1] = false;
+	if (lane == 0) {
+		mbar_init(mc.bar[0], 1); mbar_init(mc.bar[1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	/* the tensor maps were written by the host (cudaMemcpy): acquire them for the tensormap proxy once per block */
+	if (J.tmaps != nullptr) {
+		for (int i = threadIdx.x; i < J.n_slots * 6; i += blockDim.x)
+			asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" :: "l"((const char *)J.tmaps + (size_t)i * 128) : "memory");
+	}
+	__syncthreads();
 	const int nmb = J.w_mbs * J.h_mbs;
 	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
 	for (;;) {
@@ -667,7 +796,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) e264_inter_kernel(
 		__syncwarp();
 		const E264MbRec *r = (const E264MbRec *)ws->rec4;
 		fetch_residual(ws, J, r, mb, lane);
-		inter_predict(ws, J, r, J.slices + r->slice_idx, mbx, mby, lane);
+		if (!inter_predict(ws, mc, rects[w], J, r, J.slices + r->slice_idx, mbx, mby, lane)) { if (lane == 0) atomicExch(J.err, 4u); break; }
 		store_mb(ws, J, dst + (size_t)(mby * 16) * J.stride_y + mbx * 16, dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8, lane);
 		if (lane == 0) J.flags[mb] = J.epoch;     /* visible to the intra kernel through the kernel boundary */
 		__syncwarp();

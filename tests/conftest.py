@@ -31,6 +31,9 @@ STREAMS = [
     # centre half-sample (edge264_inter.c:4-9), found by bench.py's bit-exactness check
     ("b_pcm_checker",    10, 8, "-n 12 -s 23 --gop IPB --deblock 0 --pcm 250 --pcm-checker --intra-pct 5 --skip-pct 30 --density 10"),
     ("wide_33x2",        33, 2, "-n 6 -s 22 --gop IPB --deblock 0 --wp 2"),
+    # 4096 samples wide: the reference pads such strides (edge264_headers.c:2027-2037); ours pads differently,
+    # only the samples and the reported strides matter
+    ("wide_256x2",       256, 2, "-n 5 -s 24 --gop IPB --deblock 0"),
 ]
 
 
