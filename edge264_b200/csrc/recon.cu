@@ -36,7 +36,7 @@ struct E264bDevice {
 	int dev; cudaStream_t stream;
 	E264PicDesc g; int n_slots; size_t nmb; uint32_t coef_cap;
 	uint8_t *d_frames;
-	void *d_tmaps;               /* CUtensorMap[n_slots][6] over the frame pool, or NULL when the geometry does not fit TMA's rules */
+	void *d_tmaps;               /* CUtensorMap[6] over the frame pool, or NULL when the geometry does not fit TMA's rules */
 	E264MbRec *h_recs[E264_MAX_SLOTS]; cudaEvent_t rec_up[E264_MAX_SLOTS]; bool rec_busy[E264_MAX_SLOTS];
 	Staging st[NSTAGE]; int stage;
 	unsigned *d_sync;            /* [0..2] tickets (inter, deblock, intra), [3] err, then flags[2*nmb] */
@@ -129,8 +129,8 @@ extern "C" void e264b_destroy(E264bDevice *c) {
 }
 
 
-/* Tensor maps for the motion-compensation windows: per frame slot, luma boxes 48 x {21,13,9} over the W x H luma
- * plane and chroma boxes 32 x {9,5,3} over the Cb|Cr rows (one 2-D tensor: Cr starts stride_c/2 bytes into a row).
+/* Tensor maps for the motion-compensation windows: rank-3 (x, y, frame slot), luma boxes 48 x {21,13,9} over the
+ * W x H luma planes and chroma boxes 32 x {9,5,3} over the Cb|Cr rows (Cr starts stride_c/2 bytes into a row).
  * Returns 0 and leaves d_tmaps NULL when TMA cannot describe the geometry (tiny pictures, odd strides, old driver):
  * the kernel then gathers every window with clamped loads. */
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -147,16 +147,18 @@ static int build_tensor_maps(E264bDevice *c) {
 		else { cudaGetLastError(); fprintf(stderr, "edge264_b200: cuTensorMapEncodeTiled unavailable, windows fall back to gathered loads\n"); }
 	}
 	if (!enc) return 0;
-	std::vector<CUtensorMap> maps((size_t)c->n_slots * 6);
+	/* six rank-3 maps (x, y, frame slot) cover every reference of every picture: few enough to stay in the TMA
+	 * unit's descriptor cache */
+	std::vector<CUtensorMap> maps(6);
 	static const cuuint32_t lrows[3] = {21, 13, 9}, crows[3] = {9, 5, 3};
-	for (int s = 0; s < c->n_slots; s++) for (int k = 0; k < 6; k++) {
+	for (int k = 0; k < 6; k++) {
 		const bool chroma = k >= 3;
-		uint8_t *base = c->d_frames + (size_t)s * g->frame_bytes + (chroma ? g->plane_y : 0);
-		cuuint64_t dims[2] = {(cuuint64_t)(chroma ? (g->stride_c >> 1) + (W >> 1) : W), (cuuint64_t)(chroma ? H >> 1 : H)};
-		cuuint64_t strides[1] = {(cuuint64_t)(chroma ? g->stride_c : g->stride_y)};
-		cuuint32_t box[2] = {chroma ? 32u : 48u, chroma ? crows[k - 3] : lrows[k]};
-		cuuint32_t estr[2] = {1, 1};
-		CUresult r = enc(&maps[(size_t)s * 6 + k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+		uint8_t *base = c->d_frames + (chroma ? g->plane_y : 0);
+		cuuint64_t dims[3] = {(cuuint64_t)(chroma ? (g->stride_c >> 1) + (W >> 1) : W), (cuuint64_t)(chroma ? H >> 1 : H), (cuuint64_t)c->n_slots};
+		cuuint64_t strides[2] = {(cuuint64_t)(chroma ? g->stride_c : g->stride_y), (cuuint64_t)g->frame_bytes};
+		cuuint32_t box[3] = {chroma ? 32u : 48u, chroma ? crows[k - 3] : lrows[k], 1};
+		cuuint32_t estr[3] = {1, 1, 1};
+		CUresult r = enc(&maps[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
 		                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 		if (r != CUDA_SUCCESS) { fprintf(stderr, "edge264_b200: cuTensorMapEncodeTiled failed (%d) for %dx%d, windows fall back to gathered loads\n", (int)r, W, H); return 0; }
 	}
@@ -234,7 +236,7 @@ static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, const E264MbRec *r
 	J.tickets = c->d_sync; J.err = c->d_sync + 3; J.flags = c->d_sync + 4;
 	J.resid = c->st[c->stage].d_resid;
 	J.rows_mode = pd->n_intra * 2 > pd->width_mbs * pd->height_mbs;   /* intra pictures: wavefront of row warps */
-	J.word_loads = 0;
+	J.word_loads = 0; J.trace = NULL; J.trace_base = 0; J.phase_slot = 0;
 	{ static int tma = -1; if (tma < 0) { const char *e = getenv("E264B_TMA"); tma = e ? atoi(e) : 1; } J.tmaps = tma ? c->d_tmaps : NULL; }
 	{ static int force = -2; if (force == -2) { const char *e = getenv("E264B_ROWS"); force = e ? atoi(e) : -1; } if (force >= 0) J.rows_mode = force; }
 	if (c->epoch >= (1u << 20)) {   /* row progress counters encode epoch * 2048 + count: restart before it wraps */
@@ -255,7 +257,9 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 	CK(cudaMemsetAsync(c->d_sync, 0, 3 * sizeof(unsigned), c->stream));
 	if (pd->n_coefs > 0) { e264_residual_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++; }
 	if (pd->n_intra < nmb) {
-		if (minb >= 5) e264_inter_kernel<5><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+		if (minb >= 8) e264_inter_kernel<8><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+		else if (minb >= 6) e264_inter_kernel<6><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+		else if (minb >= 5) e264_inter_kernel<5><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
 		else if (minb == 4) e264_inter_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
 		else e264_inter_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
 		c->launches++;
@@ -356,22 +360,76 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, float *ms_total, 
 	size_t npic = cs[0]->kept.size();
 	for (int i = 1; i < n; i++) if (cs[i]->kept.size() < npic) npic = cs[i]->kept.size();
 	uint64_t l0 = 0; for (int i = 0; i < n; i++) l0 += cs[i]->launches;
+	/* E264B_TRACE=<file>: per-launch first-start / last-end device timestamps of the full pass, for timeline analysis */
+	const char *trace_path = getenv("E264B_TRACE");
+	unsigned long long *d_trace = NULL; size_t n_trace = (size_t)reps * npic * n * 4;
+	if (trace_path) {
+		std::vector<unsigned long long> init(n_trace * 2);
+		for (size_t i = 0; i < n_trace; i++) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; }
+		CK(cudaMalloc(&d_trace, n_trace * 16 + 128)); CK(cudaMemcpy(d_trace, init.data(), n_trace * 16, cudaMemcpyHostToDevice)); CK(cudaMemset(d_trace + n_trace * 2, 0, 128));
+	}
+	/* The replay is launch-rate bound when one host thread feeds 32 streams kernel by kernel (measured: 0.8 ms idle
+	 * between a stream's pictures), so each stream's whole sequence is captured into one CUDA graph and the timed
+	 * region launches n graphs.  Epochs restart at 1 inside a graph; its first node clears the sync words, so a graph
+	 * can be launched repeatedly.  E264B_GRAPH=0 keeps the kernel-by-kernel path. */
+	static int use_graph = -1;
+	if (use_graph < 0) { const char *e = getenv("E264B_GRAPH"); use_graph = e ? atoi(e) : 1; }
 	for (int pass = 0; pass < (ms_recon_only ? 2 : 1); pass++) {
+		std::vector<cudaGraphExec_t> execs;
+		if (use_graph) {
+			for (int i = 0; i < n; i++) {
+				E264bDevice *c = cs[i];
+				c->epoch = 0;
+				CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+				CK(cudaMemsetAsync(c->d_sync, 0, (4 + 2 * c->nmb) * sizeof(unsigned), c->stream));
+				for (int r = 0; r < reps; r++)
+					for (size_t k = 0; k < npic; k++) {
+						KeptPic &kp = c->kept[k];
+						PicJob J = make_job(c, &kp.pd, kp.d_recs, kp.d_coefs, kp.d_slices);
+						if (d_trace && pass == 0) { J.trace = d_trace; J.trace_base = (int)((((size_t)r * npic + k) * n + i) * 4); J.phase_slot = (int)(n_trace * 2); }
+						if (launch_picture(c, J, &kp.pd, pass == 0 ? kp.pd.any_deblock : 0)) return -1;
+					}
+				cudaGraph_t g; cudaGraphExec_t ge;
+				CK(cudaStreamEndCapture(c->stream, &g));
+				CK(cudaGraphInstantiate(&ge, g, 0));
+				CK(cudaGraphDestroy(g));
+				CK(cudaGraphUpload(ge, c->stream));
+				execs.push_back(ge);
+			}
+			for (int i = 0; i < n; i++) CK(cudaStreamSynchronize(cs[i]->stream));
+		}
 		CK(cudaEventRecord(start, cs[0]->stream));
 		for (int i = 1; i < n; i++) CK(cudaStreamWaitEvent(cs[i]->stream, start, 0));
-		for (int r = 0; r < reps; r++)
-			for (size_t k = 0; k < npic; k++)
-				for (int i = 0; i < n; i++) {
-					KeptPic &kp = cs[i]->kept[k];
-					PicJob J = make_job(cs[i], &kp.pd, kp.d_recs, kp.d_coefs, kp.d_slices);
-					if (launch_picture(cs[i], J, &kp.pd, pass == 0 ? kp.pd.any_deblock : 0)) return -1;
-				}
+		if (use_graph) {
+			for (int i = 0; i < n; i++) CK(cudaGraphLaunch(execs[i], cs[i]->stream));
+		} else {
+			for (int r = 0; r < reps; r++)
+				for (size_t k = 0; k < npic; k++)
+					for (int i = 0; i < n; i++) {
+						KeptPic &kp = cs[i]->kept[k];
+						PicJob J = make_job(cs[i], &kp.pd, kp.d_recs, kp.d_coefs, kp.d_slices);
+						if (d_trace && pass == 0) { J.trace = d_trace; J.trace_base = (int)((((size_t)r * npic + k) * n + i) * 4); J.phase_slot = (int)(n_trace * 2); }
+						if (launch_picture(cs[i], J, &kp.pd, pass == 0 ? kp.pd.any_deblock : 0)) return -1;
+					}
+		}
 		for (int i = 1; i < n; i++) { CK(cudaEventRecord(ends[i], cs[i]->stream)); CK(cudaStreamWaitEvent(cs[0]->stream, ends[i], 0)); }
 		CK(cudaEventRecord(stop, cs[0]->stream));
 		CK(cudaEventSynchronize(stop));
 		float ms = 0; CK(cudaEventElapsedTime(&ms, start, stop));
 		if (pass == 0) { if (ms_total) *ms_total = ms; uint64_t l1 = 0; for (int i = 0; i < n; i++) l1 += cs[i]->launches; if (launches) *launches = l1 - l0; }
 		else *ms_recon_only = ms;
+		for (auto ge : execs) cudaGraphExecDestroy(ge);
+	}
+	if (d_trace) {
+		std::vector<unsigned long long> h(n_trace * 2 + 16);
+		CK(cudaMemcpy(h.data(), d_trace, n_trace * 16 + 128, cudaMemcpyDeviceToHost)); cudaFree(d_trace);
+		{ unsigned long long tot = 0; for (int i = 0; i < 10; i++) tot += h[n_trace * 2 + i]; if (tot) { fprintf(stderr, "inter kernel phase clocks (%% of warp time):"); for (int i = 0; i < 10; i++) fprintf(stderr, " p%d=%.1f", i, 100.0 * h[n_trace * 2 + i] / tot); fprintf(stderr, "  total warp-cycles %llu\n", tot); } }
+		FILE *f = fopen(trace_path, "w");
+		if (f) {
+			fprintf(f, "rep,pic,stream,kind,start_ns,end_ns\n");
+			for (size_t j = 0; j < n_trace; j++) if (h[2 * j + 1]) fprintf(f, "%zu,%zu,%zu,%zu,%llu,%llu\n", j / 4 / n / npic, j / 4 / n % npic, j / 4 % n, j % 4, h[2 * j], h[2 * j + 1]);
+			fclose(f);
+		}
 	}
 	cudaEventDestroy(start); cudaEventDestroy(stop); for (int i = 0; i < n; i++) cudaEventDestroy(ends[i]);
 	return 0;

@@ -28,8 +28,11 @@ struct PicJob {
 	unsigned *err;
 	int rows_mode;
 	int word_loads;       /* unused (kept for ABI of the job struct) */
-	const void *tmaps;    /* CUtensorMap[n_slots][6]: luma boxes 48x{21,13,9}, chroma boxes 32x{9,5,3}; NULL = no TMA */
+	const void *tmaps;    /* CUtensorMap[6] over the whole frame pool (x, y, slot): luma boxes 48x{21,13,9}, chroma boxes 32x{9,5,3}; NULL = no TMA */
 	int16_t *resid;       /* [nmb][384] residual written by e264_residual_kernel (coded macroblocks only) */
+	unsigned long long *trace;   /* measurement only (E264B_TRACE): [trace_base + kind] = {first warp start, last warp end} in globaltimer ns */
+	int trace_base;
+	int phase_slot;              /* index into trace[] of the 10 phase counters (E264B_PHASES builds) */
 };
 
 #define WARPS_PER_BLOCK 4
@@ -51,6 +54,8 @@ struct __align__(16) WarpSmem {
 	uint8_t ytile[17 * YT_STRIDE];  /* row 0 = samples above the macroblock */
 	uint8_t ctile[2][9 * CT_STRIDE];
 	int dc[24];                     /* scaled DC: 16 luma (raster over blocks), 4 Cb, 4 Cr */
+	uint8_t pt1[256 + 128];         /* second prediction of bi-predicted 8x8 quadrants: luma y*16+x, then Cb, Cr 8x8 */
+	int wq[4][3][4];                /* per 8x8 quadrant and component: {mode, w0, w1, offset | log2wd << 16}, see mc_blend */
 	union {
 		int16_t t8[4 * 64];         /* 8x8 transform transpose buffer */
 		int edge[2][28];            /* intra 8x8 filtered reference samples */
@@ -74,13 +79,44 @@ __device__ __forceinline__ int norm8(int m, int i, int j) {
 	return h264_norm8x8[m][k];
 }
 
-/* spin until flags[idx] == epoch (lane 0), bounded so that a bug cannot hang the GPU */
+/* measurement only: first-start / last-end timestamps of a launch, see e264b_replay */
+struct TraceScope {
+	unsigned long long *t;
+	__device__ __forceinline__ static unsigned long long now() { unsigned long long v; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)); return v; }
+	__device__ __forceinline__ TraceScope(const PicJob &J, int kind) { t = J.trace ? J.trace + 2 * (J.trace_base + kind) : nullptr; if (t && (threadIdx.x & 31) == 0) atomicMin(t, now()); }
+	__device__ __forceinline__ ~TraceScope() { if (t && (threadIdx.x & 31) == 0) atomicMax(t + 1, now()); }
+};
+
+/* -DE264B_PHASES (measurement builds only): per-phase clock accumulation in the inter kernel; lane 0 of each warp
+ * adds its totals to J.trace[PHASE_SLOT + i] at exit.  Phases: 0 ticket+record, 1 residual fetch, 2 rect list,
+ * 3 window issue, 4 TMA wait, 5 luma filter, 6 chroma filter, 7 blend+residual add, 8 store. */
+#ifdef E264B_PHASES
+#define PH_DECL long long ph_acc[10] = {0,0,0,0,0,0,0,0,0,0}; long long ph_t = clock64();
+#define PH(i) do { long long c_ = clock64(); ph_acc[i] += c_ - ph_t; ph_t = c_; } while (0)
+#define PH_ARGS , long long *ph_acc, long long &ph_t
+#define PH_PASS , ph_acc, ph_t
+#define PH_FLUSH(J) do { if ((J).trace && (threadIdx.x & 31) == 0) for (int i_ = 0; i_ < 10; i_++) atomicAdd((J).trace + (J).phase_slot + i_, (unsigned long long)ph_acc[i_]); } while (0)
+#else
+#define PH_DECL
+#define PH(i)
+#define PH_ARGS
+#define PH_PASS
+#define PH_FLUSH(J)
+#endif
+
+/* spin until flags[idx] == epoch (lane 0).  Bounded so that a bug cannot hang the GPU: gives up after ~0.2 s of SM
+ * clocks, or at once when another warp has already raised the error flag. */
 __device__ __forceinline__ bool wait_flag(const unsigned *flags, int idx, unsigned epoch, unsigned *err) {
 	const volatile unsigned *f = flags + idx;
 	unsigned spins = 0;
+	long long t0 = 0;
 	while (*f != epoch) {
 		__nanosleep(64);
-		if (++spins > (1u << 24)) { atomicExch(err, 1u); return false; }
+		if ((++spins & 63) == 0) {
+			if (*(const volatile unsigned *)err) return false;
+			if (t0 == 0) t0 = clock64();
+			else if (clock64() - t0 > 400000000ll) { atomicExch(err, 1u); return false; }
+		}
 	}
 	return true;
 }
@@ -95,14 +131,17 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-/* bounded wait for the phase with the given parity; false = gave up (caller raises the error flag) */
+/* wait for the phase with the given parity, at most ~10 ms of SM clocks (a window arrives in microseconds);
+ * false = gave up (caller raises the error flag) */
 __device__ __forceinline__ bool mbar_wait(void *bar, unsigned parity) {
-	unsigned done = 0, spins = 0;
-	do {
+	unsigned done = 0;
+	const long long t0 = clock64();
+	for (;;) {
 		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
 		             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-	} while (!done && ++spins < (1u << 22));
-	return done != 0;
+		if (done) return true;
+		if (clock64() - t0 > 20000000ll) return false;
+	}
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -473,36 +512,23 @@ __device__ __noinline__ void intra_chroma(WarpSmem *ws, const E264MbRec *r, int 
 /* ------------------------------------------------------------------------------------------ */
 __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
 
-/* 8.4.2.2.1 in compact form (code size matters: the whole kernel must stay instruction-cache resident).
- * mc_half: integer / half-sample value at quarter-sample coordinates (qx,qy) in {0,2,4}^2 relative to G. */
-__device__ __forceinline__ int wp_uni(int p, int w, int o, int logwd) { return clip255((logwd >= 1 ? ((p * w + (1 << (logwd - 1))) >> logwd) : p * w) + o); }
-__device__ __forceinline__ int wp_bi(int p0, int p1, int w0, int w1, int o0, int o1, int logwd) { return clip255(((p0 * w0 + p1 * w1 + (1 << logwd)) >> (logwd + 1)) + ((o0 + o1 + 1) >> 1)); }
-
-/* 8.4.2.3 weighted sample prediction of one sample; wm: 0 store, 1 default average, 2 explicit uni, 3 bi (explicit/implicit).
- * Kept out of line: the kernel must stay within the 32 KB L1.5 instruction cache. */
-__device__ __noinline__ int wblend(int q, int v, int wm, int w0, int w1, int o, int lw) {
-	if (wm == 0) return v;
-	if (wm == 1) return (q + v + 1) >> 1;
-	if (wm == 2) return clip255((lw >= 1 ? ((v * w1 + (1 << (lw - 1))) >> lw) : v * w1) + o);
-	return clip255(((q * w0 + v * w1 + (1 << lw)) >> (lw + 1)) + o);
-}
-
 /* Motion compensation of one macroblock = a list of square rectangles (16, 8 or 4 luma samples wide, one
  * motion vector and one reference each).  Each rectangle needs a (S+5)^2 luma window and two (S/2+1)^2 chroma
  * windows of its reference picture.  Windows that lie inside the picture are fetched by the TMA unit
- * (cp.async.bulk.tensor.2d, one luma and two chroma boxes counted on one mbarrier); windows that touch the
- * border are gathered sample by sample with clamped coordinates (8.4.2.2.1).  Two window buffers per warp:
- * the fetch of rectangle i+1 is in flight while rectangle i is filtered. */
+ * (cp.async.bulk.tensor.3d over (x, y, frame slot), one luma and two chroma boxes counted on one mbarrier);
+ * windows that touch the border are gathered sample by sample with clamped coordinates (8.4.2.2.1).  Two window
+ * buffers per warp: the fetch of rectangle i+1 is in flight while rectangle i is filtered. */
 struct McCtx {
-	uint8_t *win[2];
-	unsigned long long *bar[2];
-	unsigned parity[2];
-	bool pending[2];
-	int lo[2], cob[2], cor[2];   /* where the wanted luma / Cb / Cr window starts inside its rows */
+	uint8_t *win0;                 /* two window buffers, WIN_BYTES apart */
+	unsigned long long *bar0;      /* two mbarriers, adjacent */
+	unsigned parity;               /* bit b: phase parity of barrier b */
+	unsigned pending;              /* bit b: buffer b is being filled by the TMA unit */
+	unsigned offs[2];              /* per buffer: lo | cob << 8 | cor << 16 — where the wanted luma / Cb / Cr window starts inside its rows */
 };
-__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, int y, void *bar) {
-	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-	             :: "r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+/* one box of frame slot z; x must be a multiple of 16 (bytes) */
+__device__ __forceinline__ void tma_load_box(void *dst, const void *tmap, int x, int y, int z, void *bar) {
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+	             :: "r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
 /* rectangle code: bit0 list, bits1-2 size class (0:16 1:8 2:4), bits3-4 x0/4, bits5-6 y0/4 */
@@ -518,20 +544,21 @@ __device__ __forceinline__ void mc_issue(WarpSmem *ws, McCtx &mc, int b, const P
 	const int W = J.w_mbs * 16, H = J.h_mbs * 16;
 	const int X0 = mbx * 16 + x0 + (mvx >> 2) - 2, Y0 = mby * 16 + y0 + (mvy >> 2) - 2;
 	const int CX0 = mbx * 8 + (x0 >> 1) + (mvx >> 3), CY0 = mby * 8 + (y0 >> 1) + (mvy >> 3);
-	uint8_t *win = mc.win[b];
+	uint8_t *win = mc.win0 + b * WIN_BYTES;
+	unsigned long long *bar = mc.bar0 + b;
 	const bool interior = J.tmaps != nullptr && X0 >= 0 && Y0 >= 0 && X0 + WW <= W && Y0 + WW <= H && CX0 >= 0 && CY0 >= 0 && CX0 + CWW <= (W >> 1) && CY0 + CWW <= (H >> 1);
-	mc.pending[b] = interior;
-	mc.lo[b] = mc.cob[b] = mc.cor[b] = 0;
+	mc.pending = (mc.pending & ~(1u << b)) | ((unsigned)interior << b);
+	unsigned offs = 0;
 	if (interior) {
 		const int crx = CX0 + (J.stride_c >> 1);
-		mc.lo[b] = X0 & 15; mc.cob[b] = CX0 & 15; mc.cor[b] = crx & 15;
+		offs = (unsigned)(X0 & 15) | (unsigned)(CX0 & 15) << 8 | (unsigned)(crx & 15) << 16;
 		if (lane == 0) {
-			const char *tm = (const char *)J.tmaps + (size_t)(slot * 6 + sc) * 128;
+			const char *tm = (const char *)J.tmaps + sc * 128;
 			const unsigned bytes = (unsigned)(WIN_STRIDE * WW + 2 * WIN_C_STRIDE * CWW);
-			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mc.bar[b])), "r"(bytes) : "memory");
-			tma_load_2d(win, tm, X0 & ~15, Y0, mc.bar[b]);
-			tma_load_2d(win + WIN_CB_OFF, tm + 3 * 128, CX0 & ~15, CY0, mc.bar[b]);
-			tma_load_2d(win + WIN_CR_OFF, tm + 3 * 128, crx & ~15, CY0, mc.bar[b]);
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+			tma_load_box(win, tm, X0 & ~15, Y0, slot, bar);
+			tma_load_box(win + WIN_CB_OFF, tm + 3 * 128, CX0 & ~15, CY0, slot, bar);
+			tma_load_box(win + WIN_CR_OFF, tm + 3 * 128, crx & ~15, CY0, slot, bar);
 		}
 	} else {
 		const uint8_t *ref = J.frames + (size_t)slot * J.frame_bytes;
@@ -550,45 +577,34 @@ __device__ __forceinline__ void mc_issue(WarpSmem *ws, McCtx &mc, int b, const P
 			win[(pl ? WIN_CR_OFF : WIN_CB_OFF) + row * WIN_C_STRIDE + col] = __ldg(ref + J.plane_y + pl * (J.stride_c >> 1) + (size_t)yy * J.stride_c + xx);
 		}
 	}
+	if (b) mc.offs[1] = offs; else mc.offs[0] = offs;
 }
 
-/* filter + weight the rectangle whose windows sit in buffer b; false = the TMA never completed */
-__device__ __forceinline__ bool mc_compute(WarpSmem *ws, McCtx &mc, int b, const E264MbRec *r, const E264SliceRec *sr, int rect, int lane) {
+/* filter the rectangle whose windows sit in buffer b; the plain prediction goes to the macroblock tile, or to
+ * ws->pt1 when it is the list-1 half of a bi-predicted quadrant (mc_blend combines them).  false = the TMA never
+ * completed. */
+__device__ __forceinline__ bool mc_compute(WarpSmem *ws, McCtx &mc, int b, const E264MbRec *r, int rect, int lane PH_ARGS) {
 	const int l = rect & 1, sc = (rect >> 1) & 3, x0 = ((rect >> 3) & 3) << 2, y0 = ((rect >> 5) & 3) << 2, S = 16 >> sc;
 	const int CW = S >> 1;
 	const int z0 = blk_z(x0 >> 2, y0 >> 2);
 	const int mvx = r->mv[l][z0][0], mvy = r->mv[l][z0][1];
-	const uint8_t *win = mc.win[b];
-	if (mc.pending[b]) {
-		if (!mbar_wait(mc.bar[b], mc.parity[b])) return false;
-		mc.parity[b] ^= 1; mc.pending[b] = false;
+	const uint8_t *win = mc.win0 + b * WIN_BYTES;
+	const unsigned offs = b ? mc.offs[1] : mc.offs[0];
+	if ((mc.pending >> b) & 1) {
+		if (!mbar_wait(mc.bar0 + b, (mc.parity >> b) & 1)) return false;
+		mc.parity ^= 1u << b; mc.pending &= ~(1u << b);
 	} else __syncwarp();
-	/* weighting of this rectangle is uniform (callers guarantee one 8x8 reference pair per rectangle):
-	 * wm 0 store, 1 default average with the list-0 pass, 2 explicit uni, 3 explicit/implicit bi */
+	PH(4);
 	const int i8r = ((y0 >> 3) << 1) | (x0 >> 3);
-	const int r0 = r->ref_idx[0][i8r], r1 = r->ref_idx[1][i8r];
-	int wm = 0, w0[3] = {0, 0, 0}, w1[3] = {0, 0, 0}, oo[3] = {0, 0, 0}, lw[3] = {0, 0, 0};
-	if (l == 1 && r0 >= 0) {
-		if (sr->wp_mode == WP_EXPLICIT) {
-			wm = 3;
-			for (int c = 0; c < 3; c++) { w0[c] = sr->wp_w[0][r0 & 15][c]; w1[c] = sr->wp_w[1][r1 & 15][c]; oo[c] = (sr->wp_o[0][r0 & 15][c] + sr->wp_o[1][r1 & 15][c] + 1) >> 1; lw[c] = c ? sr->chroma_log2_wd : sr->luma_log2_wd; }
-		} else if (sr->wp_mode == WP_IMPLICIT) {
-			wm = 3;
-			int iw = sr->implicit_w1[r0 & 15][r1 & 15];
-			for (int c = 0; c < 3; c++) { w0[c] = 64 - iw; w1[c] = iw; oo[c] = 0; lw[c] = 5; }
-		} else wm = 1;
-	} else if (!(l == 0 && r1 >= 0) && sr->wp_mode == WP_EXPLICIT) {
-		wm = 2;
-		int ri = (l ? r1 : r0) & 15;
-		for (int c = 0; c < 3; c++) { w1[c] = sr->wp_w[l][ri][c]; oo[c] = sr->wp_o[l][ri][c]; lw[c] = c ? sr->chroma_log2_wd : sr->luma_log2_wd; }
-	}
-#define WSTORE(dst, v, c) (dst) = (uint8_t)wblend((dst), (v), wm, w0[c], w1[c], oo[c], lw[c])
+	const bool second = l == 1 && r->ref_idx[0][i8r] >= 0;
+	uint8_t *dl = second ? ws->pt1 + y0 * 16 + x0 : &YT(x0, y0);
+	const int dls = second ? 16 : YT_STRIDE;
 	const int fx = mvx & 3, fy = mvy & 3, sh = 4 - sc;
-	const uint8_t *wl = win + mc.lo[b] + 2 * WIN_STRIDE + 2;
+	const uint8_t *wl = win + (offs & 15) + 2 * WIN_STRIDE + 2;
 	/* one loop per class of fractional position: the branch is uniform for the rectangle */
 #define HSUM(g) tap6((g)[-2], (g)[-1], (g)[0], (g)[1], (g)[2], (g)[3])
 #define VSUM(g) tap6((g)[-2 * WIN_STRIDE], (g)[-WIN_STRIDE], (g)[0], (g)[WIN_STRIDE], (g)[2 * WIN_STRIDE], (g)[3 * WIN_STRIDE])
-#define LUMA_LOOP(EXPR) _Pragma("unroll 1") for (int p = lane; p < S * S; p += 32) { int x = p & (S - 1), y = p >> sh; const uint8_t *g = wl + y * WIN_STRIDE + x; int v = (EXPR); WSTORE(YT(x0 + x, y0 + y), v, 0); }
+#define LUMA_LOOP(EXPR) _Pragma("unroll 1") for (int p = lane; p < S * S; p += 32) { int x = p & (S - 1), y = p >> sh; const uint8_t *g = wl + y * WIN_STRIDE + x; dl[y * dls + x] = (uint8_t)(EXPR); }
 	if (!(fx | fy)) { LUMA_LOOP(g[0]) }
 	else if (!fy) {   /* a, b, c */
 		const int o2 = fx == 3;
@@ -599,10 +615,10 @@ __device__ __forceinline__ bool mc_compute(WarpSmem *ws, McCtx &mc, int b, const
 	} else if ((fx & 1) && (fy & 1)) {   /* e, g, p, r: horizontal half of row y or y+1, vertical half of column x or x+1 */
 		const int ro = fy == 3 ? WIN_STRIDE : 0, cofs = fx == 3;
 		LUMA_LOOP((clip255((HSUM(g + ro) + 16) >> 5) + clip255((VSUM(g + cofs) + 16) >> 5) + 1) >> 1)
-	} else {   /* f, i, j, k, q: centre sample, combined like the reference (int16 wrap) */
+	} else {   /* f, i, j, k, q: centre sample, combined like the reference (int16 wrap, edge264_inter.c:4-9) */
 		const bool vfirst = fx & 1;
 		const int sa = vfirst ? 1 : WIN_STRIDE, sb = vfirst ? WIN_STRIDE : 1;
-		const int second = fx == 2 ? (fy == 2 ? 0 : 1) : 2;          /* 0 none (j), 1 horizontal half b/s, 2 vertical half h/m */
+		const int snd = fx == 2 ? (fy == 2 ? 0 : 1) : 2;          /* 0 none (j), 1 horizontal half b/s, 2 vertical half h/m */
 		const int so = fx == 2 ? (fy == 3 ? WIN_STRIDE : 0) : (fx == 3 ? 1 : 0);
 #pragma unroll 1
 		for (int p = lane; p < S * S; p += 32) {
@@ -613,64 +629,117 @@ __device__ __forceinline__ bool mc_compute(WarpSmem *ws, McCtx &mc, int b, const
 			int af = t[0] + t[5], be = t[1] + t[4], cd = t[2] + t[3];
 			int t16 = (short)(((af - be) >> 2) + (cd - be));
 			int v = clip255(((t16 >> 2) + cd + 32) >> 6);
-			if (second == 1) v = (v + clip255((HSUM(g + so) + 16) >> 5) + 1) >> 1;
-			else if (second == 2) v = (v + clip255((VSUM(g + so) + 16) >> 5) + 1) >> 1;
-			WSTORE(YT(x0 + x, y0 + y), v, 0);
+			if (snd == 1) v = (v + clip255((HSUM(g + so) + 16) >> 5) + 1) >> 1;
+			else if (snd == 2) v = (v + clip255((VSUM(g + so) + 16) >> 5) + 1) >> 1;
+			dl[y * dls + x] = (uint8_t)v;
 		}
 	}
+	__syncwarp(); PH(5);
 	const int cfx = mvx & 7, cfy = mvy & 7;
 	const int cA = (8 - cfx) * (8 - cfy), cB = cfx * (8 - cfy), cC = (8 - cfx) * cfy, cD = cfx * cfy;
+	const int cx0 = x0 >> 1, cy0 = y0 >> 1;
 #pragma unroll 1
 	for (int p = lane; p < 2 * CW * CW; p += 32) {
 		int pl = p >= CW * CW, q = p - pl * CW * CW, x = q & (CW - 1), y = q >> (sh - 1);
-		const uint8_t *cwn = win + (pl ? WIN_CR_OFF + mc.cor[b] : WIN_CB_OFF + mc.cob[b]) + y * WIN_C_STRIDE + x;
+		const uint8_t *cwn = win + (pl ? WIN_CR_OFF + ((offs >> 16) & 15) : WIN_CB_OFF + ((offs >> 8) & 15)) + y * WIN_C_STRIDE + x;
 		int v = (cA * cwn[0] + cB * cwn[1] + cC * cwn[WIN_C_STRIDE] + cD * cwn[WIN_C_STRIDE + 1] + 32) >> 6;
-		if (pl) WSTORE(CT(1, (x0 >> 1) + x, (y0 >> 1) + y), v, 2); else WSTORE(CT(0, (x0 >> 1) + x, (y0 >> 1) + y), v, 1);
+		if (second) ws->pt1[256 + pl * 64 + (cy0 + y) * 8 + cx0 + x] = (uint8_t)v; else CT(pl, cx0 + x, cy0 + y) = (uint8_t)v;
 	}
 #undef LUMA_LOOP
 #undef HSUM
 #undef VSUM
-#undef WSTORE
 	__syncwarp();
+	PH(6);
 	return true;
 }
 
-/* list the rectangles of this macroblock (list 0 first: list 1 blends with what list 0 stored) */
+/* 8.4.2.3 weighted sample prediction, once per macroblock after all rectangles are filtered.  Per 8x8 quadrant
+ * and component, mode: 0 keep, 1 default average of the two predictions, 2 explicit weight on the single
+ * prediction, 3 weighted sum of both (explicit, or implicit with weights 64-w1, w1, shift 6).  Same integer
+ * formulas as the reference's five schemes (edge264_inter.c:1140-1197) after its offset folding. */
+__device__ __forceinline__ void mc_blend(WarpSmem *ws, const E264MbRec *r, const E264SliceRec *sr, int lane) {
+	bool any = false;
+	if (lane < 12) {
+		const int i8 = lane & 3, c = lane >> 2;
+		const int r0 = r->ref_idx[0][i8], r1 = r->ref_idx[1][i8];
+		int mode = 0, w0 = 0, w1 = 0, o = 0, lw = 0;
+		if (r0 >= 0 && r1 >= 0) {
+			if (sr->wp_mode == WP_EXPLICIT) {
+				mode = 3; w0 = sr->wp_w[0][r0 & 15][c]; w1 = sr->wp_w[1][r1 & 15][c];
+				o = (sr->wp_o[0][r0 & 15][c] + sr->wp_o[1][r1 & 15][c] + 1) >> 1; lw = c ? sr->chroma_log2_wd : sr->luma_log2_wd;
+			} else if (sr->wp_mode == WP_IMPLICIT) {
+				mode = 3; w1 = sr->implicit_w1[r0 & 15][r1 & 15]; w0 = 64 - w1; lw = 5;
+			} else mode = 1;
+		} else if (sr->wp_mode == WP_EXPLICIT && (r0 >= 0 || r1 >= 0)) {
+			const int l = r0 >= 0 ? 0 : 1, ri = (l ? r1 : r0) & 15;
+			mode = 2; w1 = sr->wp_w[l][ri][c]; o = sr->wp_o[l][ri][c]; lw = c ? sr->chroma_log2_wd : sr->luma_log2_wd;
+		}
+		ws->wq[i8][c][0] = mode; ws->wq[i8][c][1] = w0; ws->wq[i8][c][2] = w1; ws->wq[i8][c][3] = (o & 0xffff) | (lw << 16);
+		any = mode != 0;
+	}
+	if (!__any_sync(0xffffffffu, any)) return;
+	__syncwarp();
+#pragma unroll 1
+	for (int p = lane; p < 384; p += 32) {
+		int c, i8, a; uint8_t *dst;
+		if (p < 256) { int x = p & 15, y = p >> 4; c = 0; i8 = ((y >> 3) << 1) | (x >> 3); dst = &YT(x, y); }
+		else { int q = p - 256, pl = q >> 6, x = q & 7, y = (q >> 3) & 7; c = 1 + pl; i8 = ((y >> 2) << 1) | (x >> 2); dst = &CT(pl, x, y); }
+		const int b2 = ws->pt1[p];
+		const int4 wv = *(const int4 *)ws->wq[i8][c];
+		const int mode = wv.x, o = (short)(wv.w & 0xffff), lw = wv.w >> 16;
+		a = *dst;
+		if (mode == 1) a = (a + b2 + 1) >> 1;
+		else if (mode == 2) a = clip255((lw >= 1 ? ((a * wv.z + (1 << (lw - 1))) >> lw) : a * wv.z) + o);
+		else if (mode == 3) a = clip255(((a * wv.y + b2 * wv.z + (1 << lw)) >> (lw + 1)) + o);
+		*dst = (uint8_t)a;
+	}
+	__syncwarp();
+}
+
+/* list the rectangles of this macroblock (list 0 first).  Lane 16*l + z looks at 4x4 block z of list l: two
+ * ballots tell which lists are one 16x16 partition and which 8x8 quadrants are uniform. */
 __device__ __forceinline__ int mc_rects(const E264MbRec *r, uint8_t *out, int lane) {
+	const int l = lane >> 4, z = lane & 15, lead = lane & 16;
+	const int v = *(const int *)r->mv[l][z];                                   /* (mvx, mvy) as one word */
+	const int refs = (r->ref_idx[l][z >> 2] & 0xff) | ((r->ref_idx[l ^ 1][z >> 2] & 0xff) << 8);
+	const bool e16 = v == __shfl_sync(0xffffffffu, v, lead) && refs == __shfl_sync(0xffffffffu, refs, lead);
+	const bool e8 = v == __shfl_sync(0xffffffffu, v, lead | (z & 12));
+	const unsigned m16 = __ballot_sync(0xffffffffu, e16), m8 = __ballot_sync(0xffffffffu, e8);
 	int n = 0;
-	for (int l = 0; l < 2; l++) {
-		int z = lane & 15;
-		bool same = r->mv[l][z][0] == r->mv[l][0][0] && r->mv[l][z][1] == r->mv[l][0][1] && r->ref_idx[l][z >> 2] == r->ref_idx[l][0] && r->ref_idx[l ^ 1][z >> 2] == r->ref_idx[l ^ 1][0];
-		if (__all_sync(0xffffffffu, same)) {
-			if (r->ref_idx[l][0] >= 0) { if (lane == 0) out[n] = (uint8_t)RECT(l, 0, 0, 0); n++; }
+#pragma unroll
+	for (int ll = 0; ll < 2; ll++) {
+		if (((m16 >> (16 * ll)) & 0xffff) == 0xffff) {
+			if (r->ref_idx[ll][0] >= 0) { if (lane == 0) out[n] = (uint8_t)RECT(ll, 0, 0, 0); n++; }
 			continue;
 		}
+#pragma unroll
 		for (int i8 = 0; i8 < 4; i8++) {
-			if (r->ref_idx[l][i8] < 0) continue;
-			int zb = i8 * 4, x0 = (i8 & 1) * 8, y0 = (i8 >> 1) * 8;
-			bool s8 = true;
-			for (int k = 1; k < 4; k++) s8 = s8 && r->mv[l][zb + k][0] == r->mv[l][zb][0] && r->mv[l][zb + k][1] == r->mv[l][zb][1];
-			if (s8) { if (lane == 0) out[n] = (uint8_t)RECT(l, 1, x0, y0); n++; }
-			else for (int k = 0; k < 4; k++) { if (lane == 0) out[n] = (uint8_t)RECT(l, 2, x0 + (k & 1) * 4, y0 + (k >> 1) * 4); n++; }
+			if (r->ref_idx[ll][i8] < 0) continue;
+			const int x0 = (i8 & 1) * 8, y0 = (i8 >> 1) * 8;
+			if (((m8 >> (16 * ll + 4 * i8)) & 15) == 15) { if (lane == 0) out[n] = (uint8_t)RECT(ll, 1, x0, y0); n++; }
+			else { if (lane == 0) { for (int k = 0; k < 4; k++) out[n + k] = (uint8_t)RECT(ll, 2, x0 + (k & 1) * 4, y0 + (k >> 1) * 4); } n += 4; }
 		}
 	}
 	__syncwarp();
 	return n;
 }
 
-__device__ __noinline__ bool inter_predict(WarpSmem *ws, McCtx &mc, uint8_t *rects, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int lane) {
+__device__ __noinline__ bool inter_predict(WarpSmem *ws, McCtx &mc, uint8_t *rects, const PicJob &J, const E264MbRec *r, const E264SliceRec *sr, int mbx, int mby, int lane PH_ARGS) {
 	const int n = mc_rects(r, rects, lane);
+	PH(2);
 #pragma unroll 1
 	for (int i = -1; i < n; i++) {
-		if (i + 1 < n) mc_issue(ws, mc, (i + 1) & 1, J, r, mbx, mby, rects[i + 1], lane);
-		if (i >= 0 && !mc_compute(ws, mc, i & 1, r, sr, rects[i], lane)) return false;
+		if (i + 1 < n) { mc_issue(ws, mc, (i + 1) & 1, J, r, mbx, mby, rects[i + 1], lane); PH(3); }
+		if (i >= 0 && !mc_compute(ws, mc, i & 1, r, rects[i], lane PH_PASS)) return false;
 	}
+	mc_blend(ws, r, sr, lane);
 	/* add the residual */
 #pragma unroll
 	for (int k = 0; k < 8; k++) { int p = lane + 32 * k, x = p & 15, y = p >> 4; YT(x, y) = (uint8_t)clip255((short)((int)YT(x, y) + ws->res[p])); }
 #pragma unroll
 	for (int k = 0; k < 4; k++) { int p = lane + 32 * k, pl = p >> 6, x = p & 7, y = (p >> 3) & 7; CT(pl, x, y) = (uint8_t)clip255((short)((int)CT(pl, x, y) + ws->res[256 + p])); }
 	__syncwarp();
+	PH(7);
 	return true;
 }
 
@@ -715,6 +784,7 @@ struct __align__(16) ResStage {
 };
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_residual_kernel(PicJob J) {
+	TraceScope trace_(J, 0);
 	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
 	__shared__ ResStage stage[WARPS_PER_BLOCK][2];
 	__shared__ __align__(8) unsigned long long bars[WARPS_PER_BLOCK][2];
@@ -763,6 +833,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_residual_kernel(Pic
 /* ---- kernel 2: inter macroblocks: motion compensation + weighting + residual (no dependencies) ---- */
 template <int MINB>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) e264_inter_kernel(PicJob J) {
+	TraceScope trace_(J, 1);
 	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
 	__shared__ __align__(128) uint8_t wins[WARPS_PER_BLOCK][2][WIN_BYTES];
 	__shared__ __align__(8) unsigned long long bars[WARPS_PER_BLOCK][2];
@@ -770,37 +841,51 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) e264_inter_kernel(
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	WarpSmem *ws = &smem[w];
 	McCtx mc;
-	mc.win[0] = wins[w][0]; mc.win[1] = wins[w][1]; mc.bar[0] = &bars[w][0]; mc.bar[1] = &bars[w][1];
-	mc.parity[0] = mc.parity[1] = 0; mc.pending[0] = mc.pending[1] = false;
+	mc.win0 = wins[w][0]; mc.bar0 = &bars[w][0];
+	mc.parity = 0; mc.pending = 0; mc.offs[0] = mc.offs[1] = 0;
 	if (lane == 0) {
-		mbar_init(mc.bar[0], 1); mbar_init(mc.bar[1], 1);
+		mbar_init(mc.bar0, 1); mbar_init(mc.bar0 + 1, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
 	/* the tensor maps were written by the host (cudaMemcpy): acquire them for the tensormap proxy once per block */
 	if (J.tmaps != nullptr) {
-		for (int i = threadIdx.x; i < J.n_slots * 6; i += blockDim.x)
+		if (threadIdx.x < 6) { const int i = threadIdx.x;
 			asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" :: "l"((const char *)J.tmaps + (size_t)i * 128) : "memory");
+		}
 	}
 	__syncthreads();
 	const int nmb = J.w_mbs * J.h_mbs;
 	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
+	PH_DECL
+	/* Software pipeline over macroblocks: the ticket of macroblock i+2 and the record of macroblock i+1 are in
+	 * flight while macroblock i is predicted (the atomic's and the load's round trips cost nothing). */
+	unsigned tnext = 0, tcur = 0;
+	if (lane == 0) { tcur = atomicAdd(J.tickets, 1u); tnext = atomicAdd(J.tickets, 1u); }
+	tcur = __shfl_sync(0xffffffffu, tcur, 0);
+	uint4 rq = make_uint4(0, 0, 0, 0);
+	if (tcur < (unsigned)nmb && lane < 12) rq = __ldg((const uint4 *)(J.recs + tcur) + lane);
 	for (;;) {
-		unsigned t = 0;
-		if (lane == 0) t = atomicAdd(J.tickets, 1u);
-		t = __shfl_sync(0xffffffffu, t, 0);
+		const unsigned t = tcur;
 		if (t >= (unsigned)nmb) break;
-		const int mb = (int)t, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
-		if (J.recs[mb].kind != MBK_INTER) continue;
-		if (lane < 12) ws->rec4[lane] = __ldg((const uint4 *)(J.recs + mb) + lane);
+		if (lane < 12) ws->rec4[lane] = rq;
+		tcur = __shfl_sync(0xffffffffu, tnext, 0);
+		if (lane == 0) tnext = atomicAdd(J.tickets, 1u);
+		if (tcur < (unsigned)nmb && lane < 12) rq = __ldg((const uint4 *)(J.recs + tcur) + lane);
 		__syncwarp();
+		const int mb = (int)t, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
+		if (((const E264MbRec *)ws->rec4)->kind != MBK_INTER) { __syncwarp(); continue; }
 		const E264MbRec *r = (const E264MbRec *)ws->rec4;
+		PH(0);
 		fetch_residual(ws, J, r, mb, lane);
-		if (!inter_predict(ws, mc, rects[w], J, r, J.slices + r->slice_idx, mbx, mby, lane)) { if (lane == 0) atomicExch(J.err, 4u); break; }
+		PH(1);
+		if (!inter_predict(ws, mc, rects[w], J, r, J.slices + r->slice_idx, mbx, mby, lane PH_PASS)) { if (lane == 0) atomicExch(J.err, 4u); break; }
 		store_mb(ws, J, dst + (size_t)(mby * 16) * J.stride_y + mbx * 16, dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8, lane);
 		if (lane == 0) J.flags[mb] = J.epoch;     /* visible to the intra kernel through the kernel boundary */
 		__syncwarp();
+		PH(8);
 	}
+	PH_FLUSH(J);
 }
 
 /* ---- kernel 3: intra (and I_PCM) macroblocks, in dependency order ----
@@ -868,6 +953,7 @@ __device__ __forceinline__ void intra_mb(WarpSmem *ws, const PicJob &J, uint8_t 
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_intra_kernel(PicJob J) {
+	TraceScope trace_(J, 2);
 	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
 	const int lane = threadIdx.x & 31;
 	WarpSmem *ws = &smem[threadIdx.x >> 5];
@@ -961,6 +1047,7 @@ __device__ __forceinline__ void filter_chroma(uint8_t *pix, int step, int bs, in
  * progress counter (value = epoch * 2048 + macroblocks finished).  Row y may process macroblock x once
  * row y-1 has finished x+1 (its left-edge filter touches columns 13..15 of macroblock x above us). */
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_deblock_kernel(PicJob J) {
+	TraceScope trace_(J, 3);
 	__shared__ DbSmem smem[WARPS_PER_BLOCK];
 	const int lane = threadIdx.x & 31;
 	DbSmem *ds = &smem[threadIdx.x >> 5];
@@ -1045,7 +1132,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_deblock_kernel(PicJ
 					/* the row above must have finished macroblock mbx+1 (or its whole row) */
 					if (lane == 0) {
 						unsigned need = base + (unsigned)min(mbx + 2, W), spins = 0;
-						while ((int)(progress[mby - 1] - need) < 0) { __nanosleep(32); if (++spins > (1u << 24)) { atomicExch(J.err, 1u); break; } }
+						while ((int)(progress[mby - 1] - need) < 0) { __nanosleep(32); if ((++spins & 63) == 0 && (*(const volatile unsigned *)J.err || spins > (1u << 22))) { atomicExch(J.err, 1u); break; } }
 						__threadfence();
 					}
 					__syncwarp();
