@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <cuda.h>            /* CUtensorMap types only: the encoder is resolved at run time, libcuda is not linked */
 #include <stdio.h>
+#include <time.h>
+#include <unistd.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -36,7 +38,7 @@ struct E264bDevice {
 	int dev; cudaStream_t stream;
 	E264PicDesc g; int n_slots; size_t nmb; uint32_t coef_cap;
 	uint8_t *d_frames;
-	void *d_tmaps;               /* CUtensorMap[6] over the frame pool, or NULL when the geometry does not fit TMA's rules */
+	void *d_tmaps;               /* CUtensorMap[n_slots][6] over the frame pool, or NULL when the geometry does not fit TMA's rules */
 	E264MbRec *h_recs[E264_MAX_SLOTS]; cudaEvent_t rec_up[E264_MAX_SLOTS]; bool rec_busy[E264_MAX_SLOTS];
 	Staging st[NSTAGE]; int stage;
 	unsigned *d_sync;            /* [0..2] tickets (inter, deblock, intra), [3] err, then flags[2*nmb] */
@@ -129,8 +131,8 @@ extern "C" void e264b_destroy(E264bDevice *c) {
 }
 
 
-/* Tensor maps for the motion-compensation windows: rank-3 (x, y, frame slot), luma boxes 48 x {21,13,9} over the
- * W x H luma planes and chroma boxes 32 x {9,5,3} over the Cb|Cr rows (Cr starts stride_c/2 bytes into a row).
+/* Tensor maps for the motion-compensation windows: per frame slot, luma boxes 48 x {21,13,9} over the W x H luma
+ * plane and chroma boxes 32 x {9,5,3} over the Cb|Cr rows (one 2-D tensor: Cr starts stride_c/2 bytes into a row).
  * Returns 0 and leaves d_tmaps NULL when TMA cannot describe the geometry (tiny pictures, odd strides, old driver):
  * the kernel then gathers every window with clamped loads. */
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
@@ -147,20 +149,18 @@ static int build_tensor_maps(E264bDevice *c) {
 		else { cudaGetLastError(); fprintf(stderr, "edge264_b200: cuTensorMapEncodeTiled unavailable, windows fall back to gathered loads\n"); }
 	}
 	if (!enc) return 0;
-	/* six rank-3 maps (x, y, frame slot) cover every reference of every picture: few enough to stay in the TMA
-	 * unit's descriptor cache */
-	std::vector<CUtensorMap> maps(6);
 	static const cuuint32_t lrows[3] = {21, 13, 9}, crows[3] = {9, 5, 3};
-	for (int k = 0; k < 6; k++) {
+	std::vector<CUtensorMap> maps((size_t)c->n_slots * 6);
+	for (int s = 0; s < c->n_slots; s++) for (int k = 0; k < 6; k++) {
 		const bool chroma = k >= 3;
-		uint8_t *base = c->d_frames + (chroma ? g->plane_y : 0);
-		cuuint64_t dims[3] = {(cuuint64_t)(chroma ? (g->stride_c >> 1) + (W >> 1) : W), (cuuint64_t)(chroma ? H >> 1 : H), (cuuint64_t)c->n_slots};
-		cuuint64_t strides[2] = {(cuuint64_t)(chroma ? g->stride_c : g->stride_y), (cuuint64_t)g->frame_bytes};
-		cuuint32_t box[3] = {chroma ? 32u : 48u, chroma ? crows[k - 3] : lrows[k], 1};
-		cuuint32_t estr[3] = {1, 1, 1};
-		CUresult r = enc(&maps[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
+		uint8_t *base = c->d_frames + (size_t)s * g->frame_bytes + (chroma ? g->plane_y : 0);
+		cuuint64_t dims[2] = {(cuuint64_t)(chroma ? (g->stride_c >> 1) + (W >> 1) : W), (cuuint64_t)(chroma ? H >> 1 : H)};
+		cuuint64_t strides[1] = {(cuuint64_t)(chroma ? g->stride_c : g->stride_y)};
+		cuuint32_t box[2] = {chroma ? 32u : 48u, chroma ? crows[k - 3] : lrows[k]};
+		cuuint32_t estr[2] = {1, 1};
+		CUresult r = enc(&maps[(size_t)s * 6 + k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
 		                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-		if (r != CUDA_SUCCESS) { fprintf(stderr, "edge264_b200: cuTensorMapEncodeTiled failed (%d) for %dx%d, windows fall back to gathered loads\n", (int)r, W, H); return 0; }
+		if (r != CUDA_SUCCESS) return 0;
 	}
 	CK(cudaMalloc(&c->d_tmaps, maps.size() * sizeof(CUtensorMap)));
 	CK(cudaMemcpy(c->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
@@ -287,6 +287,14 @@ extern "C" int e264b_submit(E264bDevice *c, const E264PicDesc *pd, uint8_t *host
 	c->h2d_bytes += rec_bytes + coef_bytes + sl_bytes;
 	PicJob J = make_job(c, pd, s->d_recs, s->d_coefs, s->d_slices);
 	if (launch_picture(c, J, pd, pd->any_deblock)) return -1;
+	{	/* E264B_DEBUG_SYNC=1: synchronise after every picture and report the device error word (debugging aid) */
+		static int dbg = -1; if (dbg < 0) { const char *e = getenv("E264B_DEBUG_SYNC"); dbg = e ? atoi(e) : 0; }
+		if (dbg) {
+			fprintf(stderr, "e264b: picture slot %d epoch %u (intra %d of %d, coefs %u) launched, waiting...\n", pd->dst_slot, J.epoch, pd->n_intra, J.w_mbs * J.h_mbs, pd->n_coefs);
+			cudaError_t e = cudaStreamSynchronize(c->stream); unsigned v = 0; cudaMemcpy(&v, c->d_sync + 3, sizeof(v), cudaMemcpyDeviceToHost);
+			fprintf(stderr, "e264b:   -> %s, device error word %u\n", cudaGetErrorString(e), v);
+		}
+	}
 	if (host_out) { CK(cudaMemcpyAsync(host_out, c->d_frames + (size_t)pd->dst_slot * pd->frame_bytes, (size_t)pd->frame_bytes - 16, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (size_t)pd->frame_bytes - 16; }
 	if (c->keep) {
 		KeptPic k; k.pd = *pd;
@@ -371,9 +379,10 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, float *ms_total, 
 	/* The replay is launch-rate bound when one host thread feeds 32 streams kernel by kernel (measured: 0.8 ms idle
 	 * between a stream's pictures), so each stream's whole sequence is captured into one CUDA graph and the timed
 	 * region launches n graphs.  Epochs restart at 1 inside a graph; its first node clears the sync words, so a graph
-	 * can be launched repeatedly.  E264B_GRAPH=0 keeps the kernel-by-kernel path. */
+	 * can be launched repeatedly.  E264B_GRAPH=1 selects it; measured on B200 the graphs run only ~8 streams concurrently (7.5k fps against 7.9k kernel by
+	 * kernel), so kernel-by-kernel launching stays the default. */
 	static int use_graph = -1;
-	if (use_graph < 0) { const char *e = getenv("E264B_GRAPH"); use_graph = e ? atoi(e) : 1; }
+	if (use_graph < 0) { const char *e = getenv("E264B_GRAPH"); use_graph = e ? atoi(e) : 0; }
 	for (int pass = 0; pass < (ms_recon_only ? 2 : 1); pass++) {
 		std::vector<cudaGraphExec_t> execs;
 		if (use_graph) {

@@ -28,7 +28,7 @@ struct PicJob {
 	unsigned *err;
 	int rows_mode;
 	int word_loads;       /* unused (kept for ABI of the job struct) */
-	const void *tmaps;    /* CUtensorMap[6] over the whole frame pool (x, y, slot): luma boxes 48x{21,13,9}, chroma boxes 32x{9,5,3}; NULL = no TMA */
+	const void *tmaps;    /* CUtensorMap[n_slots][6]: luma boxes 48x{21,13,9}, chroma boxes 32x{9,5,3}; NULL = no TMA */
 	int16_t *resid;       /* [nmb][384] residual written by e264_residual_kernel (coded macroblocks only) */
 	unsigned long long *trace;   /* measurement only (E264B_TRACE): [trace_base + kind] = {first warp start, last warp end} in globaltimer ns */
 	int trace_base;
@@ -131,17 +131,18 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-/* wait for the phase with the given parity, at most ~10 ms of SM clocks (a window arrives in microseconds);
- * false = gave up (caller raises the error flag) */
+/* wait for the phase with the given parity; gives up after ~10 ms of SM clocks (a window arrives in
+ * microseconds), false = gave up (the caller raises the error flag).  One loop, one exit: ptxas reconverges the
+ * warp behind it, which the __syncwarp()s that follow rely on (they compile to NOPs where the compiler has proved
+ * convergence). */
 __device__ __forceinline__ bool mbar_wait(void *bar, unsigned parity) {
 	unsigned done = 0;
 	const long long t0 = clock64();
-	for (;;) {
+	do {
 		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
 		             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-		if (done) return true;
-		if (clock64() - t0 > 20000000ll) return false;
-	}
+	} while (!done && clock64() - t0 < 20000000ll);
+	return done != 0;
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -515,7 +516,7 @@ __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { 
 /* Motion compensation of one macroblock = a list of square rectangles (16, 8 or 4 luma samples wide, one
  * motion vector and one reference each).  Each rectangle needs a (S+5)^2 luma window and two (S/2+1)^2 chroma
  * windows of its reference picture.  Windows that lie inside the picture are fetched by the TMA unit
- * (cp.async.bulk.tensor.3d over (x, y, frame slot), one luma and two chroma boxes counted on one mbarrier);
+ * (cp.async.bulk.tensor.2d, one luma and two chroma boxes counted on one mbarrier);
  * windows that touch the border are gathered sample by sample with clamped coordinates (8.4.2.2.1).  Two window
  * buffers per warp: the fetch of rectangle i+1 is in flight while rectangle i is filtered. */
 struct McCtx {
@@ -525,10 +526,10 @@ struct McCtx {
 	unsigned pending;              /* bit b: buffer b is being filled by the TMA unit */
 	unsigned offs[2];              /* per buffer: lo | cob << 8 | cor << 16 — where the wanted luma / Cb / Cr window starts inside its rows */
 };
-/* one box of frame slot z; x must be a multiple of 16 (bytes) */
+/* one box of frame slot z (its six maps follow each other); x must be a multiple of 16 (bytes) */
 __device__ __forceinline__ void tma_load_box(void *dst, const void *tmap, int x, int y, int z, void *bar) {
-	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-	             :: "r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+	             :: "r"(smem_u32(dst)), "l"((const char *)tmap + (size_t)z * 6 * 128), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
 }
 
 /* rectangle code: bit0 list, bits1-2 size class (0:16 1:8 2:4), bits3-4 x0/4, bits5-6 y0/4 */
@@ -696,28 +697,23 @@ __device__ __forceinline__ void mc_blend(WarpSmem *ws, const E264MbRec *r, const
 	__syncwarp();
 }
 
-/* list the rectangles of this macroblock (list 0 first).  Lane 16*l + z looks at 4x4 block z of list l: two
- * ballots tell which lists are one 16x16 partition and which 8x8 quadrants are uniform. */
+/* list the rectangles of this macroblock (list 0 first: list 1 blends with what list 0 stored) */
 __device__ __forceinline__ int mc_rects(const E264MbRec *r, uint8_t *out, int lane) {
-	const int l = lane >> 4, z = lane & 15, lead = lane & 16;
-	const int v = *(const int *)r->mv[l][z];                                   /* (mvx, mvy) as one word */
-	const int refs = (r->ref_idx[l][z >> 2] & 0xff) | ((r->ref_idx[l ^ 1][z >> 2] & 0xff) << 8);
-	const bool e16 = v == __shfl_sync(0xffffffffu, v, lead) && refs == __shfl_sync(0xffffffffu, refs, lead);
-	const bool e8 = v == __shfl_sync(0xffffffffu, v, lead | (z & 12));
-	const unsigned m16 = __ballot_sync(0xffffffffu, e16), m8 = __ballot_sync(0xffffffffu, e8);
 	int n = 0;
-#pragma unroll
-	for (int ll = 0; ll < 2; ll++) {
-		if (((m16 >> (16 * ll)) & 0xffff) == 0xffff) {
-			if (r->ref_idx[ll][0] >= 0) { if (lane == 0) out[n] = (uint8_t)RECT(ll, 0, 0, 0); n++; }
+	for (int l = 0; l < 2; l++) {
+		int z = lane & 15;
+		bool same = r->mv[l][z][0] == r->mv[l][0][0] && r->mv[l][z][1] == r->mv[l][0][1] && r->ref_idx[l][z >> 2] == r->ref_idx[l][0] && r->ref_idx[l ^ 1][z >> 2] == r->ref_idx[l ^ 1][0];
+		if (__all_sync(0xffffffffu, same)) {
+			if (r->ref_idx[l][0] >= 0) { if (lane == 0) out[n] = (uint8_t)RECT(l, 0, 0, 0); n++; }
 			continue;
 		}
-#pragma unroll
 		for (int i8 = 0; i8 < 4; i8++) {
-			if (r->ref_idx[ll][i8] < 0) continue;
-			const int x0 = (i8 & 1) * 8, y0 = (i8 >> 1) * 8;
-			if (((m8 >> (16 * ll + 4 * i8)) & 15) == 15) { if (lane == 0) out[n] = (uint8_t)RECT(ll, 1, x0, y0); n++; }
-			else { if (lane == 0) { for (int k = 0; k < 4; k++) out[n + k] = (uint8_t)RECT(ll, 2, x0 + (k & 1) * 4, y0 + (k >> 1) * 4); } n += 4; }
+			if (r->ref_idx[l][i8] < 0) continue;
+			int zb = i8 * 4, x0 = (i8 & 1) * 8, y0 = (i8 >> 1) * 8;
+			bool s8 = true;
+			for (int k = 1; k < 4; k++) s8 = s8 && r->mv[l][zb + k][0] == r->mv[l][zb][0] && r->mv[l][zb + k][1] == r->mv[l][zb][1];
+			if (s8) { if (lane == 0) out[n] = (uint8_t)RECT(l, 1, x0, y0); n++; }
+			else for (int k = 0; k < 4; k++) { if (lane == 0) out[n] = (uint8_t)RECT(l, 2, x0 + (k & 1) * 4, y0 + (k >> 1) * 4); n++; }
 		}
 	}
 	__syncwarp();
@@ -850,7 +846,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) e264_inter_kernel(
 	}
 	/* the tensor maps were written by the host (cudaMemcpy): acquire them for the tensormap proxy once per block */
 	if (J.tmaps != nullptr) {
-		if (threadIdx.x < 6) { const int i = threadIdx.x;
+		for (int i = threadIdx.x; i < J.n_slots * 6; i += blockDim.x) {
 			asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" :: "l"((const char *)J.tmaps + (size_t)i * 128) : "memory");
 		}
 	}
@@ -858,23 +854,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) e264_inter_kernel(
 	const int nmb = J.w_mbs * J.h_mbs;
 	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
 	PH_DECL
-	/* Software pipeline over macroblocks: the ticket of macroblock i+2 and the record of macroblock i+1 are in
-	 * flight while macroblock i is predicted (the atomic's and the load's round trips cost nothing). */
-	unsigned tnext = 0, tcur = 0;
-	if (lane == 0) { tcur = atomicAdd(J.tickets, 1u); tnext = atomicAdd(J.tickets, 1u); }
-	tcur = __shfl_sync(0xffffffffu, tcur, 0);
-	uint4 rq = make_uint4(0, 0, 0, 0);
-	if (tcur < (unsigned)nmb && lane < 12) rq = __ldg((const uint4 *)(J.recs + tcur) + lane);
+	/* tickets are drawn one macroblock ahead: the atomic's round trip overlaps the previous macroblock */
+	unsigned tnext = 0;
+	if (lane == 0) tnext = atomicAdd(J.tickets, 1u);
 	for (;;) {
-		const unsigned t = tcur;
+		const unsigned t = __shfl_sync(0xffffffffu, tnext, 0);
 		if (t >= (unsigned)nmb) break;
-		if (lane < 12) ws->rec4[lane] = rq;
-		tcur = __shfl_sync(0xffffffffu, tnext, 0);
 		if (lane == 0) tnext = atomicAdd(J.tickets, 1u);
-		if (tcur < (unsigned)nmb && lane < 12) rq = __ldg((const uint4 *)(J.recs + tcur) + lane);
-		__syncwarp();
 		const int mb = (int)t, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
-		if (((const E264MbRec *)ws->rec4)->kind != MBK_INTER) { __syncwarp(); continue; }
+		if (__ldg(&J.recs[mb].kind) != MBK_INTER) continue;
+		if (lane < 12) ws->rec4[lane] = __ldg((const uint4 *)(J.recs + mb) + lane);
+		__syncwarp();
 		const E264MbRec *r = (const E264MbRec *)ws->rec4;
 		PH(0);
 		fetch_residual(ws, J, r, mb, lane);
