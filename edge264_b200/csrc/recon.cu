@@ -150,17 +150,19 @@ static int build_tensor_maps(E264bDevice *c) {
 	}
 	if (!enc) return 0;
 	static const cuuint32_t lrows[3] = {21, 13, 9}, crows[3] = {9, 5, 3};
-	std::vector<CUtensorMap> maps((size_t)c->n_slots * 6);
-	for (int s = 0; s < c->n_slots; s++) for (int k = 0; k < 6; k++) {
+	/* six rank-3 maps (x, y, frame slot) serve every reference of every picture: few enough to stay in the TMA
+	 * unit's descriptor cache (with six maps per slot the issue of the three loads took 25% of the warps' time) */
+	std::vector<CUtensorMap> maps(6);
+	for (int k = 0; k < 6; k++) {
 		const bool chroma = k >= 3;
-		uint8_t *base = c->d_frames + (size_t)s * g->frame_bytes + (chroma ? g->plane_y : 0);
-		cuuint64_t dims[2] = {(cuuint64_t)(chroma ? (g->stride_c >> 1) + (W >> 1) : W), (cuuint64_t)(chroma ? H >> 1 : H)};
-		cuuint64_t strides[1] = {(cuuint64_t)(chroma ? g->stride_c : g->stride_y)};
-		cuuint32_t box[2] = {chroma ? 32u : 48u, chroma ? crows[k - 3] : lrows[k]};
-		cuuint32_t estr[2] = {1, 1};
-		CUresult r = enc(&maps[(size_t)s * 6 + k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+		uint8_t *base = c->d_frames + (chroma ? g->plane_y : 0);
+		cuuint64_t dims[3] = {(cuuint64_t)(chroma ? (g->stride_c >> 1) + (W >> 1) : W), (cuuint64_t)(chroma ? H >> 1 : H), (cuuint64_t)c->n_slots};
+		cuuint64_t strides[2] = {(cuuint64_t)(chroma ? g->stride_c : g->stride_y), (cuuint64_t)g->frame_bytes};
+		cuuint32_t box[3] = {chroma ? 32u : 48u, chroma ? crows[k - 3] : lrows[k], 1};
+		cuuint32_t estr[3] = {1, 1, 1};
+		CUresult r = enc(&maps[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
 		                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-		if (r != CUDA_SUCCESS) return 0;
+		if (r != CUDA_SUCCESS) { fprintf(stderr, "edge264_b200: cuTensorMapEncodeTiled failed (%d) for %dx%d, windows fall back to gathered loads\n", (int)r, W, H); return 0; }
 	}
 	CK(cudaMalloc(&c->d_tmaps, maps.size() * sizeof(CUtensorMap)));
 	CK(cudaMemcpy(c->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));

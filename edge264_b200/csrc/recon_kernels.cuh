@@ -28,7 +28,7 @@ struct PicJob {
 	unsigned *err;
 	int rows_mode;
 	int word_loads;       /* unused (kept for ABI of the job struct) */
-	const void *tmaps;    /* CUtensorMap[n_slots][6]: luma boxes 48x{21,13,9}, chroma boxes 32x{9,5,3}; NULL = no TMA */
+	const void *tmaps;    /* CUtensorMap[6] over the whole frame pool (x, y, slot): luma boxes 48x{21,13,9}, chroma boxes 32x{9,5,3}; NULL = no TMA */
 	int16_t *resid;       /* [nmb][384] residual written by e264_residual_kernel (coded macroblocks only) */
 	unsigned long long *trace;   /* measurement only (E264B_TRACE): [trace_base + kind] = {first warp start, last warp end} in globaltimer ns */
 	int trace_base;
@@ -516,7 +516,7 @@ __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { 
 /* Motion compensation of one macroblock = a list of square rectangles (16, 8 or 4 luma samples wide, one
  * motion vector and one reference each).  Each rectangle needs a (S+5)^2 luma window and two (S/2+1)^2 chroma
  * windows of its reference picture.  Windows that lie inside the picture are fetched by the TMA unit
- * (cp.async.bulk.tensor.2d, one luma and two chroma boxes counted on one mbarrier);
+ * (cp.async.bulk.tensor.3d over (x, y, frame slot), one luma and two chroma boxes counted on one mbarrier);
  * windows that touch the border are gathered sample by sample with clamped coordinates (8.4.2.2.1).  Two window
  * buffers per warp: the fetch of rectangle i+1 is in flight while rectangle i is filtered. */
 struct McCtx {
@@ -526,10 +526,10 @@ struct McCtx {
 	unsigned pending;              /* bit b: buffer b is being filled by the TMA unit */
 	unsigned offs[2];              /* per buffer: lo | cob << 8 | cor << 16 — where the wanted luma / Cb / Cr window starts inside its rows */
 };
-/* one box of frame slot z (its six maps follow each other); x must be a multiple of 16 (bytes) */
+/* one box of frame slot z (third tensor coordinate); x must be a multiple of 16 (bytes) */
 __device__ __forceinline__ void tma_load_box(void *dst, const void *tmap, int x, int y, int z, void *bar) {
-	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-	             :: "r"(smem_u32(dst)), "l"((const char *)tmap + (size_t)z * 6 * 128), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+	             :: "r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
 /* rectangle code: bit0 list, bits1-2 size class (0:16 1:8 2:4), bits3-4 x0/4, bits5-6 y0/4 */
@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) e264_inter_kernel(
 	}
 	/* the tensor maps were written by the host (cudaMemcpy): acquire them for the tensormap proxy once per block */
 	if (J.tmaps != nullptr) {
-		for (int i = threadIdx.x; i < J.n_slots * 6; i += blockDim.x) {
+		for (int i = threadIdx.x; i < 6; i += blockDim.x) {
 			asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" :: "l"((const char *)J.tmaps + (size_t)i * 128) : "memory");
 		}
 	}
