@@ -51,7 +51,7 @@ typedef struct MbInfo {
 	uint8_t  direct8;         /* per 8x8: predicted in direct mode (B) */
 	uint8_t  tc[24];          /* CAVLC total_coeff: luma z-order 0..15, Cb 16..19, Cr 20..23 */
 	int8_t   ipm[16];         /* Intra4x4/8x8PredMode per luma4x4BlkIdx, 2 when not I_NxN */
-	uint8_t  mvd[2][16][2];   /* |mvd| clipped to 255 per list/blk/comp (CABAC ctxIdxInc) */
+	uint8_t  mvd[2][16][2] __attribute__((aligned(2)));   /* |mvd| clipped to 255 per list/blk/comp (CABAC ctxIdxInc); filled pairwise as 16-bit words */
 } MbInfo;
 
 typedef struct SliceHeader {
