@@ -303,9 +303,42 @@ static int bump_frame(Edge264Decoder *d, int ignore_slot) {
 /* ------------------------------------------------------------------------------------------ */
 static void apply_marking(Edge264Decoder *d);
 
+/* Macroblocks that no slice delivered (lost or damaged slices): give them a neutral, self-consistent record so
+ * that every picture the backend sees is complete — copy of the co-located samples of the most recent reference
+ * picture (a P_Skip with zero motion), or DC intra prediction when there is none.  The reference blends an
+ * error-probability-weighted intra DC / re-runs P_Skip (recover_slice, edge264_headers.c:295-430); matching its
+ * concealed samples is not attempted, only a deterministic, safe picture. */
+static void conceal_missing(Edge264Decoder *d) {
+	const int total = d->w_mbs * d->h_mbs;
+	Pic *cp = &d->pics[d->cur];
+	int ref = -1, best = -1;
+	for (int i = 0; i < d->n_slots; i++) if (i != d->cur && d->pics[i].in_use && d->pics[i].ref && !d->pics[i].nonexisting && d->pics[i].uid > best) { best = d->pics[i].uid; ref = i; }
+	if (d->n_slices == 0) {   /* not one slice arrived: a neutral slice record for the concealed macroblocks to point to */
+		E264SliceRec *sr = &d->slices[0];
+		memset(sr, 0, sizeof(*sr));
+		memset(sr->scaling4x4, 16, sizeof(sr->scaling4x4)); memset(sr->scaling8x8, 16, sizeof(sr->scaling8x8));
+		d->n_slices = 1;
+	}
+	for (int a = 0; a < total; a++) {
+		if (d->mbi[a].slice_id) continue;
+		E264MbRec *r = cp->recs + a;
+		memset(r, 0, sizeof(*r));
+		r->qp[0] = r->qp[1] = r->qp[2] = 26;
+		memset(r->ref_idx, -1, sizeof(r->ref_idx)); memset(r->ref_pic, -1, sizeof(r->ref_pic));
+		if (ref >= 0) {
+			r->kind = MBK_INTER; r->flags = MBF_SKIP;
+			for (int i8 = 0; i8 < 4; i8++) { r->ref_idx[0][i8] = 0; r->ref_pic[0][i8] = (int8_t)ref; }
+		} else {
+			r->kind = MBK_I16x16; r->i16_mode = IMODE(2, 1 | 2 | 8); r->chroma_mode = IMODE(0, 1 | 2 | 8);
+			d->n_intra++;
+		}
+	}
+}
+
 static int finish_picture(Edge264Decoder *d) {
 	if (d->cur < 0) return 0;
 	Pic *p = &d->pics[d->cur];
+	if (d->mbs_done < d->w_mbs * d->h_mbs) conceal_missing(d);
 	E264PicDesc pd; memset(&pd, 0, sizeof(pd));
 	pd.width_mbs = d->w_mbs; pd.height_mbs = d->h_mbs; pd.stride_y = d->stride_y; pd.stride_c = d->stride_c;
 	pd.plane_y = d->plane_y; pd.frame_bytes = d->frame_bytes; pd.dst_slot = d->cur;
