@@ -44,6 +44,7 @@ struct E264bDevice {
 	unsigned *d_sync;            /* [0..2] tickets (inter, deblock, intra), [3] err, then flags[2*nmb] */
 	unsigned epoch;
 	cudaEvent_t tick_ev[NTICK]; uint64_t tick_seq;
+	unsigned *h_err;             /* pinned [NTICK]: the device error word as it stood when ticket t % NTICK completed */
 	bool keep; std::vector<KeptPic> kept;
 	uint64_t launches, h2d_bytes, d2h_bytes;
 	int sm_count;
@@ -103,6 +104,7 @@ extern "C" int e264b_create(E264bDevice **out) {
 	for (int i = 0; i < NSTAGE; i++) CK(cudaEventCreateWithFlags(&c->st[i].done, cudaEventDisableTiming | cudaEventBlockingSync));
 	for (int i = 0; i < NTICK; i++) CK(cudaEventCreateWithFlags(&c->tick_ev[i], cudaEventDisableTiming | cudaEventBlockingSync));   /* waiting threads sleep: host CPUs are the scarce resource */
 	cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, dev);
+	c->h_err = NULL; CK(cudaHostAlloc(&c->h_err, NTICK * sizeof(unsigned), cudaHostAllocDefault)); memset(c->h_err, 0, NTICK * sizeof(unsigned));
 	const char *k = getenv("E264B_KEEP");
 	c->keep = k && atoi(k) != 0;
 	*out = c;
@@ -126,6 +128,7 @@ extern "C" void e264b_destroy(E264bDevice *c) {
 	for (int i = 0; i < E264_MAX_SLOTS; i++) cudaEventDestroy(c->rec_up[i]);
 	for (int i = 0; i < NSTAGE; i++) cudaEventDestroy(c->st[i].done);
 	for (int i = 0; i < NTICK; i++) cudaEventDestroy(c->tick_ev[i]);
+	if (c->h_err) cudaFreeHost(c->h_err);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -308,6 +311,7 @@ extern "C" int e264b_submit(E264bDevice *c, const E264PicDesc *pd, uint8_t *host
 	}
 	CK(cudaEventRecord(s->done, c->stream)); s->busy = true;
 	uint64_t t = ++c->tick_seq;
+	if (c->d_sync) CK(cudaMemcpyAsync(&c->h_err[t % NTICK], c->d_sync + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaEventRecord(c->tick_ev[t % NTICK], c->stream));
 	*ticket = t;
 	return 0;
@@ -318,6 +322,10 @@ extern "C" int e264b_wait(E264bDevice *c, uint64_t ticket) {
 	/* the ring slot holds this ticket or a later one of the same stream: either way it implies completion */
 	CK(cudaSetDevice(c->dev));
 	CK(cudaEventSynchronize(c->tick_ev[ticket % NTICK]));
+	if (c->h_err[ticket % NTICK]) {   /* a kernel gave up on a dependency or a TMA transfer: the picture is not trustworthy */
+		fprintf(stderr, "edge264_b200: the device raised error word %u while reconstructing (ticket %llu)\n", c->h_err[ticket % NTICK], (unsigned long long)ticket);
+		return -1;
+	}
 	return 0;
 }
 
