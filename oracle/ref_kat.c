@@ -2,6 +2,9 @@
  * sources the way its own edge264_check.c:20-22 does, and
  *   ref_kat fuzz     differential fuzz of the reference's decode_inter_luma / decode_inter_chroma against
  *                    the plain-C restatement (oracle/port_recon.c), all 48 luma modes, random + extreme sources
+ *   ref_kat residual differential fuzz of the reference's add_idct4x4 / add_idct8x8 / transform_dc4x4 / transform_dc2x2
+ *                    (edge264_residual.c:108-538) against port_idct4x4 / port_idct8x8 / port_luma_dc / port_chroma_dc:
+ *                    random QP 0..51, random and flat scaling lists, intra/inter lists, conformant-range and extreme levels
  *   ref_kat dump     prints the known-answer inputs/outputs of the reference's KAT setup as JSON
  *                    (tests/golden/kat_*.json are generated from this)
  * Nothing from the reference is copied: the sources are compiled from $(REF)/src at build time. */
@@ -11,6 +14,7 @@
 #include "edge264_internal.h"
 #include "edge264_intra.c"
 #include "edge264_inter.c"
+#include "edge264_residual.c"
 
 typedef struct { const uint8_t *p; int stride, w, h; } Plane;
 int port_mc_luma_sample(const Plane *r, int x, int y, int fx, int fy);
@@ -19,6 +23,10 @@ void port_intra4x4(uint8_t *p, int stride, int imode);
 void port_intra8x8(uint8_t *p, int stride, int imode);
 void port_intra16x16(uint8_t *p, int stride, int imode);
 void port_intra_chroma(uint8_t *p, int stride, int imode);
+void port_idct4x4(const int16_t *c, const uint8_t *scaling, int qp, int has_dc_override, int dc, int16_t *r);
+void port_idct8x8(const int16_t *c, const uint8_t *scaling, int qp, int16_t *r);
+void port_luma_dc(const int16_t *c, const uint8_t *scaling_y_intra, int qp, int *dc);
+void port_chroma_dc(const int16_t *c, int scale0, int qpc, int *dc);
 
 static uint64_t rs = 88172645463325252ull;
 static unsigned rnd(void) { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (unsigned)(rs >> 11); }
@@ -46,6 +54,89 @@ static int fuzz_inter(void) {
 		}
 	}
 	printf("inter luma fuzz: %s\n", bad ? "MISMATCHES" : "ok");
+	return bad;
+}
+
+
+/* ---- residual: the reference works on ctx->c[] (int32, column-major: c[x*4+y]) and adds into the picture;
+ * the restatement works on raster int16 levels and returns the residual.  Scaling lists are stored by the reference in
+ * the same column-major order as c[] (they multiply element-wise, residual.c:114-121), ours are raster. */
+static int clip8(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
+static int fuzz_residual(void) {
+	static Edge264Context ctx __attribute__((aligned(64)));
+	static Edge264Macroblock mbs __attribute__((aligned(64)));
+	static uint8_t pix[32 * 16] __attribute__((aligned(16))), want[32 * 16];
+	int bad = 0;
+	memset(&ctx, 0, sizeof(ctx)); memset(&mbs, 0, sizeof(mbs));
+	ctx._mb = &mbs;
+	for (int k = 0; k < 3; k++) { ctx.t.stride[k] = 32; ctx.t.samples_clip[k][0] = 255; }
+	for (int trial = 0; trial < 20000 && bad < 10; trial++) {
+		const int iY = rnd() % 3, inter = rnd() & 1, qp = rnd() % 52, extreme = (trial % 5) == 4, flat = (trial % 3) == 0;
+		ctx.t.QP[0] = ctx.t.QP[1] = ctx.t.QP[2] = qp; mbs.mbIsInterFlag = inter;
+		for (int i = 0; i < 32 * 16; i++) pix[i] = rnd();
+		memcpy(want, pix, sizeof(pix));
+		/* --- 4x4 --- */
+		uint8_t sc[16]; int16_t lv[16], res[16];
+		for (int i = 0; i < 16; i++) sc[i] = flat ? 16 : 1 + rnd() % 255;
+		const int range = extreme ? 32768 : (rnd() % 3 ? 64 : 2048);
+		for (int i = 0; i < 16; i++) lv[i] = (rnd() % 3) ? 0 : (int)(rnd() % (2 * range)) - range;
+		const int dcidx = (rnd() % 3 == 0) ? (int)(rnd() % 8) : -1, dcv = (int)(rnd() % 65536) - 32768;
+		for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) {
+			ctx.c[j * 4 + i] = lv[i * 4 + j];
+			((uint8_t *)&ctx.t.pps.weightScale4x4_v[iY + inter * 3])[j * 4 + i] = sc[i * 4 + j];
+		}
+		if (dcidx >= 0) ctx.c[16 + dcidx] = dcv;
+		add_idct4x4(&ctx, iY, dcidx, pix + 32 * 4 + 8);
+		port_idct4x4(lv, sc, qp, dcidx >= 0, dcv, res);
+		for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) want[32 * (4 + y) + 8 + x] = (uint8_t)clip8((int16_t)(want[32 * (4 + y) + 8 + x] + res[y * 4 + x]));
+		if (memcmp(want, pix, sizeof(pix))) { if (bad++ < 5) printf("IDCT4x4 MISMATCH trial %d qp %d plane %d inter %d dcidx %d\n", trial, qp, iY, inter, dcidx); memcpy(want, pix, sizeof(pix)); }
+		for (int i = 0; i < 16; i++) if (ctx.c[i]) { if (bad++ < 5) printf("IDCT4x4 did not clear c[]\n"); break; }
+		/* --- 8x8 (luma lists only in 4:2:0: index (iYCbCr*2+inter)*4 with iYCbCr = 0, residual.c:203) --- */
+		uint8_t sc8[64]; int16_t lv8[64], res8[64];
+		for (int i = 0; i < 64; i++) { sc8[i] = flat ? 16 : 1 + rnd() % 255; lv8[i] = (rnd() % 4) ? 0 : (int)(rnd() % (2 * range)) - range; }
+		for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) {
+			ctx.c[j * 8 + i] = lv8[i * 8 + j];
+			((uint8_t *)(ctx.t.pps.weightScale8x8_v + inter * 4))[j * 8 + i] = sc8[i * 8 + j];
+		}
+		add_idct8x8(&ctx, 0, pix + 32 * 6 + 16);
+		port_idct8x8(lv8, sc8, qp, res8);
+		for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) want[32 * (6 + y) + 16 + x] = (uint8_t)clip8((int16_t)(want[32 * (6 + y) + 16 + x] + res8[y * 8 + x]));
+		if (memcmp(want, pix, sizeof(pix))) { if (bad++ < 5) printf("IDCT8x8 MISMATCH trial %d qp %d inter %d extreme %d\n", trial, qp, inter, extreme); memcpy(want, pix, sizeof(pix)); }
+		memset(ctx.c, 0, sizeof(ctx.c));
+		/* --- Intra16x16 luma DC (results kept for the AC pass: mb->bits[0] bit 5, residual.c:395-399) --- */
+		int16_t dl[16]; int dcs[16];
+		for (int i = 0; i < 16; i++) dl[i] = (int)(rnd() % (2 * (extreme ? 32768 : 512))) - (extreme ? 32768 : 512);
+		for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) ctx.c[j * 4 + i] = dl[i * 4 + j];
+		((uint8_t *)&ctx.t.pps.weightScale4x4_v[0])[0] = sc[0]; ((uint8_t *)ctx.t.pps.weightScale4x4[0])[0] = sc[0];
+		mbs.bits[0] |= 1 << 5;
+		transform_dc4x4(&ctx, 0);
+		port_luma_dc(dl, sc, qp, dcs);
+		{	/* the reference stores the 16 DCs in luma4x4BlkIdx order (ziplo64/ziphi64 pairs, residual.c:396-399) */
+			static const uint8_t zr[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
+			int ok = 1;
+			for (int b = 0; b < 16; b++) if (ctx.c[16 + b] != dcs[zr[b]]) ok = 0;
+			if (!ok && bad++ < 5) { printf("LUMA DC MISMATCH trial %d qp %d:", trial, qp); for (int b = 0; b < 16; b++) printf(" %d/%d", ctx.c[16 + b], dcs[zr[b]]); printf("\n"); }
+		}
+		memset(ctx.c, 0, sizeof(ctx.c));
+		/* --- chroma DC 2x2, both planes at once (Cb at c[{0,4,2,6}], Cr at c[{1,5,3,7}], slice.c:448-462) --- */
+		int16_t cb[4], cr[4]; int dcb[4], dcr[4];
+		for (int i = 0; i < 4; i++) { cb[i] = (int)(rnd() % 2048) - 1024; cr[i] = (int)(rnd() % 2048) - 1024; }
+		static const uint8_t posb[4] = {0, 4, 2, 6}, posr[4] = {1, 5, 3, 7};
+		for (int i = 0; i < 4; i++) { ctx.c[posb[i]] = cb[i]; ctx.c[posr[i]] = cr[i]; }
+		const int qb = rnd() % 52, qr = rnd() % 52, sb = flat ? 16 : 1 + rnd() % 255, sr_ = flat ? 16 : 1 + rnd() % 255;
+		ctx.t.QP[1] = qb; ctx.t.QP[2] = qr;
+		((uint8_t *)ctx.t.pps.weightScale4x4[1 + inter * 3])[0] = sb; ((uint8_t *)ctx.t.pps.weightScale4x4[2 + inter * 3])[0] = sr_;
+		mbs.f.CodedBlockPatternChromaAC = 1;
+		transform_dc2x2(&ctx);
+		port_chroma_dc(cb, sb, qb, dcb); port_chroma_dc(cr, sr_, qr, dcr);
+		{
+			int ok = 1;
+			for (int i = 0; i < 4; i++) if (ctx.c[16 + i] != dcb[i] || ctx.c[20 + i] != dcr[i]) ok = 0;
+			if (!ok && bad++ < 5) { printf("CHROMA DC MISMATCH trial %d:", trial); for (int i = 0; i < 4; i++) printf(" %d/%d %d/%d", ctx.c[16 + i], dcb[i], ctx.c[20 + i], dcr[i]); printf("\n"); }
+		}
+		memset(ctx.c, 0, sizeof(ctx.c));
+	}
+	printf("residual fuzz: %s\n", bad ? "MISMATCHES" : "ok");
 	return bad;
 }
 
@@ -81,7 +172,8 @@ static int dump_kat(void) {
 
 int main(int argc, char **argv) {
 	if (argc > 1 && !strcmp(argv[1], "fuzz")) return fuzz_inter() != 0;
+	if (argc > 1 && !strcmp(argv[1], "residual")) return fuzz_residual() != 0;
 	if (argc > 1 && !strcmp(argv[1], "dump")) return dump_kat();
-	fprintf(stderr, "usage: ref_kat fuzz\n");
+	fprintf(stderr, "usage: ref_kat fuzz | residual | dump\n");
 	return 2;
 }
