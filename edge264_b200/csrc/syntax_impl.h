@@ -360,7 +360,7 @@ static inline __attribute__((always_inline)) int residual_block_cabac_cat(SliceC
 	CR_OUT
 	return nsig;
 }
-static int residual_block_cabac(SliceCtx *s, int cat, int cbf_inc, int has_cbf, int16_t *blk, const uint8_t *scan, int n) {
+static __attribute__((noinline)) int residual_block_cabac(SliceCtx *s, int cat, int cbf_inc, int has_cbf, int16_t *blk, const uint8_t *scan, int n) {
 	switch (cat) {
 	case 0: return residual_block_cabac_cat(s, 0, cbf_inc, 1, blk, scan, 16);
 	case 1: return residual_block_cabac_cat(s, 1, cbf_inc, 1, blk, scan, 15);
@@ -553,6 +553,18 @@ static inline int sx_cbf_na(SliceCtx *s) { return s->cur->is_intra; }
 /* z-index of the block left of / above block b inside the same macroblock (valid when x>0 / y>0) */
 static const uint8_t sx_left_z[16]  = {0, 0, 0, 2, 1, 4, 3, 6, 0, 8, 0, 10, 9, 12, 11, 14};
 static const uint8_t sx_above_z[16] = {0, 0, 0, 1, 0, 0, 4, 5, 2, 3, 8, 9, 6, 7, 12, 13};
+/* The same, macroblock at a time: bits 0-15 = coded_block_flags of this macroblock so far (z-order), bits 16-19 =
+ * the left neighbour's right column by row, bits 20-23 = the top neighbour's bottom row by column (each already
+ * resolved for unavailable / I_PCM neighbours); sx_cbf_la/tb give the bit to test for block b. */
+static const uint8_t sx_cbf_la[16] = {16, 0, 17, 2, 1, 4, 3, 6, 18, 8, 19, 10, 9, 12, 11, 14};
+static const uint8_t sx_cbf_tb[16] = {20, 21, 0, 1, 22, 23, 4, 5, 2, 3, 8, 9, 6, 7, 12, 13};
+static inline uint32_t sx_cbf_luma_border(SliceCtx *s) {
+	const uint32_t na = (uint32_t)sx_cbf_na(s);
+	uint32_t left = na * 15u, top = na * 15u;
+	if (s->A) { const uint32_t c = s->A->cbf_luma; left = s->A->is_pcm ? 15u : ((c >> 5) & 1) | ((c >> 7) & 1) << 1 | ((c >> 13) & 1) << 2 | ((c >> 15) & 1) << 3; }
+	if (s->B) { const uint32_t c = s->B->cbf_luma; top = s->B->is_pcm ? 15u : ((c >> 10) & 1) | ((c >> 11) & 1) << 1 | ((c >> 14) & 1) << 2 | ((c >> 15) & 1) << 3; }
+	return left << 16 | top << 20;
+}
 static int sx_cbf_inc_luma(SliceCtx *s, int b) {
 	const int x = e264_blk_x(b), y = e264_blk_y(b);
 	int a, bb;
@@ -585,6 +597,7 @@ static void sx_residual(SliceCtx *s, int is_i16, int cbp) {
 		                 : residual_block_cavlc(s, sx_nC_luma(s, 0), blk, h264_zigzag4x4, 16);
 		if (n) { coded |= CODED_Y_DC; m->cbf_dc |= 1; } else s->n_coefs -= 16;
 	}
+	uint32_t cbf_ext = (s->cabac && !m->t8x8 && (cbp & 15)) ? sx_cbf_luma_border(s) : 0;
 	for (int i8 = 0; i8 < 4; i8++) {
 		if (!((cbp >> i8) & 1)) continue;
 		if (m->t8x8) {
@@ -606,9 +619,10 @@ static void sx_residual(SliceCtx *s, int is_i16, int cbp) {
 				int16_t *blk = sx_pool_take(s, 16, 16 + 16 * b);
 				int n;
 				if (s->cabac) {
-					n = is_i16 ? residual_block_cabac(s, 1, sx_cbf_inc_luma(s, b), 1, blk, sx_scan_ac, 15)
-					           : residual_block_cabac(s, 2, sx_cbf_inc_luma(s, b), 1, blk, h264_zigzag4x4, 16);
-					if (n) m->cbf_luma |= 1 << b;
+					const int inc = (int)(((cbf_ext >> sx_cbf_la[b]) & 1) + 2 * ((cbf_ext >> sx_cbf_tb[b]) & 1));
+					n = is_i16 ? residual_block_cabac(s, 1, inc, 1, blk, sx_scan_ac, 15)
+					           : residual_block_cabac(s, 2, inc, 1, blk, h264_zigzag4x4, 16);
+					if (n) { m->cbf_luma |= 1 << b; cbf_ext |= 1u << b; }
 				} else {
 					n = is_i16 ? residual_block_cavlc(s, sx_nC_luma(s, b), blk, sx_scan_ac, 15)
 					           : residual_block_cavlc(s, sx_nC_luma(s, b), blk, h264_zigzag4x4, 16);
