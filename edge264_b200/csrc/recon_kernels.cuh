@@ -1,16 +1,17 @@
 /* recon_kernels.cuh — sm_100a device code of the pixel-reconstruction path.
  *
- * One warp per macroblock.  Two kernels per picture:
- *   e264_recon_kernel    inverse quantisation + 4x4/8x8 inverse transforms + DC transforms
- *                        (reference edge264_residual.c:108-538), intra prediction of every mode
- *                        (edge264_intra.c:291-765), 6-tap / bilinear motion compensation with
- *                        default / explicit / implicit weighting (edge264_inter.c:416-1251);
- *   e264_deblock_kernel  boundary strengths and the in-loop filter (edge264_deblock.c:284-1123).
- * Warps take macroblocks in raster order from a ticket counter; an intra macroblock waits on the
- * "done" flags of its A/B/C/D neighbours, a deblocked macroblock on (x-1,y) and (x+1,y-1) — the
- * same dependencies the reference resolves by decoding in raster order with deblocking one row
- * behind (edge264_slice.c:1809-1826).  Arithmetic is restated from ITU-T H.264 with the reference's
- * observable integer widths; results are bit-exact with the reference decoder (tests/test_gpu_*.py).
+ * One warp per macroblock (per macroblock row where a wavefront runs).  Up to four kernels per picture:
+ *   e264_residual_kernel  inverse quantisation + 4x4/8x8 inverse transforms + DC transforms
+ *                         (reference edge264_residual.c:108-538); coefficient runs staged by cp.async.bulk;
+ *   e264_inter_kernel     6-tap / bilinear motion compensation with default / explicit / implicit weighting
+ *                         (edge264_inter.c:416-1251); reference windows staged by cp.async.bulk.tensor;
+ *   e264_intra_kernel     intra prediction of every mode and I_PCM (edge264_intra.c:291-765, slice.c:886-939);
+ *   e264_deblock_kernel   boundary strengths and the in-loop filter (edge264_deblock.c:284-1123).
+ * Inter macroblocks have no dependency inside a picture (tickets); an intra macroblock waits on the "done" flags
+ * of its A/B/C/D neighbours; a deblocking row-warp waits on the progress counter of the row above — the same
+ * dependencies the reference resolves by decoding in raster order with deblocking one row behind
+ * (edge264_slice.c:1809-1826).  Arithmetic is restated from ITU-T H.264 with the reference's observable integer
+ * widths; results are bit-exact with the reference decoder (tests/test_gpu_parity.py).
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -27,7 +28,7 @@ struct PicJob {
 	unsigned *tickets;    /* [2] zeroed before the picture */
 	unsigned *err;
 	int rows_mode;
-	int word_loads;       /* unused (kept for ABI of the job struct) */
+	int word_loads;       /* unused */
 	const void *tmaps;    /* CUtensorMap[6] over the whole frame pool (x, y, slot): luma boxes 48x{21,13,9}, chroma boxes 32x{9,5,3}; NULL = no TMA */
 	int16_t *resid;       /* [nmb][384] residual written by e264_residual_kernel (coded macroblocks only) */
 	unsigned long long *trace;   /* measurement only (E264B_TRACE): [trace_base + kind] = {first warp start, last warp end} in globaltimer ns */
