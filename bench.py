@@ -105,6 +105,15 @@ def peaks():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(group, pictures):
+    """DRAM bytes the profiler saw for this kernel group, scaled to `pictures` (profiles/r1_ncu_traffic.json); None if absent."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))[group]["dram_bytes_per_picture"]
+        return float(t) * pictures
+    except Exception:
+        return None
+
+
 def reference_arm(args, rank, emit):
     """CPU reference decoder on all host cores (rank 0 only)."""
     if rank != 0:
@@ -227,7 +236,8 @@ def main():
     kern = {"recon": (rb / t_rec / 1e9, t_rec), "deblock": (db / t_db / 1e9, t_db)}
     dom = "recon" if t_rec >= t_db else "deblock"
     roof = {"bound": "hbm", "kernel": ("e264_deblock_kernel" if dom == "deblock" else "e264_inter_kernel (+ e264_residual_kernel, e264_intra_kernel: the reconstruction launches of a picture)"), "achieved": kern[dom][0], "peak": peak, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)", "unit": "GB/s",
-            "frac": kern[dom][0] / peak, "traffic": None,
+            "frac": kern[dom][0] / peak, "traffic": ncu_traffic(dom, S * F), "algorithmic_bytes": (rb if dom == "recon" else db),
+            "traffic_note": "bytes per step of this GPU: ncu dram read+write per picture (profiles/r1_ncu_traffic.json, serialised cold-cache capture) x pictures per step, next to the algorithmic bytes `achieved` is computed from",
             "per_kernel": {k: {"achieved_gbs": v[0], "ms_per_step": v[1] * 1000, "frac": v[0] / peak} for k, v in kern.items()},
             "note": "S streams replayed concurrently; single-stream pictures are dependency-latency bound (wavefront), not bandwidth bound"}
 
