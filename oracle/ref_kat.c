@@ -5,6 +5,10 @@
  *   ref_kat residual differential fuzz of the reference's add_idct4x4 / add_idct8x8 / transform_dc4x4 / transform_dc2x2
  *                    (edge264_residual.c:108-538) against port_idct4x4 / port_idct8x8 / port_luma_dc / port_chroma_dc:
  *                    random QP 0..51, random and flat scaling lists, intra/inter lists, conformant-range and extreme levels
+ *   ref_kat deblock  differential fuzz of the reference's deblock_Y_8bit + deblock_CbCr_8bit (edge264_deblock.c:284-895) on one
+ *                    macroblock with its left and top neighbours against the restatement's line filters: random alpha/beta,
+ *                    tC0 per 4-sample (2-sample chroma) segment incl. -1 = bS 0, HARD edges when a neighbour is intra,
+ *                    transform_size_8x8_flag, smooth and noisy pictures
  *   ref_kat dump     prints the known-answer inputs/outputs of the reference's KAT setup as JSON
  *                    (tests/golden/kat_*.json are generated from this)
  * Nothing from the reference is copied: the sources are compiled from $(REF)/src at build time. */
@@ -15,6 +19,7 @@
 #include "edge264_intra.c"
 #include "edge264_inter.c"
 #include "edge264_residual.c"
+#include "edge264_deblock.c"
 
 typedef struct { const uint8_t *p; int stride, w, h; } Plane;
 int port_mc_luma_sample(const Plane *r, int x, int y, int fx, int fy);
@@ -27,6 +32,8 @@ void port_idct4x4(const int16_t *c, const uint8_t *scaling, int qp, int has_dc_o
 void port_idct8x8(const int16_t *c, const uint8_t *scaling, int qp, int16_t *r);
 void port_luma_dc(const int16_t *c, const uint8_t *scaling_y_intra, int qp, int *dc);
 void port_chroma_dc(const int16_t *c, int scale0, int qpc, int *dc);
+void port_deblock_luma_line(uint8_t *pix, int step, int bs, int alpha, int beta, int tc0);
+void port_deblock_chroma_line(uint8_t *pix, int step, int bs, int alpha, int beta, int tc0);
 
 static uint64_t rs = 88172645463325252ull;
 static unsigned rnd(void) { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (unsigned)(rs >> 11); }
@@ -140,6 +147,77 @@ static int fuzz_residual(void) {
 	return bad;
 }
 
+/* ---- deblocking: the reference filters a whole macroblock from ctx->alpha/beta/tC0 (layout edge264_internal.h:323-325:
+ * alpha/beta {internal Y,Cb,Cr,-,...,left Y,Cb,Cr @8,-,top Y,Cb,Cr @12}; tC0: 4 bytes per edge, 8 luma edges (4 vertical
+ * left to right, 4 horizontal top to bottom) then Cb/Cr alternating for left, internal vertical, top, internal horizontal).
+ * The expected picture applies the restatement's one-line filters in the same edge order (vertical edges first). */
+static int fuzz_deblock(void) {
+	static Edge264Context ctx __attribute__((aligned(64)));
+	static Edge264Macroblock mbs[3] __attribute__((aligned(64)));
+	enum { ST = 64 };
+	static uint8_t y[ST * 48] __attribute__((aligned(16))), c[ST * 32] __attribute__((aligned(16))), wy[ST * 48], wc[ST * 32];
+	int bad = 0;
+	memset(&ctx, 0, sizeof(ctx)); memset(mbs, 0, sizeof(mbs));
+	ctx._mb = &mbs[0]; ctx._mbA = &mbs[1]; ctx._mbB = &mbs[2];
+	ctx.t.stride[0] = ST; ctx.t.stride[1] = ST;
+	for (int trial = 0; trial < 30000 && bad < 10; trial++) {
+		const int smooth = trial % 3 != 0;
+		int v = rnd() % 256;
+		for (int i = 0; i < ST * 48; i++) { if (smooth) { v += (int)(rnd() % 9) - 4; v = v < 0 ? 0 : v > 255 ? 255 : v; if (rnd() % 23 == 0) v = rnd() % 256; y[i] = (uint8_t)v; } else y[i] = rnd(); }
+		for (int i = 0; i < ST * 32; i++) { if (smooth) { v += (int)(rnd() % 7) - 3; v = v < 0 ? 0 : v > 255 ? 255 : v; if (rnd() % 19 == 0) v = rnd() % 256; c[i] = (uint8_t)v; } else c[i] = rnd(); }
+		memcpy(wy, y, sizeof(y)); memcpy(wc, c, sizeof(c));
+		const int fe = trial % 7 == 0 ? rnd() & 3 : 3, t8 = rnd() & 1;
+		mbs[0].filter_edges = fe; mbs[0].f.transform_size_8x8_flag = t8;
+		mbs[0].mbIsInterFlag = rnd() % 4 != 0; mbs[1].mbIsInterFlag = rnd() % 3 != 0; mbs[2].mbIsInterFlag = rnd() % 3 != 0;
+		for (int i = 0; i < 16; i++) { ctx.alpha[i] = (rnd() % 5 == 0) ? 0 : (smooth ? 4 + rnd() % 60 : rnd() % 256); ctx.beta[i] = (rnd() % 7 == 0) ? 0 : 2 + rnd() % 17; }
+		int8_t *tc = (int8_t *)ctx.tC0_s;
+		for (int i = 0; i < 64; i++) tc[i] = (rnd() % 3 == 0) ? -1 : (int8_t)(rnd() % 14);
+		if (rnd() % 5 == 0) for (int e = 0; e < 16; e++) if (rnd() & 1) for (int k = 0; k < 4; k++) tc[e * 4 + k] = -1;
+		ctx.samples_mb[0] = y + ST * 16 + 16; ctx.samples_mb[1] = c + ST * 8 + 8; ctx.samples_mb[2] = ctx.samples_mb[1] + ST / 2;
+		/* expected */
+		uint8_t *Y = wy + ST * 16 + 16;
+		for (int dir = 0; dir < 2; dir++) for (int e = 0; e < 4; e++) {
+			if (e == 0 && !(fe & (dir ? 2 : 1))) continue;
+			if (e && t8 && (e & 1)) continue;
+			const int hard = e == 0 && !(mbs[0].mbIsInterFlag & (dir ? mbs[2].mbIsInterFlag : mbs[1].mbIsInterFlag));
+			const int ai = e ? 0 : dir ? 12 : 8;
+			if (hard && ctx.alpha[ai] == 0) continue;
+			for (int k = 0; k < 16; k++) {
+				const int t0 = tc[(dir * 4 + e) * 4 + (k >> 2)];
+				if (!hard && t0 < 0) continue;
+				uint8_t *pix = dir ? Y + e * 4 * ST + k : Y + k * ST + e * 4;
+				port_deblock_luma_line(pix, dir ? ST : 1, hard ? 4 : 1, ctx.alpha[ai], ctx.beta[ai], hard ? 0 : t0);
+			}
+		}
+		for (int pl = 0; pl < 2; pl++) {
+			uint8_t *C = wc + ST * 8 + 8 + pl * (ST / 2);
+			for (int dir = 0; dir < 2; dir++) for (int e = 0; e < 2; e++) {
+				if (e == 0 && !(fe & (dir ? 2 : 1))) continue;
+				const int hard = e == 0 && !(mbs[0].mbIsInterFlag & (dir ? mbs[2].mbIsInterFlag : mbs[1].mbIsInterFlag));
+				const int ai = (e ? 0 : dir ? 12 : 8) + 1 + pl;
+				for (int k = 0; k < 8; k++) {
+					const int t0 = tc[32 + ((dir * 2 + e) * 2 + pl) * 4 + (k >> 1)];
+					if (!hard && t0 < 0) continue;
+					uint8_t *pix = dir ? C + e * 4 * ST + k : C + k * ST + e * 4;
+					port_deblock_chroma_line(pix, dir ? ST : 1, hard ? 4 : 1, ctx.alpha[ai], ctx.beta[ai], hard ? 0 : t0);
+				}
+			}
+		}
+		deblock_Y_8bit(&ctx);
+		if (memcmp(wy, y, sizeof(y)) || memcmp(wc, c, sizeof(c))) {
+			if (bad++ < 6) {
+				int py = -1, pc = -1;
+				for (int i = 0; i < ST * 48 && py < 0; i++) if (wy[i] != y[i]) py = i;
+				for (int i = 0; i < ST * 32 && pc < 0; i++) if (wc[i] != c[i]) pc = i;
+				printf("DEBLOCK MISMATCH trial %d fe %d t8 %d inter %d/%d/%d: first luma diff at (%d,%d) ref %d port %d, first chroma diff at (%d,%d)\n", trial, fe, t8, mbs[0].mbIsInterFlag, mbs[1].mbIsInterFlag, mbs[2].mbIsInterFlag,
+				       py < 0 ? -1 : py % ST - 16, py < 0 ? -1 : py / ST - 16, py < 0 ? 0 : y[py], py < 0 ? 0 : wy[py], pc < 0 ? -1 : pc % ST - 8, pc < 0 ? -1 : pc / ST - 8);
+			}
+		}
+	}
+	printf("deblock fuzz: %s\n", bad ? "MISMATCHES" : "ok");
+	return bad;
+}
+
 /* Known-answer dump: the inputs of the reference's own KATs (edge264_check.c:173-180 border ramp, :286-290
  * luma source) run through the reference's functions; one JSON object on stdout. */
 static void dump_block(const char *name, int mode, const uint8_t *p, int stride, int w, int h, int last) {
@@ -173,7 +251,8 @@ static int dump_kat(void) {
 int main(int argc, char **argv) {
 	if (argc > 1 && !strcmp(argv[1], "fuzz")) return fuzz_inter() != 0;
 	if (argc > 1 && !strcmp(argv[1], "residual")) return fuzz_residual() != 0;
+	if (argc > 1 && !strcmp(argv[1], "deblock")) return fuzz_deblock() != 0;
 	if (argc > 1 && !strcmp(argv[1], "dump")) return dump_kat();
-	fprintf(stderr, "usage: ref_kat fuzz | residual | dump\n");
+	fprintf(stderr, "usage: ref_kat fuzz | residual | deblock | dump\n");
 	return 2;
 }
