@@ -37,6 +37,17 @@ STREAMS = [
 ]
 
 
+# decoded-picture-buffer logic (host side only): list modification to short/long-term pictures, memory-management
+# operations, long-term IDR, frame_num wrap-around, picture order count types 1 and 2 — checked CPU-side against the
+# reference and the golden digests (reference behaviours mirrored: edge264_headers.c:611-701, 768-893)
+DPB_STREAMS = [
+    ("dpb_mmco_cabac",   4, 3, "-n 40 -s 101 --gop IP --refs 4 --idr 17 --dpb --deblock 0"),
+    ("dpb_mmco_cavlc_poc1", 3, 2, "-n 50 -s 113 --gop IP --refs 3 --idr 23 --dpb --poc-type 1 --deblock 0 --cavlc"),
+    ("dpb_mmco_poc2",    3, 2, "-n 50 -s 131 --gop IP --refs 2 --idr 29 --dpb --poc-type 2 --deblock 0"),
+    ("dpb_mmco_refs5",   3, 2, "-n 60 -s 149 --gop IP --refs 5 --idr 40 --dpb --deblock 0 --wp 1"),
+]
+
+
 @pytest.fixture(scope="session")
 def workdir(tmp_path_factory):
     return str(tmp_path_factory.mktemp("streams"))

@@ -2,12 +2,12 @@
 /root/reference by oracle/Makefile).  Run in the build container: python tests/make_golden.py"""
 import json, os, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from conftest import ROOT, STREAMS, make_stream, md5_frames
+from conftest import ROOT, STREAMS, DPB_STREAMS, make_stream, md5_frames
 from edge264_b200 import decode_bytes
 
 out = {}
 tmp = tempfile.mkdtemp()
-for name, w, h, args in STREAMS:
+for name, w, h, args in STREAMS + DPB_STREAMS:
     data = open(make_stream(tmp, name, w, h, args), "rb").read()
     frames, _ = decode_bytes(data, "ref")
     out[name] = {"args": f"-W {w} -H {h} {args}", "bytes": len(data), "md5": md5_frames(frames)}

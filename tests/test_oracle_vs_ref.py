@@ -3,13 +3,13 @@ the reference decoder's exact YUV on generated streams, and both must match the 
 digests (tests/golden/streams.json, produced by tests/make_golden.py from the reference)."""
 import json, os
 import pytest
-from conftest import ROOT, STREAMS, make_stream, md5_frames, have
+from conftest import ROOT, STREAMS, DPB_STREAMS, make_stream, md5_frames, have
 from edge264_b200 import decode_bytes
 
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "streams.json")))
 
 
-@pytest.mark.parametrize("name,w,h,args", STREAMS, ids=[s[0] for s in STREAMS])
+@pytest.mark.parametrize("name,w,h,args", STREAMS + DPB_STREAMS, ids=[s[0] for s in STREAMS + DPB_STREAMS])
 def test_port_matches_reference_and_golden(workdir, name, w, h, args):
     data = open(make_stream(workdir, name, w, h, args), "rb").read()
     port, _ = decode_bytes(data, "port")

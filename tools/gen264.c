@@ -12,6 +12,9 @@
  *          [--refs N] [--t8x8 pct] [--scaling 0|1|2] [--wp 0|1|2] [--slices N] [--deblock 0|1|2]
  *          [--density pct] [--qp Q] [--temporal] [--pcm permille] [--crop-bottom px] [--level idc]
  *          [--mvrange qpel] [--intra-pct P] [--skip-pct P]
+ *          [--dpb] [--poc-type 0|1|2]      (with --gop IP: reference-list modification to short- and long-term
+ *                                           pictures, memory-management operations 1,2,3,4,6, long-term IDR,
+ *                                           4-bit frame_num wrap-around; picture order count types 1 and 2)
  */
 #define E264_ENCODER
 #include <stdio.h>
@@ -21,6 +24,7 @@
 
 typedef struct GenPic {
 	int used, frame_num, poc; int32_t uid;
+	int is_long, long_idx;   /* --dpb: long-term reference and its LongTermFrameIdx */
 	E264MbRec *recs; int32_t slot_uid[E264_MAX_SLOTS];
 } GenPic;
 
@@ -36,6 +40,7 @@ typedef struct GenState {
 	int log2_max_frame_num, log2_max_poc_lsb;
 	int drift[2];           /* per-picture global motion */
 	int cur_is_b;
+	int dpb_mode, poc_type, max_long_idx_plus1, stat_rplm, stat_mmco[7], stat_idr_long;   /* --dpb: list modification + memory-management stress on I P P P streams; --poc-type 0|1|2 */
 } GenState;
 
 static inline uint64_t rnd64(GenState *g) { uint64_t x = g->rng; x ^= x >> 12; x ^= x << 25; x ^= x >> 27; g->rng = x; return x * 0x2545F4914F6CDD1Dull; }
@@ -81,7 +86,9 @@ static void write_sps(GenState *g, ByteBuf *out) {
 	bw_u(&w, 1, g->scaling == 1 || g->scaling == 3);
 	if (g->scaling == 1 || g->scaling == 3) put_scaling_matrix(g, &w, 8);
 	bw_ue(&w, g->log2_max_frame_num - 4);
-	bw_ue(&w, 0); bw_ue(&w, g->log2_max_poc_lsb - 4);
+	bw_ue(&w, g->poc_type);
+	if (g->poc_type == 0) bw_ue(&w, g->log2_max_poc_lsb - 4);
+	else if (g->poc_type == 1) { bw_u(&w, 1, 1); bw_se(&w, 0); bw_se(&w, 0); bw_ue(&w, 1); bw_se(&w, 2); }   /* delta_pic_order_always_zero, offsets 0, one ref frame per cycle, +2 per frame */
 	bw_ue(&w, g->refs);
 	bw_u(&w, 1, 0);
 	bw_ue(&w, g->W - 1); bw_ue(&w, g->H - 1);
@@ -327,6 +334,41 @@ static void encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr
 	g->drift[0] = laplace(g, 6); g->drift[1] = laplace(g, 4);
 	g->cur_is_b = pp->type == 1;
 
+	/* --dpb: plan this picture's reference marking (8.2.5.4) on a copy of the DPB model; every operation targets a
+	 * picture that exists, and at most refs-1 other references remain so that the picture itself fits */
+	int mmco[40][3], n_mmco = 0, idr_long = 0, cur_long = -1;
+	int m_used[E264_MAX_SLOTS], m_long[E264_MAX_SLOTS], m_idx[E264_MAX_SLOTS], m_max = g->max_long_idx_plus1;
+	for (int i = 0; i < E264_MAX_SLOTS; i++) { m_used[i] = g->dpb[i].used && i != slot; m_long[i] = g->dpb[i].is_long; m_idx[i] = g->dpb[i].long_idx; }
+	if (g->dpb_mode && pp->idr) { idr_long = g->refs > 1 && rnd(g, 4) == 0;   /* with one reference frame the reference decoder asserts (edge264_headers.c:1099) */ m_max = idr_long ? 1 : 0; cur_long = idr_long ? 0 : -1; }
+	if (g->dpb_mode && !pp->idr && pp->type == 0 && pp->is_ref) {
+		const int maxfn = 1 << g->log2_max_frame_num, cur = pp->frame_num & (maxfn - 1);
+#define DIFF(i) (cur - (((g->dpb[i].frame_num & (maxfn - 1)) > cur) ? (g->dpb[i].frame_num & (maxfn - 1)) - maxfn : (g->dpb[i].frame_num & (maxfn - 1))))
+#define PICK(cond, out) do { int c_[E264_MAX_SLOTS], n_ = 0; for (int i = 0; i < E264_MAX_SLOTS; i++) if (m_used[i] && (cond)) c_[n_++] = i; out = n_ ? c_[rnd(g, n_)] : -1; } while (0)
+#define DROP_IDX(k) do { for (int i = 0; i < E264_MAX_SLOTS; i++) if (m_used[i] && m_long[i] && m_idx[i] == (k)) m_used[i] = 0; } while (0)
+		int cnt0 = 0, nshort0 = 0, t;
+		for (int i = 0; i < E264_MAX_SLOTS; i++) if (m_used[i]) { cnt0++; nshort0 += !m_long[i]; }
+		const int adaptive = rnd(g, 2) || (cnt0 >= g->refs && nshort0 == 0);   /* the sliding window needs a short-term picture to drop */
+		/* short-term pictures about to alias in frame_num must go in any case */
+		for (int i = 0; i < E264_MAX_SLOTS; i++) if (m_used[i] && !m_long[i] && pp->frame_num - g->dpb[i].frame_num >= maxfn - 3) { mmco[n_mmco][0] = 1; mmco[n_mmco][1] = DIFF(i) - 1; n_mmco++; m_used[i] = 0; }
+		if (adaptive || n_mmco) {
+			if (rnd(g, 3) == 0) { m_max = rnd(g, g->refs + 1); mmco[n_mmco][0] = 4; mmco[n_mmco][1] = m_max; n_mmco++; for (int i = 0; i < E264_MAX_SLOTS; i++) if (m_used[i] && m_long[i] && m_idx[i] >= m_max) m_used[i] = 0; }
+			if (m_max > 0 && rnd(g, 2)) { PICK(!m_long[i], t); if (t >= 0) { int k = rnd(g, m_max); DROP_IDX(k); mmco[n_mmco][0] = 3; mmco[n_mmco][1] = DIFF(t) - 1; mmco[n_mmco][2] = k; n_mmco++; m_long[t] = 1; m_idx[t] = k; } }
+			if (rnd(g, 3) == 0) { PICK(!m_long[i], t); if (t >= 0) { mmco[n_mmco][0] = 1; mmco[n_mmco][1] = DIFF(t) - 1; n_mmco++; m_used[t] = 0; } }
+			if (rnd(g, 4) == 0) { PICK(m_long[i], t); if (t >= 0) { mmco[n_mmco][0] = 2; mmco[n_mmco][1] = m_idx[t]; n_mmco++; m_used[t] = 0; } }
+			for (;;) {   /* room for the current picture */
+				int cnt = 0; for (int i = 0; i < E264_MAX_SLOTS; i++) cnt += m_used[i];
+				if (cnt < g->refs) break;
+				int old = -1; for (int i = 0; i < E264_MAX_SLOTS; i++) if (m_used[i] && !m_long[i] && (old < 0 || g->dpb[i].frame_num < g->dpb[old].frame_num)) old = i;
+				if (old >= 0) { mmco[n_mmco][0] = 1; mmco[n_mmco][1] = DIFF(old) - 1; n_mmco++; m_used[old] = 0; }
+				else { PICK(m_long[i], t); mmco[n_mmco][0] = 2; mmco[n_mmco][1] = m_idx[t]; n_mmco++; m_used[t] = 0; }
+			}
+			if (m_max > 0 && rnd(g, 4) == 0) { int k = rnd(g, m_max); DROP_IDX(k); mmco[n_mmco][0] = 6; mmco[n_mmco][1] = k; n_mmco++; cur_long = k; }
+		}
+#undef DIFF
+#undef PICK
+#undef DROP_IDX
+	}
+
 	int pps_id = pp->type == 2 ? 0 : pp->type == 0 ? 1 : 2;
 	int rows_per_slice = (g->H + g->slices - 1) / g->slices;
 	int16_t w_tab[2][16][3], o_tab[2][16][3]; int lwd = 0, cwd = 0;
@@ -339,14 +381,27 @@ static void encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr
 		bw_ue(&w, pps_id);
 		bw_u(&w, g->log2_max_frame_num, pp->frame_num & ((1 << g->log2_max_frame_num) - 1));
 		if (pp->idr) bw_ue(&w, idr_pic_id);
-		bw_u(&w, g->log2_max_poc_lsb, pp->poc & ((1 << g->log2_max_poc_lsb) - 1));
+		if (g->poc_type == 0) bw_u(&w, g->log2_max_poc_lsb, pp->poc & ((1 << g->log2_max_poc_lsb) - 1));
 		int direct_spatial = !g->temporal;
 		if (pp->type != 2) {
 			if (pp->type == 1) bw_u(&w, 1, direct_spatial);
 			bw_u(&w, 1, 1);   /* num_ref_idx_active_override_flag */
 			bw_ue(&w, num_ref[0] - 1);
 			if (pp->type == 1) bw_ue(&w, num_ref[1] - 1);
-			bw_u(&w, 1, 0);   /* ref_pic_list_modification_flag_l0 */
+			if (g->dpb_mode && pp->type == 0 && n0 > 0 && rnd(g, 2)) {   /* ref_pic_list_modification (7.3.3.1, 8.2.4.3): move existing pictures to the front */
+				bw_u(&w, 1, 1); g->stat_rplm++;
+				const int maxfn = 1 << g->log2_max_frame_num;
+				int pred = pp->frame_num & (maxfn - 1), nops = 1 + rnd(g, num_ref[0] < 3 ? num_ref[0] : 3);
+				for (int k = 0; k < nops; k++) {
+					const GenPic *t = &g->dpb[l0[rnd(g, n0)]];
+					if (t->is_long) { bw_ue(&w, 2); bw_ue(&w, t->long_idx); continue; }
+					const int nowrap = t->frame_num & (maxfn - 1);   /* picNumL0NoWrap of a frame is its frame_num */
+					if (nowrap == pred) continue;
+					if (nowrap < pred) { bw_ue(&w, 0); bw_ue(&w, pred - nowrap - 1); } else { bw_ue(&w, 1); bw_ue(&w, nowrap - pred - 1); }
+					pred = nowrap;
+				}
+				bw_ue(&w, 3);
+			} else bw_u(&w, 1, 0);   /* ref_pic_list_modification_flag_l0 */
 			if (pp->type == 1) bw_u(&w, 1, 0);
 			int wp = pp->type == 0 ? g->wp_p : g->wp_b;
 			if (wp == 1) {
@@ -371,7 +426,23 @@ static void encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr
 				}
 			}
 		}
-		if (pp->is_ref) { if (pp->idr) { bw_u(&w, 1, 0); bw_u(&w, 1, 0); } else bw_u(&w, 1, 0); }
+		if (pp->is_ref) {
+			if (pp->idr) { bw_u(&w, 1, 0); bw_u(&w, 1, g->dpb_mode && idr_long); }
+			else if (n_mmco) {   /* dec_ref_pic_marking( ) with adaptive_ref_pic_marking_mode_flag = 1 (7.3.3.3) */
+				bw_u(&w, 1, 1);
+				for (int k = 0; k < n_mmco; k++) {
+					const int op = mmco[k][0];
+					bw_ue(&w, op);
+					if (op == 1 || op == 3) bw_ue(&w, mmco[k][1]);        /* difference_of_pic_nums_minus1 */
+					if (op == 2) bw_ue(&w, mmco[k][1]);                   /* long_term_pic_num */
+					if (op == 3) bw_ue(&w, mmco[k][2]);                   /* long_term_frame_idx */
+					if (op == 4) bw_ue(&w, mmco[k][1]);                   /* max_long_term_frame_idx_plus1 */
+					if (op == 6) bw_ue(&w, mmco[k][1]);                   /* long_term_frame_idx */
+				}
+				bw_ue(&w, 0);
+			}
+			else bw_u(&w, 1, 0);
+		}
 		int cabac_init_idc = rnd(g, 3);
 		if (g->cabac && pp->type != 2) bw_ue(&w, cabac_init_idc);
 		int slice_qp = g->qp0 + rnd(g, 7) - 3;
@@ -415,14 +486,23 @@ static void encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr
 		e264_emit_nal(out, pp->is_ref ? 2 + pp->idr : 0, pp->idr ? 5 : 1, w.buf, w.pos / 8);
 		free(w.buf); free(s);
 	}
-	/* sliding-window marking */
+	for (int k = 0; k < n_mmco; k++) g->stat_mmco[mmco[k][0]]++;
+	g->stat_idr_long += idr_long;
+	/* marking: the planned memory-management operations, or the sliding window (8.2.5.3) */
 	if (pp->is_ref) {
-		cp->used = 1;
-		int n = 0; for (int i = 0; i < E264_MAX_SLOTS; i++) n += g->dpb[i].used;
-		while (n > g->refs) {
-			int best = -1;
-			for (int i = 0; i < E264_MAX_SLOTS; i++) if (g->dpb[i].used && i != slot && (best < 0 || g->dpb[i].frame_num < g->dpb[best].frame_num)) best = i;
-			g->dpb[best].used = 0; n--;
+		if (n_mmco || (g->dpb_mode && pp->idr)) {
+			for (int i = 0; i < E264_MAX_SLOTS; i++) if (i != slot) { g->dpb[i].used = m_used[i]; g->dpb[i].is_long = m_long[i]; g->dpb[i].long_idx = m_idx[i]; }
+			g->max_long_idx_plus1 = m_max;
+			cp->used = 1; cp->is_long = cur_long >= 0; cp->long_idx = cur_long >= 0 ? cur_long : 0;
+		} else {
+			cp->used = 1; cp->is_long = 0; cp->long_idx = 0;
+			int n = 0; for (int i = 0; i < E264_MAX_SLOTS; i++) n += g->dpb[i].used;
+			while (n > g->refs) {
+				int best = -1;
+				for (int i = 0; i < E264_MAX_SLOTS; i++) if (g->dpb[i].used && !g->dpb[i].is_long && i != slot && (best < 0 || g->dpb[i].frame_num < g->dpb[best].frame_num)) best = i;
+				if (best < 0) break;
+				g->dpb[best].used = 0; n--;
+			}
 		}
 	}
 }
@@ -459,7 +539,9 @@ int main(int argc, char **argv) {
 	g->mvrange = argi(argc, argv, "--mvrange", 24);
 	g->intra_pct = argi(argc, argv, "--intra-pct", 10);
 	g->skip_pct = argi(argc, argv, "--skip-pct", 15);
-	g->log2_max_frame_num = 8; g->log2_max_poc_lsb = 10;
+	g->dpb_mode = argf(argc, argv, "--dpb"); g->poc_type = argi(argc, argv, "--poc-type", 0);
+	g->log2_max_frame_num = g->dpb_mode ? 4 : 8; g->log2_max_poc_lsb = 10;
+	if ((g->dpb_mode || g->poc_type) && g->gop != 1) { fprintf(stderr, "gen264: --dpb / --poc-type need --gop IP\n"); return 2; }
 	if (g->slices > g->H) g->slices = g->H;
 	if (g->refs < 1) g->refs = 1;
 	if (g->refs > 16) g->refs = 16;
@@ -501,5 +583,6 @@ int main(int argc, char **argv) {
 	if (!f) { perror(outp); return 2; }
 	fwrite(out.p, 1, out.n, f); fclose(f);
 	fprintf(stderr, "gen264: %d frames %dx%d, %zu bytes (%.1f bits/MB)\n", g->frames, g->W * 16, g->H * 16, out.n, 8.0 * out.n / ((double)g->frames * nmb));
+	if (g->dpb_mode) fprintf(stderr, "gen264: --dpb: %d slices with list modification, memory-management ops 1..6: %d %d %d %d %d %d, %d long-term IDR\n", g->stat_rplm, g->stat_mmco[1], g->stat_mmco[2], g->stat_mmco[3], g->stat_mmco[4], g->stat_mmco[5], g->stat_mmco[6], g->stat_idr_long);
 	return 0;
 }
