@@ -45,6 +45,9 @@ DPB_STREAMS = [
     ("dpb_mmco_cavlc_poc1", 3, 2, "-n 50 -s 113 --gop IP --refs 3 --idr 23 --dpb --poc-type 1 --deblock 0 --cavlc"),
     ("dpb_mmco_poc2",    3, 2, "-n 50 -s 131 --gop IP --refs 2 --idr 29 --dpb --poc-type 2 --deblock 0"),
     ("dpb_mmco_refs5",   3, 2, "-n 60 -s 149 --gop IP --refs 5 --idr 40 --dpb --deblock 0 --wp 1"),
+    # long-term pictures in B slices: temporal direct (no vector scaling for long-term references) and implicit weights
+    ("dpb_ipb_temporal", 3, 2, "-n 60 -s 211 --gop IPB --refs 4 --idr 31 --dpb --deblock 0 --wp 2 --temporal"),
+    ("dpb_ipb_spatial",  3, 2, "-n 60 -s 222 --gop IPB --refs 3 --idr 25 --dpb --deblock 0 --wp 1"),
 ]
 
 

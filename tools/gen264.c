@@ -541,7 +541,7 @@ int main(int argc, char **argv) {
 	g->skip_pct = argi(argc, argv, "--skip-pct", 15);
 	g->dpb_mode = argf(argc, argv, "--dpb"); g->poc_type = argi(argc, argv, "--poc-type", 0);
 	g->log2_max_frame_num = g->dpb_mode ? 4 : 8; g->log2_max_poc_lsb = 10;
-	if ((g->dpb_mode || g->poc_type) && g->gop != 1) { fprintf(stderr, "gen264: --dpb / --poc-type need --gop IP\n"); return 2; }
+	if ((g->dpb_mode && g->gop == 0) || (g->poc_type && g->gop != 1)) { fprintf(stderr, "gen264: --dpb needs --gop IP or IPB, --poc-type needs --gop IP\n"); return 2; }
 	if (g->slices > g->H) g->slices = g->H;
 	if (g->refs < 1) g->refs = 1;
 	if (g->refs > 16) g->refs = 16;
