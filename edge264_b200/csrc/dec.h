@@ -75,6 +75,8 @@ typedef struct Pic {
 	int frame_num, long_term_idx;
 	int poc;                  /* PicOrderCnt = min(top, bottom): direct / implicit weights */
 	int poc_top;              /* TopFieldOrderCnt: bumping and B list order (as the reference, headers.c:82,762) */
+	int poc_dec, poc_top_dec; /* the values in force while the picture itself is decoded: memory_management_control_operation 5 rebases
+	                           * poc/poc_top for output and later pictures only (8.2.1; reference headers.c:46-49, 673-680) */
 	int32_t uid;              /* unique id of the picture = FrameId */
 	int nonexisting;
 	E264MbRec *recs;          /* pinned host records of this picture (kept: co-located info for B direct) */

@@ -399,6 +399,7 @@ static void apply_marking(Edge264Decoder *d) {
 		if (best >= 0) { d->pics[best].ref = 0; slot_release_if_unused(d, best); }
 	}
 	cur->ref = cur_long ? 2 : 1;
+	for (int k = 0; k < h->n_mmco; k++) if (h->mmco[k].op == 5) cur->frame_num = 0;   /* 8.2.1: the picture is now "frame_num 0" for everything that follows */
 	d->prev_ref_frame_num = cur->frame_num;
 	d->q_prev_ref_frame_num = d->q_cur_frame_num;
 	for (int k = 0; k < h->n_mmco; k++) if (h->mmco[k].op == 5) d->q_prev_ref_frame_num = 0;
@@ -566,7 +567,7 @@ static void build_ref_lists(Edge264Decoder *d, const SliceHeader *h, int lists[2
 		nlist[0] = n;
 	} else {
 		int before[E264_MAX_SLOTS], after[E264_MAX_SLOTS], nb = 0, na = 0;
-		for (int i = 0; i < nst; i++) { if (d->pics[st[i]].poc_top <= cur->poc_top) before[nb++] = st[i]; else after[na++] = st[i]; }
+		for (int i = 0; i < nst; i++) { if (d->pics[st[i]].poc_top <= cur->poc_top_dec) before[nb++] = st[i]; else after[na++] = st[i]; }
 		for (int i = 1; i < nb; i++) for (int j = i; j > 0 && d->pics[before[j]].poc_top > d->pics[before[j - 1]].poc_top; j--) { int t = before[j]; before[j] = before[j - 1]; before[j - 1] = t; }
 		for (int i = 1; i < na; i++) for (int j = i; j > 0 && d->pics[after[j]].poc_top < d->pics[after[j - 1]].poc_top; j--) { int t = after[j]; after[j] = after[j - 1]; after[j - 1] = t; }
 		int n = 0;
@@ -674,7 +675,7 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 			}
 			d->q_cur_frame_num = qfn;
 		}
-		cp->in_use = 1; cp->frame_num = frame_num_abs; cp->poc = poc; cp->poc_top = poc_top; cp->uid = d->next_uid++; cp->host_buf = hbuf;
+		cp->in_use = 1; cp->frame_num = frame_num_abs; cp->poc = cp->poc_dec = poc; cp->poc_top = cp->poc_top_dec = poc_top; cp->uid = d->next_uid++; cp->host_buf = hbuf;
 		d->hb[hbuf].state = 1; d->hb[hbuf].frame_id = cp->uid; d->hb[hbuf].borrowed = 0; d->hb[hbuf].submitted = 0;
 		d->cur = slot; d->cur_idr = idr; d->cur_nal_ref_idc = nal_ref_idc;
 		d->first_sh = *h;
@@ -691,7 +692,7 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 		for (int k = 0; k < h->n_mmco; k++) if (h->mmco[k].op == 5) has_mmco5 = 1;
 		if (idr || has_mmco5) {
 			while (bump_frame(d, slot));
-			if (has_mmco5) { cp->frame_num = 0; cp->poc_top -= cp->poc; cp->poc = 0; /* tempPicOrderCnt subtraction (8.2.1) */ }
+			if (has_mmco5) { cp->poc_top -= cp->poc; cp->poc = 0; }   /* tempPicOrderCnt subtraction (8.2.1) for output order and later pictures; frame_num restarts in apply_marking, once the picture's own lists and operations have used the real value */
 		}
 		/* C.4.5.3 bumping before insertion (reference headers.c:1229-1250) */
 		int max_bump = s->max_num_ref_frames;
@@ -729,7 +730,7 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 	c->num_ref[0] = h->num_ref[0]; c->num_ref[1] = h->num_ref[1];
 	c->direct_spatial = h->direct_spatial; c->direct_8x8_inference = s->direct_8x8_inference; c->transform_8x8_mode = p->transform_8x8_mode;
 	c->qp = h->slice_qp; c->chroma_qp_offset[0] = p->chroma_qp_index_offset[0]; c->chroma_qp_offset[1] = p->chroma_qp_index_offset[1];
-	c->deblock_idc = h->deblock_idc; c->cur_poc = cp->poc;
+	c->deblock_idc = h->deblock_idc; c->cur_poc = cp->poc_dec;
 	c->mbi = d->mbi; c->recs = cp->recs; c->coefs = d->coefs; c->n_coefs = d->n_coefs; c->coef_cap = d->coef_cap;
 	c->col_recs = NULL; c->col_slot_uid = NULL; c->error = 0; c->n_intra = 0;
 	memset(c->ref_slot, -1, sizeof(c->ref_slot)); memset(c->ref_long, 0, sizeof(c->ref_long));
@@ -753,7 +754,7 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 				int w1 = 32;
 				if (c->ref_slot[0][i0] >= 0 && c->ref_slot[1][i1] >= 0 && !c->ref_long[0][i0] && !c->ref_long[1][i1]) {
 					int poc0 = c->ref_poc[0][i0], poc1 = c->ref_poc[1][i1];
-					int tb = cp->poc - poc0, td = poc1 - poc0;
+					int tb = cp->poc_dec - poc0, td = poc1 - poc0;
 					tb = tb < -128 ? -128 : tb > 127 ? 127 : tb; td = td < -128 ? -128 : td > 127 ? 127 : td;
 					if (td != 0) {
 						int tx = (16384 + (td < 0 ? -td : td) / 2) / td;

@@ -12,7 +12,7 @@
  *          [--refs N] [--t8x8 pct] [--scaling 0|1|2] [--wp 0|1|2] [--slices N] [--deblock 0|1|2]
  *          [--density pct] [--qp Q] [--temporal] [--pcm permille] [--crop-bottom px] [--level idc]
  *          [--mvrange qpel] [--intra-pct P] [--skip-pct P]
- *          [--dpb] [--poc-type 0|1|2]      (with --gop IP: reference-list modification to short- and long-term
+ *          [--dpb] [--mmco5] [--poc-type 0|1|2]  (with --gop IP / IPB: reference-list modification to short- and long-term
  *                                           pictures, memory-management operations 1,2,3,4,6, long-term IDR,
  *                                           4-bit frame_num wrap-around; picture order count types 1 and 2)
  */
@@ -40,7 +40,7 @@ typedef struct GenState {
 	int log2_max_frame_num, log2_max_poc_lsb;
 	int drift[2];           /* per-picture global motion */
 	int cur_is_b;
-	int dpb_mode, poc_type, max_long_idx_plus1, stat_rplm, stat_mmco[7], stat_idr_long;   /* --dpb: list modification + memory-management stress on I P P P streams; --poc-type 0|1|2 */
+	int dpb_mode, mmco5, poc_type, max_long_idx_plus1, stat_rplm, stat_mmco[7], stat_idr_long;   /* --dpb: list modification + memory-management stress on I P P P streams; --poc-type 0|1|2 */
 } GenState;
 
 static inline uint64_t rnd64(GenState *g) { uint64_t x = g->rng; x ^= x >> 12; x ^= x << 25; x ^= x >> 27; g->rng = x; return x * 0x2545F4914F6CDD1Dull; }
@@ -296,7 +296,8 @@ static void gen_choose_mb(GenState *g, SliceCtx *s, MbSyn *m, int allow_skip) {
 /* ------------------------------------------------------------------------------------------ */
 typedef struct PicPlan { int type; int idr; int is_ref; int frame_num; int poc; } PicPlan;   /* type: 0 P, 1 B, 2 I */
 
-static void encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr_pic_id) {
+/* returns 1 when the picture carried memory_management_control_operation 5 (frame_num and POC restart after it) */
+static int encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr_pic_id) {
 	int nmb = g->W * g->H;
 	/* free DPB slot for this picture */
 	int slot = -1;
@@ -336,7 +337,7 @@ static void encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr
 
 	/* --dpb: plan this picture's reference marking (8.2.5.4) on a copy of the DPB model; every operation targets a
 	 * picture that exists, and at most refs-1 other references remain so that the picture itself fits */
-	int mmco[40][3], n_mmco = 0, idr_long = 0, cur_long = -1;
+	int mmco[40][3], n_mmco = 0, idr_long = 0, cur_long = -1, did_op5 = 0;
 	int m_used[E264_MAX_SLOTS], m_long[E264_MAX_SLOTS], m_idx[E264_MAX_SLOTS], m_max = g->max_long_idx_plus1;
 	for (int i = 0; i < E264_MAX_SLOTS; i++) { m_used[i] = g->dpb[i].used && i != slot; m_long[i] = g->dpb[i].is_long; m_idx[i] = g->dpb[i].long_idx; }
 	if (g->dpb_mode && pp->idr) { idr_long = g->refs > 1 && rnd(g, 4) == 0;   /* with one reference frame the reference decoder asserts (edge264_headers.c:1099) */ m_max = idr_long ? 1 : 0; cur_long = idr_long ? 0 : -1; }
@@ -347,12 +348,14 @@ static void encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr
 #define DROP_IDX(k) do { for (int i = 0; i < E264_MAX_SLOTS; i++) if (m_used[i] && m_long[i] && m_idx[i] == (k)) m_used[i] = 0; } while (0)
 		int cnt0 = 0, nshort0 = 0, t;
 		for (int i = 0; i < E264_MAX_SLOTS; i++) if (m_used[i]) { cnt0++; nshort0 += !m_long[i]; }
-		const int adaptive = rnd(g, 2) || (cnt0 >= g->refs && nshort0 == 0);   /* the sliding window needs a short-term picture to drop */
+		const int op5 = g->mmco5 && g->gop == 1 && pp->frame_num >= 3 && rnd(g, 12) == 0;   /* --mmco5 only: the reference reports one FrameId twice after such a picture (observed), so these streams are not in the parity suite */   /* 8.2.5.4: everything else leaves, this picture restarts frame_num and POC at 0 */
+		const int adaptive = !op5 && (rnd(g, 2) || (cnt0 >= g->refs && nshort0 == 0));   /* the sliding window needs a short-term picture to drop */
+		if (op5) { mmco[0][0] = 5; n_mmco = 1; did_op5 = 1; for (int i = 0; i < E264_MAX_SLOTS; i++) m_used[i] = 0; m_max = 0; }
 		/* short-term pictures about to alias in frame_num must go in any case */
-		for (int i = 0; i < E264_MAX_SLOTS; i++) if (m_used[i] && !m_long[i] && pp->frame_num - g->dpb[i].frame_num >= maxfn - 3) { mmco[n_mmco][0] = 1; mmco[n_mmco][1] = DIFF(i) - 1; n_mmco++; m_used[i] = 0; }
+		for (int i = 0; i < E264_MAX_SLOTS && !op5; i++) if (m_used[i] && !m_long[i] && pp->frame_num - g->dpb[i].frame_num >= maxfn - 3) { mmco[n_mmco][0] = 1; mmco[n_mmco][1] = DIFF(i) - 1; n_mmco++; m_used[i] = 0; }
 		if (adaptive || n_mmco) {
 			if (rnd(g, 3) == 0) { m_max = rnd(g, g->refs + 1); mmco[n_mmco][0] = 4; mmco[n_mmco][1] = m_max; n_mmco++; for (int i = 0; i < E264_MAX_SLOTS; i++) if (m_used[i] && m_long[i] && m_idx[i] >= m_max) m_used[i] = 0; }
-			if (m_max > 0 && rnd(g, 2)) { PICK(!m_long[i], t); if (t >= 0) { int k = rnd(g, m_max); DROP_IDX(k); mmco[n_mmco][0] = 3; mmco[n_mmco][1] = DIFF(t) - 1; mmco[n_mmco][2] = k; n_mmco++; m_long[t] = 1; m_idx[t] = k; } }
+			if (g->refs > 1 && m_max > 0 && rnd(g, 2)) { PICK(!m_long[i], t); if (t >= 0) { int k = rnd(g, m_max); DROP_IDX(k); mmco[n_mmco][0] = 3; mmco[n_mmco][1] = DIFF(t) - 1; mmco[n_mmco][2] = k; n_mmco++; m_long[t] = 1; m_idx[t] = k; } }
 			if (rnd(g, 3) == 0) { PICK(!m_long[i], t); if (t >= 0) { mmco[n_mmco][0] = 1; mmco[n_mmco][1] = DIFF(t) - 1; n_mmco++; m_used[t] = 0; } }
 			if (rnd(g, 4) == 0) { PICK(m_long[i], t); if (t >= 0) { mmco[n_mmco][0] = 2; mmco[n_mmco][1] = m_idx[t]; n_mmco++; m_used[t] = 0; } }
 			for (;;) {   /* room for the current picture */
@@ -362,7 +365,7 @@ static void encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr
 				if (old >= 0) { mmco[n_mmco][0] = 1; mmco[n_mmco][1] = DIFF(old) - 1; n_mmco++; m_used[old] = 0; }
 				else { PICK(m_long[i], t); mmco[n_mmco][0] = 2; mmco[n_mmco][1] = m_idx[t]; n_mmco++; m_used[t] = 0; }
 			}
-			if (m_max > 0 && rnd(g, 4) == 0) { int k = rnd(g, m_max); DROP_IDX(k); mmco[n_mmco][0] = 6; mmco[n_mmco][1] = k; n_mmco++; cur_long = k; }
+			if (g->refs > 1 && m_max > 0 && rnd(g, 4) == 0) { int k = rnd(g, m_max); DROP_IDX(k); mmco[n_mmco][0] = 6; mmco[n_mmco][1] = k; n_mmco++; cur_long = k; }
 		}
 #undef DIFF
 #undef PICK
@@ -487,6 +490,7 @@ static void encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr
 		free(w.buf); free(s);
 	}
 	for (int k = 0; k < n_mmco; k++) g->stat_mmco[mmco[k][0]]++;
+	if (getenv("GEN264_DEBUG")) { fprintf(stderr, "pic uid %d type %d idr %d frame_num %d poc %d refs %d:", cp->uid, pp->type, pp->idr, pp->frame_num, pp->poc, n0); for (int k = 0; k < n_mmco; k++) fprintf(stderr, " mmco%d(%d,%d)", mmco[k][0], mmco[k][1], mmco[k][2]); fprintf(stderr, "%s\n", idr_long ? " long-term IDR" : ""); }
 	g->stat_idr_long += idr_long;
 	/* marking: the planned memory-management operations, or the sliding window (8.2.5.3) */
 	if (pp->is_ref) {
@@ -494,6 +498,7 @@ static void encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr
 			for (int i = 0; i < E264_MAX_SLOTS; i++) if (i != slot) { g->dpb[i].used = m_used[i]; g->dpb[i].is_long = m_long[i]; g->dpb[i].long_idx = m_idx[i]; }
 			g->max_long_idx_plus1 = m_max;
 			cp->used = 1; cp->is_long = cur_long >= 0; cp->long_idx = cur_long >= 0 ? cur_long : 0;
+			if (did_op5) { cp->frame_num = 0; cp->poc = 0; }
 		} else {
 			cp->used = 1; cp->is_long = 0; cp->long_idx = 0;
 			int n = 0; for (int i = 0; i < E264_MAX_SLOTS; i++) n += g->dpb[i].used;
@@ -505,6 +510,7 @@ static void encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr
 			}
 		}
 	}
+	return did_op5;
 }
 
 static int argi(int argc, char **argv, const char *name, int def) {
@@ -539,7 +545,7 @@ int main(int argc, char **argv) {
 	g->mvrange = argi(argc, argv, "--mvrange", 24);
 	g->intra_pct = argi(argc, argv, "--intra-pct", 10);
 	g->skip_pct = argi(argc, argv, "--skip-pct", 15);
-	g->dpb_mode = argf(argc, argv, "--dpb"); g->poc_type = argi(argc, argv, "--poc-type", 0);
+	g->dpb_mode = argf(argc, argv, "--dpb"); g->mmco5 = argf(argc, argv, "--mmco5"); g->poc_type = argi(argc, argv, "--poc-type", 0);
 	g->log2_max_frame_num = g->dpb_mode ? 4 : 8; g->log2_max_poc_lsb = 10;
 	if ((g->dpb_mode && g->gop == 0) || (g->poc_type && g->gop != 1)) { fprintf(stderr, "gen264: --dpb needs --gop IP or IPB, --poc-type needs --gop IP\n"); return 2; }
 	if (g->slices > g->H) g->slices = g->H;
@@ -565,7 +571,7 @@ int main(int argc, char **argv) {
 		}
 		if (g->gop == 1) {
 			PicPlan p = {0, 0, 1, frame_num, disp * 2};
-			encode_picture(g, &out, &p, 0);
+			if (encode_picture(g, &out, &p, 0)) { frame_num = 0; disp = 0; }
 			frame_num++; disp++; since_idr++; k++;
 			continue;
 		}
