@@ -34,6 +34,8 @@ STREAMS = [
     # 4096 samples wide: the reference pads such strides (edge264_headers.c:2027-2037); ours pads differently,
     # only the samples and the reported strides matter
     ("wide_256x2",       256, 2, "-n 5 -s 24 --gop IPB --deblock 0"),
+    # long-term references, list modification, memory-management operations (more of these, CPU side, in DPB_STREAMS)
+    ("dpb_mmco_cabac",   4, 3, "-n 40 -s 101 --gop IP --refs 4 --idr 17 --dpb --deblock 0"),
 ]
 
 
@@ -41,7 +43,6 @@ STREAMS = [
 # operations, long-term IDR, frame_num wrap-around, picture order count types 1 and 2 — checked CPU-side against the
 # reference and the golden digests (reference behaviours mirrored: edge264_headers.c:611-701, 768-893)
 DPB_STREAMS = [
-    ("dpb_mmco_cabac",   4, 3, "-n 40 -s 101 --gop IP --refs 4 --idr 17 --dpb --deblock 0"),
     ("dpb_mmco_cavlc_poc1", 3, 2, "-n 50 -s 113 --gop IP --refs 3 --idr 23 --dpb --poc-type 1 --deblock 0 --cavlc"),
     ("dpb_mmco_poc2",    3, 2, "-n 50 -s 131 --gop IP --refs 2 --idr 29 --dpb --poc-type 2 --deblock 0"),
     ("dpb_mmco_refs5",   3, 2, "-n 60 -s 149 --gop IP --refs 5 --idr 40 --dpb --deblock 0 --wp 1"),
