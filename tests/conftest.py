@@ -49,6 +49,9 @@ DPB_STREAMS = [
     # long-term pictures in B slices: temporal direct (no vector scaling for long-term references) and implicit weights
     ("dpb_ipb_temporal", 3, 2, "-n 60 -s 211 --gop IPB --refs 4 --idr 31 --dpb --deblock 0 --wp 2 --temporal"),
     ("dpb_ipb_spatial",  3, 2, "-n 60 -s 222 --gop IPB --refs 3 --idr 25 --dpb --deblock 0 --wp 1"),
+    # slices of one picture with different slice types (I in P pictures, I/P in B pictures), deblocking across them
+    ("mixed_slices_cabac", 5, 6, "-n 24 -s 503 --gop IPB --refs 3 --idr 13 --slices 4 --mixed-slices --deblock 0 --wp 1"),
+    ("mixed_slices_cavlc", 5, 6, "-n 24 -s 505 --gop IPB --refs 2 --idr 13 --slices 3 --mixed-slices --deblock 2 --wp 2 --temporal --cavlc"),
 ]
 
 

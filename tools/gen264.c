@@ -12,6 +12,7 @@
  *          [--refs N] [--t8x8 pct] [--scaling 0|1|2] [--wp 0|1|2] [--slices N] [--deblock 0|1|2]
  *          [--density pct] [--qp Q] [--temporal] [--pcm permille] [--crop-bottom px] [--level idc]
  *          [--mvrange qpel] [--intra-pct P] [--skip-pct P]
+ *          [--mixed-slices]                 (slices of one picture take different slice types)
  *          [--dpb] [--mmco5] [--poc-type 0|1|2]  (with --gop IP / IPB: reference-list modification to short- and long-term
  *                                           pictures, memory-management operations 1,2,3,4,6, long-term IDR,
  *                                           4-bit frame_num wrap-around; picture order count types 1 and 2)
@@ -40,7 +41,7 @@ typedef struct GenState {
 	int log2_max_frame_num, log2_max_poc_lsb;
 	int drift[2];           /* per-picture global motion */
 	int cur_is_b;
-	int dpb_mode, mmco5, poc_type, max_long_idx_plus1, stat_rplm, stat_mmco[7], stat_idr_long;   /* --dpb: list modification + memory-management stress on I P P P streams; --poc-type 0|1|2 */
+	int mixed, dpb_mode, mmco5, poc_type, max_long_idx_plus1, stat_rplm, stat_mmco[7], stat_idr_long;   /* --dpb: list modification + memory-management stress on I P P P streams; --poc-type 0|1|2 */
 } GenState;
 
 static inline uint64_t rnd64(GenState *g) { uint64_t x = g->rng; x ^= x >> 12; x ^= x << 25; x ^= x >> 27; g->rng = x; return x * 0x2545F4914F6CDD1Dull; }
@@ -372,26 +373,30 @@ static int encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr_
 #undef DROP_IDX
 	}
 
-	int pps_id = pp->type == 2 ? 0 : pp->type == 0 ? 1 : 2;
 	int rows_per_slice = (g->H + g->slices - 1) / g->slices;
-	int16_t w_tab[2][16][3], o_tab[2][16][3]; int lwd = 0, cwd = 0;
+	int16_t w_tab[2][16][3], o_tab[2][16][3]; int lwd = 0, cwd = 0, w_ready = 0; uint8_t w_sent[2][16]; memset(w_sent, 0, sizeof(w_sent));
 	for (int sl = 0; sl * rows_per_slice < g->H; sl++) {
+		/* --mixed-slices: later slices of a P picture may be I slices, of a B picture I or P slices (7.4.3: slice types of one
+		 * picture are independent) */
+		int st = pp->type;
+		if (g->mixed && sl > 0 && pp->type != 2 && rnd(g, 3) == 0) st = (pp->type == 1 && rnd(g, 2)) ? 0 : 2;
 		int first_mb = sl * rows_per_slice * g->W;
 		int last_mb = (sl + 1) * rows_per_slice * g->W; if (last_mb > nmb) last_mb = nmb;
+		int pps_id = st == 2 ? 0 : st == 0 ? 1 : 2;
 		BitWriter w; bw_init(&w, 1 << 16);
 		bw_ue(&w, first_mb);
-		bw_ue(&w, pp->type + (rnd(g, 2) ? 5 : 0));
+		bw_ue(&w, st + (rnd(g, 2) ? 5 : 0));
 		bw_ue(&w, pps_id);
 		bw_u(&w, g->log2_max_frame_num, pp->frame_num & ((1 << g->log2_max_frame_num) - 1));
 		if (pp->idr) bw_ue(&w, idr_pic_id);
 		if (g->poc_type == 0) bw_u(&w, g->log2_max_poc_lsb, pp->poc & ((1 << g->log2_max_poc_lsb) - 1));
 		int direct_spatial = !g->temporal;
-		if (pp->type != 2) {
-			if (pp->type == 1) bw_u(&w, 1, direct_spatial);
+		if (st != 2) {
+			if (st == 1) bw_u(&w, 1, direct_spatial);
 			bw_u(&w, 1, 1);   /* num_ref_idx_active_override_flag */
 			bw_ue(&w, num_ref[0] - 1);
-			if (pp->type == 1) bw_ue(&w, num_ref[1] - 1);
-			if (g->dpb_mode && pp->type == 0 && n0 > 0 && rnd(g, 2)) {   /* ref_pic_list_modification (7.3.3.1, 8.2.4.3): move existing pictures to the front */
+			if (st == 1) bw_ue(&w, num_ref[1] - 1);
+			if (g->dpb_mode && st == 0 && n0 > 0 && rnd(g, 2)) {   /* ref_pic_list_modification (7.3.3.1, 8.2.4.3): move existing pictures to the front */
 				bw_u(&w, 1, 1); g->stat_rplm++;
 				const int maxfn = 1 << g->log2_max_frame_num;
 				int pred = pp->frame_num & (maxfn - 1), nops = 1 + rnd(g, num_ref[0] < 3 ? num_ref[0] : 3);
@@ -405,10 +410,10 @@ static int encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr_
 				}
 				bw_ue(&w, 3);
 			} else bw_u(&w, 1, 0);   /* ref_pic_list_modification_flag_l0 */
-			if (pp->type == 1) bw_u(&w, 1, 0);
-			int wp = pp->type == 0 ? g->wp_p : g->wp_b;
+			if (st == 1) bw_u(&w, 1, 0);
+			int wp = st == 0 ? g->wp_p : g->wp_b;
 			if (wp == 1) {
-				if (sl == 0) {
+				if (!w_ready) { w_ready = 1;
 					lwd = rnd(g, pp->type == 1 ? 7 : 8); cwd = rnd(g, pp->type == 1 ? 7 : 8);   /* logWD 7 + inferred weight 128 is only legal for uni-prediction */
 					for (int l = 0; l < 2; l++) for (int i = 0; i < 16; i++) for (int c = 0; c < 3; c++) {
 						int wd = c ? cwd : lwd;
@@ -419,13 +424,14 @@ static int encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr_
 					}
 				}
 				bw_ue(&w, lwd); bw_ue(&w, cwd);
-				for (int l = 0; l <= (pp->type == 1); l++) for (int i = 0; i < num_ref[l]; i++) {
+				for (int l = 0; l <= (st == 1); l++) for (int i = 0; i < num_ref[l]; i++) {
 					int lf = rnd(g, 4) != 0, cf = rnd(g, 4) != 0;
-					if (sl > 0) { lf = !(w_tab[l][i][0] == (1 << lwd) && o_tab[l][i][0] == 0); cf = 1; }
+					if (w_sent[l][i]) { lf = !(w_tab[l][i][0] == (1 << lwd) && o_tab[l][i][0] == 0); cf = 1; }
 					if (!lf) { w_tab[l][i][0] = (int16_t)(1 << lwd); o_tab[l][i][0] = 0; }
 					if (!cf) for (int c = 1; c < 3; c++) { w_tab[l][i][c] = (int16_t)(1 << cwd); o_tab[l][i][c] = 0; }
 					bw_u(&w, 1, lf); if (lf) { bw_se(&w, w_tab[l][i][0]); bw_se(&w, o_tab[l][i][0]); }
 					bw_u(&w, 1, cf); if (cf) for (int c = 1; c < 3; c++) { bw_se(&w, w_tab[l][i][c]); bw_se(&w, o_tab[l][i][c]); }
+					w_sent[l][i] = 1;
 				}
 			}
 		}
@@ -447,7 +453,7 @@ static int encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr_
 			else bw_u(&w, 1, 0);
 		}
 		int cabac_init_idc = rnd(g, 3);
-		if (g->cabac && pp->type != 2) bw_ue(&w, cabac_init_idc);
+		if (g->cabac && st != 2) bw_ue(&w, cabac_init_idc);
 		int slice_qp = g->qp0 + rnd(g, 7) - 3;
 		int pic_init_qp = g->qp0;
 		bw_se(&w, slice_qp - pic_init_qp);
@@ -460,7 +466,7 @@ static int encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr_
 		MbSyn syn;
 		s->cabac = g->cabac; s->bw = &w; s->syn = &syn;
 		s->w_mbs = g->W; s->h_mbs = g->H;
-		s->slice_type = pp->type; s->slice_id = sl + 1; s->slice_idx = sl;
+		s->slice_type = st; s->slice_id = sl + 1; s->slice_idx = sl;
 		s->num_ref[0] = num_ref[0]; s->num_ref[1] = num_ref[1];
 		s->direct_spatial = direct_spatial; s->direct_8x8_inference = 1; s->transform_8x8_mode = g->t8x8_mode;
 		s->qp = slice_qp; s->deblock_idc = idc; s->cur_poc = pp->poc;
@@ -468,11 +474,11 @@ static int encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr_
 		memset(s->ref_slot, -1, sizeof(s->ref_slot));
 		for (int i = 0; i < n0 && i < 16; i++) { s->ref_slot[0][i] = (int8_t)l0[i]; s->ref_uid[0][i] = g->dpb[l0[i]].uid; s->ref_poc[0][i] = g->dpb[l0[i]].poc; }
 		for (int i = 0; i < n1 && i < 16; i++) { s->ref_slot[1][i] = (int8_t)l1[i]; s->ref_uid[1][i] = g->dpb[l1[i]].uid; s->ref_poc[1][i] = g->dpb[l1[i]].poc; }
-		if (pp->type == 1 && n1 > 0) { s->col_recs = g->dpb[l1[0]].recs; s->col_slot_uid = g->dpb[l1[0]].slot_uid; }
+		if (st == 1 && n1 > 0) { s->col_recs = g->dpb[l1[0]].recs; s->col_slot_uid = g->dpb[l1[0]].slot_uid; }
 		s->skip_run = 0;
 		if (g->cabac) {
 			while (w.pos & 7) bw_u(&w, 1, 1);   /* cabac_alignment_one_bit */
-			cabac_init_states(s->ce.state, pp->type == 2 ? 0 : 1 + cabac_init_idc, slice_qp);
+			cabac_init_states(s->ce.state, st == 2 ? 0 : 1 + cabac_init_idc, slice_qp);
 			cabac_enc_start(&s->ce, &w);
 		}
 		for (int a = first_mb; a < last_mb; a++) {
@@ -545,6 +551,7 @@ int main(int argc, char **argv) {
 	g->mvrange = argi(argc, argv, "--mvrange", 24);
 	g->intra_pct = argi(argc, argv, "--intra-pct", 10);
 	g->skip_pct = argi(argc, argv, "--skip-pct", 15);
+	g->mixed = argf(argc, argv, "--mixed-slices");
 	g->dpb_mode = argf(argc, argv, "--dpb"); g->mmco5 = argf(argc, argv, "--mmco5"); g->poc_type = argi(argc, argv, "--poc-type", 0);
 	g->log2_max_frame_num = g->dpb_mode ? 4 : 8; g->log2_max_poc_lsb = 10;
 	if ((g->dpb_mode && g->gop == 0) || (g->poc_type && g->gop != 1)) { fprintf(stderr, "gen264: --dpb needs --gop IP or IPB, --poc-type needs --gop IP\n"); return 2; }
