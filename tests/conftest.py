@@ -51,6 +51,10 @@ DPB_STREAMS = [
     ("dpb_ipb_spatial",  3, 2, "-n 60 -s 222 --gop IPB --refs 3 --idr 25 --dpb --deblock 0 --wp 1"),
     # slices of one picture with different slice types (I in P pictures, I/P in B pictures), deblocking across them
     ("mixed_slices_cabac", 5, 6, "-n 24 -s 503 --gop IPB --refs 3 --idr 13 --slices 4 --mixed-slices --deblock 0 --wp 1"),
+    # frame cropping rectangle on all four sides; parameter sets re-sent between pictures (new chroma QP offsets and
+    # scaling lists in the picture parameter sets, the unchanged sequence parameter set repeated)
+    ("crop_rect",        4, 3, "-n 8 -s 838 --gop IPB --refs 2 --crop-left 10 --crop-right 6 --crop-top 8 --crop-bottom 4 --deblock 0"),
+    ("ps_update",        4, 4, "-n 30 -s 701 --gop IP --refs 2 --idr 11 --ps-update --scaling 3 --t8x8 50 --deblock 0"),
     ("mixed_slices_cavlc", 5, 6, "-n 24 -s 505 --gop IPB --refs 2 --idr 13 --slices 3 --mixed-slices --deblock 2 --wp 2 --temporal --cavlc"),
 ]
 

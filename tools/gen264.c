@@ -12,7 +12,10 @@
  *          [--refs N] [--t8x8 pct] [--scaling 0|1|2] [--wp 0|1|2] [--slices N] [--deblock 0|1|2]
  *          [--density pct] [--qp Q] [--temporal] [--pcm permille] [--crop-bottom px] [--level idc]
  *          [--mvrange qpel] [--intra-pct P] [--skip-pct P]
+ *          [--crop-left px] [--crop-right px] [--crop-top px]   (even numbers; with --crop-bottom: frame cropping rectangle)
  *          [--mixed-slices]                 (slices of one picture take different slice types)
+ *          [--ps-update]                    (picture parameter sets re-sent with new chroma QP offsets, and the unchanged
+ *                                            sequence parameter set repeated, between pictures)
  *          [--dpb] [--mmco5] [--poc-type 0|1|2]  (with --gop IP / IPB: reference-list modification to short- and long-term
  *                                           pictures, memory-management operations 1,2,3,4,6, long-term IDR,
  *                                           4-bit frame_num wrap-around; picture order count types 1 and 2)
@@ -41,7 +44,7 @@ typedef struct GenState {
 	int log2_max_frame_num, log2_max_poc_lsb;
 	int drift[2];           /* per-picture global motion */
 	int cur_is_b;
-	int mixed, dpb_mode, mmco5, poc_type, max_long_idx_plus1, stat_rplm, stat_mmco[7], stat_idr_long;   /* --dpb: list modification + memory-management stress on I P P P streams; --poc-type 0|1|2 */
+	int crop_left, crop_right, crop_top, mixed, ps_update, dpb_mode, mmco5, poc_type, max_long_idx_plus1, stat_rplm, stat_mmco[7], stat_idr_long;   /* --dpb: list modification + memory-management stress on I P P P streams; --poc-type 0|1|2 */
 } GenState;
 
 static inline uint64_t rnd64(GenState *g) { uint64_t x = g->rng; x ^= x >> 12; x ^= x << 25; x ^= x >> 27; g->rng = x; return x * 0x2545F4914F6CDD1Dull; }
@@ -95,8 +98,9 @@ static void write_sps(GenState *g, ByteBuf *out) {
 	bw_ue(&w, g->W - 1); bw_ue(&w, g->H - 1);
 	bw_u(&w, 1, 1);                      /* frame_mbs_only_flag */
 	bw_u(&w, 1, 1);                      /* direct_8x8_inference_flag */
-	bw_u(&w, 1, g->crop_bottom > 0);
-	if (g->crop_bottom > 0) { bw_ue(&w, 0); bw_ue(&w, 0); bw_ue(&w, 0); bw_ue(&w, g->crop_bottom / 2); }
+	const int any_crop = g->crop_bottom > 0 || g->crop_left > 0 || g->crop_right > 0 || g->crop_top > 0;
+	bw_u(&w, 1, any_crop);
+	if (any_crop) { bw_ue(&w, g->crop_left / 2); bw_ue(&w, g->crop_right / 2); bw_ue(&w, g->crop_top / 2); bw_ue(&w, g->crop_bottom / 2); }
 	bw_u(&w, 1, 1);                      /* vui_parameters_present_flag: only bitstream_restriction */
 	bw_u(&w, 1, 0); bw_u(&w, 1, 0); bw_u(&w, 1, 0); bw_u(&w, 1, 0); bw_u(&w, 1, 0); bw_u(&w, 1, 0); bw_u(&w, 1, 0); bw_u(&w, 1, 0);
 	bw_u(&w, 1, 1);
@@ -551,7 +555,8 @@ int main(int argc, char **argv) {
 	g->mvrange = argi(argc, argv, "--mvrange", 24);
 	g->intra_pct = argi(argc, argv, "--intra-pct", 10);
 	g->skip_pct = argi(argc, argv, "--skip-pct", 15);
-	g->mixed = argf(argc, argv, "--mixed-slices");
+	g->crop_left = argi(argc, argv, "--crop-left", 0); g->crop_right = argi(argc, argv, "--crop-right", 0); g->crop_top = argi(argc, argv, "--crop-top", 0);
+	g->mixed = argf(argc, argv, "--mixed-slices"); g->ps_update = argf(argc, argv, "--ps-update");
 	g->dpb_mode = argf(argc, argv, "--dpb"); g->mmco5 = argf(argc, argv, "--mmco5"); g->poc_type = argi(argc, argv, "--poc-type", 0);
 	g->log2_max_frame_num = g->dpb_mode ? 4 : 8; g->log2_max_poc_lsb = 10;
 	if ((g->dpb_mode && g->gop == 0) || (g->poc_type && g->gop != 1)) { fprintf(stderr, "gen264: --dpb needs --gop IP or IPB, --poc-type needs --gop IP\n"); return 2; }
@@ -576,6 +581,7 @@ int main(int argc, char **argv) {
 			frame_num = 1; disp = 1; since_idr = 1; k++;
 			continue;
 		}
+		if (g->ps_update && rnd(g, 4) == 0) { if (rnd(g, 3) == 0) write_sps(g, &out); for (int id = 0; id < 3; id++) write_pps(g, &out, id, g->qp0); }
 		if (g->gop == 1) {
 			PicPlan p = {0, 0, 1, frame_num, disp * 2};
 			if (encode_picture(g, &out, &p, 0)) { frame_num = 0; disp = 0; }
