@@ -51,6 +51,9 @@ DPB_STREAMS = [
     ("dpb_ipb_spatial",  3, 2, "-n 60 -s 222 --gop IPB --refs 3 --idr 25 --dpb --deblock 0 --wp 1"),
     # slices of one picture with different slice types (I in P pictures, I/P in B pictures), deblocking across them
     ("mixed_slices_cabac", 5, 6, "-n 24 -s 503 --gop IPB --refs 3 --idr 13 --slices 4 --mixed-slices --deblock 0 --wp 1"),
+    # B pictures used as references (their own marking, lists with references on both sides, B co-located pictures)
+    ("bref_spatial",     4, 4, "-n 40 -s 901 --gop IPB --bref --refs 3 --idr 17 --deblock 0 --wp 1"),
+    ("bref_implicit",    4, 4, "-n 40 -s 905 --gop IPB --bref --refs 4 --idr 21 --deblock 0 --wp 2 --cavlc"),
     # frame cropping rectangle on all four sides; parameter sets re-sent between pictures (new chroma QP offsets and
     # scaling lists in the picture parameter sets, the unchanged sequence parameter set repeated)
     ("crop_rect",        4, 3, "-n 8 -s 838 --gop IPB --refs 2 --crop-left 10 --crop-right 6 --crop-top 8 --crop-bottom 4 --deblock 0"),

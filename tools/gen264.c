@@ -13,6 +13,7 @@
  *          [--density pct] [--qp Q] [--temporal] [--pcm permille] [--crop-bottom px] [--level idc]
  *          [--mvrange qpel] [--intra-pct P] [--skip-pct P]
  *          [--crop-left px] [--crop-right px] [--crop-top px]   (even numbers; with --crop-bottom: frame cropping rectangle)
+ *          [--bref]                         (with --gop IPB: the first B picture of each pair is a reference picture)
  *          [--mixed-slices]                 (slices of one picture take different slice types)
  *          [--ps-update]                    (picture parameter sets re-sent with new chroma QP offsets, and the unchanged
  *                                            sequence parameter set repeated, between pictures)
@@ -44,7 +45,7 @@ typedef struct GenState {
 	int log2_max_frame_num, log2_max_poc_lsb;
 	int drift[2];           /* per-picture global motion */
 	int cur_is_b;
-	int crop_left, crop_right, crop_top, mixed, ps_update, dpb_mode, mmco5, poc_type, max_long_idx_plus1, stat_rplm, stat_mmco[7], stat_idr_long;   /* --dpb: list modification + memory-management stress on I P P P streams; --poc-type 0|1|2 */
+	int bref, crop_left, crop_right, crop_top, mixed, ps_update, dpb_mode, mmco5, poc_type, max_long_idx_plus1, stat_rplm, stat_mmco[7], stat_idr_long;   /* --dpb: list modification + memory-management stress on I P P P streams; --poc-type 0|1|2 */
 } GenState;
 
 static inline uint64_t rnd64(GenState *g) { uint64_t x = g->rng; x ^= x >> 12; x ^= x << 25; x ^= x >> 27; g->rng = x; return x * 0x2545F4914F6CDD1Dull; }
@@ -556,6 +557,7 @@ int main(int argc, char **argv) {
 	g->intra_pct = argi(argc, argv, "--intra-pct", 10);
 	g->skip_pct = argi(argc, argv, "--skip-pct", 15);
 	g->crop_left = argi(argc, argv, "--crop-left", 0); g->crop_right = argi(argc, argv, "--crop-right", 0); g->crop_top = argi(argc, argv, "--crop-top", 0);
+	g->bref = argf(argc, argv, "--bref");
 	g->mixed = argf(argc, argv, "--mixed-slices"); g->ps_update = argf(argc, argv, "--ps-update");
 	g->dpb_mode = argf(argc, argv, "--dpb"); g->mmco5 = argf(argc, argv, "--mmco5"); g->poc_type = argi(argc, argv, "--poc-type", 0);
 	g->log2_max_frame_num = g->dpb_mode ? 4 : 8; g->log2_max_poc_lsb = 10;
@@ -595,7 +597,7 @@ int main(int argc, char **argv) {
 		PicPlan p = {0, 0, 1, frame_num, (disp + nb) * 2};
 		encode_picture(g, &out, &p, 0);
 		frame_num++; k++;
-		for (int b = 0; b < nb; b++) { PicPlan q = {1, 0, 0, frame_num, (disp + b) * 2}; encode_picture(g, &out, &q, 0); k++; }
+		for (int b = 0; b < nb; b++) { PicPlan q = {1, 0, g->bref && b == 0 && nb == 2, frame_num, (disp + b) * 2}; encode_picture(g, &out, &q, 0); if (q.is_ref) frame_num++; k++; }
 		disp += nb + 1; since_idr += nb + 1;
 	}
 	FILE *f = fopen(outp, "wb");
