@@ -51,6 +51,9 @@ DPB_STREAMS = [
     ("dpb_ipb_spatial",  3, 2, "-n 60 -s 222 --gop IPB --refs 3 --idr 25 --dpb --deblock 0 --wp 1"),
     # slices of one picture with different slice types (I in P pictures, I/P in B pictures), deblocking across them
     ("mixed_slices_cabac", 5, 6, "-n 24 -s 503 --gop IPB --refs 3 --idr 13 --slices 4 --mixed-slices --deblock 0 --wp 1"),
+    # quantiser extremes (both 8x8 dequantisation branches, saturating paths) with vectors far outside the picture
+    ("qp_low_far_mv",    4, 3, "-n 9 -s 1101 --gop IPB --refs 2 --qp 2 --t8x8 50 --scaling 1 --density 60 --mvrange 200 --deblock 0 --wp 2"),
+    ("qp_high_far_mv",   4, 3, "-n 9 -s 1104 --gop IPB --refs 2 --qp 50 --t8x8 50 --scaling 3 --density 60 --mvrange 240 --deblock 0 --wp 1 --cavlc"),
     # B pictures used as references (their own marking, lists with references on both sides, B co-located pictures)
     ("bref_spatial",     4, 4, "-n 40 -s 901 --gop IPB --bref --refs 3 --idr 17 --deblock 0 --wp 1"),
     ("bref_implicit",    4, 4, "-n 40 -s 905 --gop IPB --bref --refs 4 --idr 21 --deblock 0 --wp 2 --cavlc"),

@@ -460,6 +460,8 @@ static int encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr_
 		int cabac_init_idc = rnd(g, 3);
 		if (g->cabac && st != 2) bw_ue(&w, cabac_init_idc);
 		int slice_qp = g->qp0 + rnd(g, 7) - 3;
+		if (slice_qp < 0) slice_qp = 0;
+		if (slice_qp > 51) slice_qp = 51;
 		int pic_init_qp = g->qp0;
 		bw_se(&w, slice_qp - pic_init_qp);
 		int idc = g->deblock;
