@@ -36,6 +36,8 @@ STREAMS = [
     ("wide_256x2",       256, 2, "-n 5 -s 24 --gop IPB --deblock 0"),
     # long-term references, list modification, memory-management operations (more of these, CPU side, in DPB_STREAMS)
     ("dpb_mmco_cabac",   4, 3, "-n 40 -s 101 --gop IP --refs 4 --idr 17 --dpb --deblock 0"),
+    # B pictures used as references (verified on the B200 like the one above; its siblings run CPU side)
+    ("bref_spatial",     4, 4, "-n 40 -s 901 --gop IPB --bref --refs 3 --idr 17 --deblock 0 --wp 1"),
 ]
 
 
@@ -55,7 +57,6 @@ DPB_STREAMS = [
     ("qp_low_far_mv",    4, 3, "-n 9 -s 1101 --gop IPB --refs 2 --qp 2 --t8x8 50 --scaling 1 --density 60 --mvrange 200 --deblock 0 --wp 2"),
     ("qp_high_far_mv",   4, 3, "-n 9 -s 1104 --gop IPB --refs 2 --qp 50 --t8x8 50 --scaling 3 --density 60 --mvrange 240 --deblock 0 --wp 1 --cavlc"),
     # B pictures used as references (their own marking, lists with references on both sides, B co-located pictures)
-    ("bref_spatial",     4, 4, "-n 40 -s 901 --gop IPB --bref --refs 3 --idr 17 --deblock 0 --wp 1"),
     ("bref_implicit",    4, 4, "-n 40 -s 905 --gop IPB --bref --refs 4 --idr 21 --deblock 0 --wp 2 --cavlc"),
     # frame cropping rectangle on all four sides; parameter sets re-sent between pictures (new chroma QP offsets and
     # scaling lists in the picture parameter sets, the unchanged sequence parameter set repeated)
