@@ -53,6 +53,12 @@ DPB_STREAMS = [
     ("dpb_ipb_spatial",  3, 2, "-n 60 -s 222 --gop IPB --refs 3 --idr 25 --dpb --deblock 0 --wp 1"),
     # slices of one picture with different slice types (I in P pictures, I/P in B pictures), deblocking across them
     ("mixed_slices_cabac", 5, 6, "-n 24 -s 503 --gop IPB --refs 3 --idr 13 --slices 4 --mixed-slices --deblock 0 --wp 1"),
+    # direct prediction per 4x4 block (direct_8x8_inference_flag 0), P pictures that are not references, access unit
+    # delimiters / SEI / filler NAL units between pictures
+    ("direct4x4_temporal", 4, 4, "-n 20 -s 1203 --gop IPB --direct4x4 --temporal --refs 3 --idr 9 --t8x8 50 --deblock 0 --wp 2"),
+    ("direct4x4_spatial", 4, 4, "-n 20 -s 1204 --gop IPB --direct4x4 --refs 2 --idr 9 --t8x8 50 --deblock 0 --wp 1 --cavlc"),
+    ("nonref_p",         4, 4, "-n 20 -s 1207 --gop IP --nonref-p --refs 3 --idr 9 --deblock 0"),
+    ("extra_nals",       4, 4, "-n 20 -s 1209 --gop IPB --extra-nals --refs 2 --idr 9 --deblock 0"),
     # quantiser extremes (both 8x8 dequantisation branches, saturating paths) with vectors far outside the picture
     ("qp_low_far_mv",    4, 3, "-n 9 -s 1101 --gop IPB --refs 2 --qp 2 --t8x8 50 --scaling 1 --density 60 --mvrange 200 --deblock 0 --wp 2"),
     ("qp_high_far_mv",   4, 3, "-n 9 -s 1104 --gop IPB --refs 2 --qp 50 --t8x8 50 --scaling 3 --density 60 --mvrange 240 --deblock 0 --wp 1 --cavlc"),

@@ -13,6 +13,9 @@
  *          [--density pct] [--qp Q] [--temporal] [--pcm permille] [--crop-bottom px] [--level idc]
  *          [--mvrange qpel] [--intra-pct P] [--skip-pct P]
  *          [--crop-left px] [--crop-right px] [--crop-top px]   (even numbers; with --crop-bottom: frame cropping rectangle)
+ *          [--direct4x4]                    (direct_8x8_inference_flag = 0: direct prediction per 4x4 block)
+ *          [--nonref-p]                     (with --gop IP: some P pictures are not used for reference)
+ *          [--extra-nals]                   (access unit delimiters, SEI and filler data NAL units between pictures)
  *          [--bref]                         (with --gop IPB: the first B picture of each pair is a reference picture)
  *          [--mixed-slices]                 (slices of one picture take different slice types)
  *          [--ps-update]                    (picture parameter sets re-sent with new chroma QP offsets, and the unchanged
@@ -45,7 +48,7 @@ typedef struct GenState {
 	int log2_max_frame_num, log2_max_poc_lsb;
 	int drift[2];           /* per-picture global motion */
 	int cur_is_b;
-	int bref, crop_left, crop_right, crop_top, mixed, ps_update, dpb_mode, mmco5, poc_type, max_long_idx_plus1, stat_rplm, stat_mmco[7], stat_idr_long;   /* --dpb: list modification + memory-management stress on I P P P streams; --poc-type 0|1|2 */
+	int direct4x4, nonref_p, extra_nals, bref, crop_left, crop_right, crop_top, mixed, ps_update, dpb_mode, mmco5, poc_type, max_long_idx_plus1, stat_rplm, stat_mmco[7], stat_idr_long;   /* --dpb: list modification + memory-management stress on I P P P streams; --poc-type 0|1|2 */
 } GenState;
 
 static inline uint64_t rnd64(GenState *g) { uint64_t x = g->rng; x ^= x >> 12; x ^= x << 25; x ^= x >> 27; g->rng = x; return x * 0x2545F4914F6CDD1Dull; }
@@ -98,7 +101,7 @@ static void write_sps(GenState *g, ByteBuf *out) {
 	bw_u(&w, 1, 0);
 	bw_ue(&w, g->W - 1); bw_ue(&w, g->H - 1);
 	bw_u(&w, 1, 1);                      /* frame_mbs_only_flag */
-	bw_u(&w, 1, 1);                      /* direct_8x8_inference_flag */
+	bw_u(&w, 1, !g->direct4x4);          /* direct_8x8_inference_flag */
 	const int any_crop = g->crop_bottom > 0 || g->crop_left > 0 || g->crop_right > 0 || g->crop_top > 0;
 	bw_u(&w, 1, any_crop);
 	if (any_crop) { bw_ue(&w, g->crop_left / 2); bw_ue(&w, g->crop_right / 2); bw_ue(&w, g->crop_top / 2); bw_ue(&w, g->crop_bottom / 2); }
@@ -248,6 +251,7 @@ static void gen_choose_mb(GenState *g, SliceCtx *s, MbSyn *m, int allow_skip) {
 		else { base[l][0] = g->drift[0] * (l ? -1 : 1); base[l][1] = g->drift[1] * (l ? -1 : 1); }
 	}
 	int no_sub8 = 1, direct16 = 0;
+	const int infer8 = !g->direct4x4;
 	if (st == SLICE_P) {
 		int r = rnd(g, 100);
 		m->mb_type = r < 35 ? 0 : r < 50 ? 1 : r < 65 ? 2 : 3;
@@ -264,7 +268,7 @@ static void gen_choose_mb(GenState *g, SliceCtx *s, MbSyn *m, int allow_skip) {
 		}
 	} else {
 		int r = rnd(g, 100);
-		if (r < 15) { m->mb_type = 0; direct16 = 1; }
+		if (r < 15) { m->mb_type = 0; direct16 = 1; if (!infer8) no_sub8 = 0; }   /* 7.3.5: B_Direct_16x16 may use the 8x8 transform only with direct_8x8_inference_flag */
 		else if (r < 45) m->mb_type = 1 + rnd(g, 3);
 		else if (r < 75) m->mb_type = 4 + rnd(g, 18);
 		else m->mb_type = 22;
@@ -280,7 +284,7 @@ static void gen_choose_mb(GenState *g, SliceCtx *s, MbSyn *m, int allow_skip) {
 			for (int i = 0; i < 4; i++) {
 				int t = rnd(g, 100) < 25 ? 0 : 1 + rnd(g, 12);
 				m->sub_type[i] = t;
-				if (t == 0) { /* direct_8x8_inference_flag = 1 in our SPS: no_sub8 unaffected */ }
+				if (t == 0) { if (!infer8) no_sub8 = 0; }
 				else if (sx_b_sub_shape[t]) no_sub8 = 0;
 				int sh = sx_b_sub_shape[t], x0 = (i & 1) * 2, y0 = (i >> 1) * 2;
 				for (int l = 0; l < 2; l++) {
@@ -475,7 +479,7 @@ static int encode_picture(GenState *g, ByteBuf *out, const PicPlan *pp, int idr_
 		s->w_mbs = g->W; s->h_mbs = g->H;
 		s->slice_type = st; s->slice_id = sl + 1; s->slice_idx = sl;
 		s->num_ref[0] = num_ref[0]; s->num_ref[1] = num_ref[1];
-		s->direct_spatial = direct_spatial; s->direct_8x8_inference = 1; s->transform_8x8_mode = g->t8x8_mode;
+		s->direct_spatial = direct_spatial; s->direct_8x8_inference = !g->direct4x4; s->transform_8x8_mode = g->t8x8_mode;
 		s->qp = slice_qp; s->deblock_idc = idc; s->cur_poc = pp->poc;
 		s->mbi = g->mbi; s->recs = cp->recs; s->coefs = g->pool; s->coef_cap = (uint32_t)nmb * 408; s->n_coefs = 0;
 		memset(s->ref_slot, -1, sizeof(s->ref_slot));
@@ -559,6 +563,7 @@ int main(int argc, char **argv) {
 	g->intra_pct = argi(argc, argv, "--intra-pct", 10);
 	g->skip_pct = argi(argc, argv, "--skip-pct", 15);
 	g->crop_left = argi(argc, argv, "--crop-left", 0); g->crop_right = argi(argc, argv, "--crop-right", 0); g->crop_top = argi(argc, argv, "--crop-top", 0);
+	g->direct4x4 = argf(argc, argv, "--direct4x4"); g->nonref_p = argf(argc, argv, "--nonref-p"); g->extra_nals = argf(argc, argv, "--extra-nals");
 	g->bref = argf(argc, argv, "--bref");
 	g->mixed = argf(argc, argv, "--mixed-slices"); g->ps_update = argf(argc, argv, "--ps-update");
 	g->dpb_mode = argf(argc, argv, "--dpb"); g->mmco5 = argf(argc, argv, "--mmco5"); g->poc_type = argi(argc, argv, "--poc-type", 0);
@@ -586,10 +591,17 @@ int main(int argc, char **argv) {
 			continue;
 		}
 		if (g->ps_update && rnd(g, 4) == 0) { if (rnd(g, 3) == 0) write_sps(g, &out); for (int id = 0; id < 3; id++) write_pps(g, &out, id, g->qp0); }
+		if (g->extra_nals) {
+			if (rnd(g, 2)) { uint8_t aud[1] = {(uint8_t)(rnd(g, 3) << 5 | 0x10)}; e264_emit_nal(&out, 0, 9, aud, 1); }
+			if (rnd(g, 3) == 0) { uint8_t sei[40]; int n = 2 + rnd(g, 30); sei[0] = 5; sei[1] = (uint8_t)n; for (int i = 0; i < n; i++) sei[2 + i] = (uint8_t)rnd(g, 256); sei[2 + n] = 0x80; e264_emit_nal(&out, 0, 6, sei, 3 + n); }
+			if (rnd(g, 4) == 0) { uint8_t fil[24]; int n = 1 + rnd(g, 20); for (int i = 0; i < n; i++) fil[i] = 0xff; fil[n] = 0x80; e264_emit_nal(&out, 0, 12, fil, n + 1); }
+		}
 		if (g->gop == 1) {
-			PicPlan p = {0, 0, 1, frame_num, disp * 2};
+			const int is_ref = !(g->nonref_p && g->poc_type == 0 && !g->dpb_mode && rnd(g, 3) == 0);
+			PicPlan p = {0, 0, is_ref, frame_num, disp * 2};
 			if (encode_picture(g, &out, &p, 0)) { frame_num = 0; disp = 0; }
-			frame_num++; disp++; since_idr++; k++;
+			if (is_ref) frame_num++;
+			disp++; since_idr++; k++;
 			continue;
 		}
 		/* IPB: next anchor P at display disp+2 (or fewer if the sequence ends), then the B pictures before it */
