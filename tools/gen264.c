@@ -611,7 +611,12 @@ int main(int argc, char **argv) {
 		PicPlan p = {0, 0, 1, frame_num, (disp + nb) * 2};
 		encode_picture(g, &out, &p, 0);
 		frame_num++; k++;
-		for (int b = 0; b < nb; b++) { PicPlan q = {1, 0, g->bref && b == 0 && nb == 2, frame_num, (disp + b) * 2}; encode_picture(g, &out, &q, 0); if (q.is_ref) frame_num++; k++; }
+		for (int b = 0; b < nb; b++) {
+			int used = 0, nshort = 0;
+			for (int i = 0; i < E264_MAX_SLOTS; i++) if (g->dpb[i].used) { used++; nshort += !g->dpb[i].is_long; }
+			const int can_ref = used < g->refs || nshort > 0;   /* the sliding window needs a short-term picture to drop */
+			PicPlan q = {1, 0, g->bref && b == 0 && nb == 2 && can_ref, frame_num, (disp + b) * 2}; encode_picture(g, &out, &q, 0); if (q.is_ref) frame_num++; k++;
+		}
 		disp += nb + 1; since_idr += nb + 1;
 	}
 	FILE *f = fopen(outp, "wb");
