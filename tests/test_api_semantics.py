@@ -1,0 +1,85 @@
+"""API behaviour beyond the plain decode loop, compared between the reference and our host code (CPU backend):
+borrowed frames (edge264_get_frame(borrow=1) / edge264_return_frame, reference edge264.c:365-414), flush in the middle
+of a stream (edge264.c:261-270), and the sequence of return codes of edge264_decode_NAL."""
+import ctypes, errno, os
+import pytest
+from conftest import STREAMS, make_stream, have
+from edge264_b200 import load, Edge264Frame, _frame_bytes
+
+
+def decode_borrowing(data, backend, hold, flush_at=None):
+    lib = load(backend)
+    buf = ctypes.create_string_buffer(data, len(data) + 64)
+    base = ctypes.addressof(buf); end = base + len(data)
+    dec = lib.edge264_alloc(0, None, None, 0, None, None, None)
+    assert dec
+    nal = base + 3 + (1 if data[2] == 0 else 0)
+    held, out, codes, f, n_nal, drained = [], [], [], Edge264Frame(), 0, False
+    while True:
+        sc = lib.edge264_find_start_code(nal, end, 0) if nal < end else end
+        before = len(out) + len(held)
+        res = lib.edge264_decode_NAL(dec, nal, sc, None, None)
+        if nal >= end:
+            drained = True
+        while lib.edge264_get_frame(dec, ctypes.byref(f), 1) == 0:
+            # remember where the samples live and what they look like now; they must be unchanged when we give them back
+            held.append((f.FrameId, f.width_Y, f.height_Y, _frame_bytes(f), f.return_arg, Edge264Frame.from_buffer_copy(bytes(f))))
+            while len(held) > hold:
+                fid, w, h, snap, arg, fr = held.pop(0)
+                assert _frame_bytes(fr) == snap, "a borrowed frame changed while it was held"
+                out.append((fid, w, h, snap))
+                lib.edge264_return_frame(dec, arg)
+        if res == errno.ENOBUFS:
+            if len(out) + len(held) == before:
+                if not held:
+                    break
+                fid, w, h, snap, arg, fr = held.pop(0)      # the decoder is out of frame buffers: hand one back
+                assert _frame_bytes(fr) == snap
+                out.append((fid, w, h, snap)); lib.edge264_return_frame(dec, arg)
+            continue
+        codes.append(res)
+        n_nal += 1
+        if flush_at is not None and n_nal == flush_at:
+            for fid, w, h, snap, arg, fr in held:
+                out.append((fid, w, h, snap)); lib.edge264_return_frame(dec, arg)
+            held = []
+            lib.edge264_flush(dec)
+        if res in (errno.ENOTSUP, errno.EBADMSG):
+            res = 0
+        nal = sc + 3 if sc + 3 < end else end
+        if res != 0 or drained:
+            break
+    for fid, w, h, snap, arg, fr in held:
+        assert _frame_bytes(fr) == snap
+        out.append((fid, w, h, snap)); lib.edge264_return_frame(dec, arg)
+    d = ctypes.c_void_p(dec)
+    lib.edge264_free(ctypes.byref(d))
+    return out, codes
+
+
+CASES = [STREAMS[6], STREAMS[8], STREAMS[9]]   # I P B B streams: frames leave out of decoding order
+
+
+@pytest.mark.parametrize("name,w,h,args", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("hold", [1, 3])
+def test_borrowed_frames_match_reference(workdir, name, w, h, args, hold):
+    data = open(make_stream(workdir, name, w, h, args), "rb").read()
+    plain, _ = decode_borrowing(data, "port", 0)
+    ours, codes = decode_borrowing(data, "port", hold)
+    assert [(f[0], f[3]) for f in ours] == [(f[0], f[3]) for f in plain], "holding frames changed the output"
+    if have("ref"):
+        ref, rcodes = decode_borrowing(data, "ref", hold)
+        assert [(f[0], f[3]) for f in ref] == [(f[0], f[3]) for f in ours]
+        assert rcodes == codes, "edge264_decode_NAL return codes differ from the reference's"
+
+
+def test_flush_mid_stream_matches_reference(workdir):
+    name, w, h, args = STREAMS[6]
+    data = open(make_stream(workdir, name, w, h, args), "rb").read()
+    if not have("ref"):
+        pytest.skip("reference library not built")
+    for at in (7, 12):
+        ours, codes = decode_borrowing(data, "port", 0, flush_at=at)
+        ref, rcodes = decode_borrowing(data, "ref", 0, flush_at=at)
+        assert rcodes == codes
+        assert [(f[0], f[3]) for f in ref] == [(f[0], f[3]) for f in ours]
