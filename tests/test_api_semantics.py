@@ -83,3 +83,42 @@ def test_flush_mid_stream_matches_reference(workdir):
         ref, rcodes = decode_borrowing(data, "ref", 0, flush_at=at)
         assert rcodes == codes
         assert [(f[0], f[3]) for f in ref] == [(f[0], f[3]) for f in ours]
+
+
+UNREF = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.c_void_p)
+
+
+def decode_with_unref(data, backend):
+    """Every edge264_decode_NAL gets an unref callback; returns [(return code, callback calls as (ret, arg))] per NAL."""
+    lib = load(backend)
+    buf = ctypes.create_string_buffer(data, len(data) + 64)
+    base = ctypes.addressof(buf); end = base + len(data)
+    dec = lib.edge264_alloc(0, None, None, 0, None, None, None)
+    nal = base + 3 + (1 if data[2] == 0 else 0)
+    calls, log, f, k = [], [], Edge264Frame(), 0
+    cb = UNREF(lambda ret, arg: calls.append((ret, arg)))
+    while nal < end:
+        sc = lib.edge264_find_start_code(nal, end, 0)
+        k += 1
+        n0 = len(calls)
+        res = lib.edge264_decode_NAL(dec, nal, sc, cb, ctypes.c_void_p(k))
+        while lib.edge264_get_frame(dec, ctypes.byref(f), 0) == 0:
+            pass
+        if res == errno.ENOBUFS:
+            k -= 1
+            continue
+        log.append((res, calls[n0:]))
+        nal = sc + 3 if sc + 3 < end else end
+    d = ctypes.c_void_p(dec)
+    lib.edge264_free(ctypes.byref(d))
+    return log
+
+
+def test_unref_callback_matches_reference(workdir):
+    """n_threads = 0: the reference calls unref_cb(ret, arg) exactly once before edge264_decode_NAL returns, for slices and
+    for every other NAL (edge264.c:356-357, edge264_headers.c:497-498)."""
+    if not have("ref"):
+        pytest.skip("reference library not built")
+    for name, w, h, args in (STREAMS[2], STREAMS[6]):
+        data = open(make_stream(workdir, name, w, h, args), "rb").read()
+        assert decode_with_unref(data, "port") == decode_with_unref(data, "ref")
