@@ -144,13 +144,14 @@ static int build_tensor_maps(E264bDevice *c) {
 	const E264PicDesc *g = &c->g;
 	const int W = g->width_mbs * 16, H = g->height_mbs * 16;
 	if (W < 48 || H < 32 || (g->stride_y & 15) || (g->stride_c & 15) || (g->plane_y & 15) || (g->frame_bytes & 15)) return 0;
-	static EncodeTiledFn enc = NULL; static bool tried = false;
-	if (!tried) {
-		tried = true;
+	/* resolved once per process; decoders are created from many threads at once (one per stream), so the lookup is
+	 * serialised — a thread must never see "tried" without the pointer and silently lose the TMA path */
+	static EncodeTiledFn enc = NULL; static std::once_flag enc_once;
+	std::call_once(enc_once, [] {
 		void *fn = NULL; cudaDriverEntryPointQueryResult q;
 		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) enc = (EncodeTiledFn)fn;
 		else { cudaGetLastError(); fprintf(stderr, "edge264_b200: cuTensorMapEncodeTiled unavailable, windows fall back to gathered loads\n"); }
-	}
+	});
 	if (!enc) return 0;
 	static const cuuint32_t lrows[3] = {21, 13, 9}, crows[3] = {9, 5, 3};
 	/* six rank-3 maps (x, y, frame slot) serve every reference of every picture: few enough to stay in the TMA
