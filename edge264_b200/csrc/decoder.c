@@ -654,6 +654,44 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 			poc = top < bot ? top : bot; poc_top = top;
 		} else poc = poc_top = frame_num_abs * 2 + (nal_ref_idc != 0) - 1;
 
+		/* 8.2.5.2 gaps in frame_num (a reference picture was lost): like the reference (headers.c:1095-1139) insert
+		 * "non-existing" short-term frames for the missing numbers — they take FrameIds and list positions and push
+		 * older pictures out through the sliding window, which keeps the reference indices of the surviving pictures
+		 * what the encoder meant.  Their samples are undefined in the reference (never-written buffers); ours are
+		 * cleared. */
+		int gap_frames = 0;
+		if (!idr && prev >= 0 && frame_num_abs - prev > 1) {
+			int nlong = 0, nshort = 0;
+			for (int i = 0; i < d->n_slots; i++) if (d->pics[i].in_use) { nlong += d->pics[i].ref == 2; nshort += d->pics[i].ref == 1; }
+			int room = s->max_num_ref_frames - nlong;
+			gap_frames = frame_num_abs - prev - 1 < room ? frame_num_abs - prev - 1 : room;
+			if (gap_frames < 0) gap_frames = 0;
+			for (; gap_frames + nshort > room && nshort > 0; nshort--) {
+				int old = -1;
+				for (int i = 0; i < d->n_slots; i++) if (d->pics[i].in_use && d->pics[i].ref == 1 && (old < 0 || d->pics[i].frame_num < d->pics[old].frame_num)) old = i;
+				d->pics[old].ref = 0; slot_release_if_unused(d, old);
+			}
+			for (int fn = frame_num_abs - gap_frames; fn < frame_num_abs; fn++) {
+				int sl = find_free_slot(d);
+				while (sl < 0 && bump_frame(d, -1)) sl = find_free_slot(d);
+				if (sl < 0) { d->next_uid++; continue; }   /* no room even after bumping: keep at least the FrameId numbering */
+				Pic *np = &d->pics[sl];
+				memset(np, 0, sizeof(*np));
+				np->in_use = 1; np->ref = 1; np->nonexisting = 1; np->frame_num = fn; np->uid = d->next_uid++; np->host_buf = -1;
+				int npoc = 0;
+				if (s->poc_type == 2) npoc = fn * 2;
+				else if (s->poc_type == 1 && s->num_ref_frames_in_poc_cycle > 0) {
+					int tot = 0, part = 0, in = fn % s->num_ref_frames_in_poc_cycle;
+					for (int i = 0; i < s->num_ref_frames_in_poc_cycle; i++) { tot += s->offset_for_ref_frame[i]; if (i < in) part += s->offset_for_ref_frame[i]; }
+					npoc = (fn / s->num_ref_frames_in_poc_cycle) * tot + part;   /* as the reference computes it (headers.c:1133-1139) */
+				}
+				np->poc = np->poc_dec = np->poc_top = np->poc_top_dec = npoc;
+				for (int i = 0; i < E264_MAX_SLOTS; i++) np->slot_uid[i] = -1;
+				if (d->be->fill_slot) d->be->fill_slot(d->be_ctx, sl, 0, 0);
+			}
+			d->prev_ref_frame_num = frame_num_abs - 1;   /* the last inserted frame is the previous reference frame now (headers.c:1131) */
+		}
+
 		int slot = find_free_slot(d);
 		if (slot < 0) {   /* DPB invariant broken (stream exceeds its own limits): drop the oldest output-pending picture */
 			if (!bump_frame(d, -1)) return EBADMSG;
@@ -667,12 +705,13 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 			int q = d->q_prev_ref_frame_num;
 			int qfn = q + 1 + (((idr ? 0 : h->frame_num) - q - 1) & mask);
 			int gap = qfn - q;
-			if (gap > 1) {
+			if (gap > 1 && !gap_frames) {   /* a real gap has just been given its frames (and FrameIds) above */
 				int nlong = 0;
 				for (int i = 0; i < d->n_slots; i++) if (d->pics[i].in_use && d->pics[i].ref == 2) nlong++;
 				int room = s->max_num_ref_frames - nlong;
 				d->next_uid += (gap - 1 < room ? gap - 1 : room) > 0 ? (gap - 1 < room ? gap - 1 : room) : 0;
 			}
+			if (gap > 1) d->q_prev_ref_frame_num = qfn - 1;
 			d->q_cur_frame_num = qfn;
 		}
 		cp->in_use = 1; cp->frame_num = frame_num_abs; cp->poc = cp->poc_dec = poc; cp->poc_top = cp->poc_top_dec = poc_top; cp->uid = d->next_uid++; cp->host_buf = hbuf;

@@ -122,3 +122,40 @@ def test_unref_callback_matches_reference(workdir):
     for name, w, h, args in (STREAMS[2], STREAMS[6]):
         data = open(make_stream(workdir, name, w, h, args), "rb").read()
         assert decode_with_unref(data, "port") == decode_with_unref(data, "ref")
+
+
+def _split_nals(b):
+    idx, i = [], 0
+    while True:
+        j = b.find(b"\x00\x00\x01", i)
+        if j < 0:
+            break
+        idx.append(j); i = j + 3
+    return [b[idx[k]:(idx[k + 1] if k + 1 < len(idx) else len(b))] for k in range(len(idx))]
+
+
+@pytest.mark.parametrize("case", [("-W 3 -H 2 -n 12 -s 90292 --gop IPB --refs 5 --idr 17 --deblock 0 --wp 1", [8]),
+                                  ("-W 3 -H 3 -n 10 -s 31 --gop IP --refs 3 --deblock 0", [5]),
+                                  ("-W 2 -H 3 -n 30 -s 90293 --gop IPB --refs 5 --idr 9 --deblock 0 --wp 2", [24, 34, 44])],
+                         ids=["ipb_one_anchor", "ip_one_picture", "ipb_three_anchors"])
+def test_lost_reference_pictures_follow_the_reference(workdir, case):
+    """A lost reference picture is a gap in frame_num (8.2.5.2): like the reference (edge264_headers.c:1095-1139) we insert
+    non-existing frames, so the number of output frames, their order and their FrameIds must match.  Samples of pictures
+    predicted from a non-existing frame are undefined in the reference (never-written buffers) and are not compared,
+    except that everything output before the loss must be identical."""
+    import subprocess
+    from conftest import ROOT
+    from edge264_b200 import decode_bytes
+    if not have("ref"):
+        pytest.skip("reference library not built")
+    args, drop = case
+    path = os.path.join(workdir, "gap_%d.264" % abs(hash(args)))
+    subprocess.run([os.path.join(ROOT, "tools", "gen264"), "-o", path] + args.split(), check=True, stderr=subprocess.DEVNULL)
+    nals = _split_nals(open(path, "rb").read())
+    data = b"".join(n for k, n in enumerate(nals) if k not in drop)
+    ref, _ = decode_bytes(data, "ref")
+    ours, _ = decode_bytes(data, "port")
+    assert [(f[0], f[1], f[2]) for f in ours] == [(f[0], f[1], f[2]) for f in ref]
+    intact, _ = decode_bytes(b"".join(nals[:min(drop)]), "ref")
+    n_before = max(0, len(intact) - 3)     # pictures complete and output-ordered before the first loss
+    assert [f[3] for f in ours[:n_before]] == [f[3] for f in ref[:n_before]]
