@@ -159,3 +159,64 @@ def test_lost_reference_pictures_follow_the_reference(workdir, case):
     intact, _ = decode_bytes(b"".join(nals[:min(drop)]), "ref")
     n_before = max(0, len(intact) - 3)     # pictures complete and output-ordered before the first loss
     assert [f[3] for f in ours[:n_before]] == [f[3] for f in ref[:n_before]]
+
+
+ALLOC = ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint, ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint, ctypes.c_int, ctypes.c_void_p)
+FREE = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+
+
+def decode_with_allocator(data, backend):
+    """Decode with application-provided frame memory (edge264.h: Edge264AllocCb / Edge264FreeCb); returns the frames
+    and the allocator traffic [(samples_size, mbs_size)], number of frees."""
+    lib = load(backend)
+    libc = ctypes.CDLL(None)
+    libc.malloc.restype = ctypes.c_void_p; libc.malloc.argtypes = [ctypes.c_size_t]; libc.free.argtypes = [ctypes.c_void_p]
+    allocs, frees, live = [], [], set()
+
+    def on_alloc(samples, samples_size, mbs, mbs_size, err, arg):
+        a = libc.malloc(samples_size + 64); b = libc.malloc(mbs_size + 64)
+        samples[0] = a; mbs[0] = b
+        allocs.append((samples_size, mbs_size)); live.add(a)
+
+    def on_free(samples, mbs, arg):
+        frees.append(samples); live.discard(samples)
+        libc.free(samples); libc.free(mbs)
+
+    acb, fcb = ALLOC(on_alloc), FREE(on_free)
+    buf = ctypes.create_string_buffer(data, len(data) + 64)
+    base = ctypes.addressof(buf); end = base + len(data)
+    dec = lib.edge264_alloc(0, None, None, 0, acb, fcb, None)
+    assert dec
+    nal = base + 3 + (1 if data[2] == 0 else 0)
+    out, f, drained = [], Edge264Frame(), False
+    while True:
+        sc = lib.edge264_find_start_code(nal, end, 0) if nal < end else end
+        before = len(out)
+        res = lib.edge264_decode_NAL(dec, nal, sc, None, None)
+        if nal >= end:
+            drained = True
+        while lib.edge264_get_frame(dec, ctypes.byref(f), 0) == 0:
+            out.append((f.FrameId, _frame_bytes(f)))
+        if res == errno.ENOBUFS:
+            if len(out) == before:
+                break
+            continue
+        nal = sc + 3 if sc + 3 < end else end
+        if (res not in (0, errno.ENOTSUP, errno.EBADMSG)) or drained:
+            break
+    d = ctypes.c_void_p(dec)
+    lib.edge264_free(ctypes.byref(d))
+    return out, allocs, len(frees), len(live)
+
+
+def test_application_allocator_is_used_and_balanced(workdir):
+    name, w, h, args = STREAMS[6]
+    data = open(make_stream(workdir, name, w, h, args), "rb").read()
+    frames, allocs, n_free, leaked = decode_with_allocator(data, "port")
+    plain, _ = decode_borrowing(data, "port", 0)
+    assert [(f[0], f[1]) for f in frames] == [(f[0], f[3]) for f in plain]
+    assert allocs and n_free == len(allocs) and leaked == 0, "every buffer obtained from alloc_cb must go back through free_cb"
+    if have("ref"):
+        rframes, rallocs, rfree, rleak = decode_with_allocator(data, "ref")
+        assert [(f[0], f[1]) for f in rframes] == [(f[0], f[1]) for f in frames]
+        assert set(rallocs) == set(allocs), "buffer sizes requested from the application differ from the reference's"
