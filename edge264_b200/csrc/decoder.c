@@ -414,7 +414,9 @@ static int bump_all(Edge264Decoder *d) {
 	return d->outq_n ? ENOBUFS : 0;
 }
 
-static int configure_sequence(Edge264Decoder *d, const SPS *s) {
+/* keep_numbering: the frame format is unchanged and only the frame pool grows — the reference does not clear its decoder
+ * then (it compares size, crop and bit depth only, headers.c:2016-2024), so FrameId numbering and the parameter sets go on */
+static int configure_sequence(Edge264Decoder *d, const SPS *s, int keep_numbering) {
 	int w = s->width_mbs * 16, h = s->height_mbs * 16;
 	d->w_mbs = s->width_mbs; d->h_mbs = s->height_mbs;
 	d->stride_y = w; if (!(d->stride_y & 2047)) d->stride_y += 16;       /* reference headers.c:2027-2029 */
@@ -442,8 +444,7 @@ static int configure_sequence(Edge264Decoder *d, const SPS *s) {
 	o->frame_crop_offsets[0] = (int16_t)s->crop[2]; o->frame_crop_offsets[1] = (int16_t)s->crop[1];
 	o->frame_crop_offsets[2] = (int16_t)s->crop[3]; o->frame_crop_offsets[3] = (int16_t)s->crop[0];
 	d->configured = 1;
-	d->q_prev_ref_frame_num = -1;
-	d->prev_ref_frame_num = -1; d->prev_poc_msb = d->prev_poc_lsb = 0;
+	if (!keep_numbering) { d->q_prev_ref_frame_num = -1; d->prev_ref_frame_num = -1; d->prev_poc_msb = d->prev_poc_lsb = 0; }
 	return 0;
 }
 
@@ -881,13 +882,13 @@ int edge264_decode_NAL(Edge264Decoder *d, const uint8_t *buf, const uint8_t *end
 	case 7: {
 		SPS s; ret = parse_sps(d, &b, &s);
 		if (ret == 0) {
-			int same = d->configured && d->sps.width_mbs == s.width_mbs && d->sps.height_mbs == s.height_mbs &&
-			           !memcmp(d->sps.crop, s.crop, sizeof(s.crop)) && d->sps.max_num_ref_frames == s.max_num_ref_frames;
-			if (!same) {
+			int same_format = d->configured && d->sps.width_mbs == s.width_mbs && d->sps.height_mbs == s.height_mbs && !memcmp(d->sps.crop, s.crop, sizeof(s.crop));
+			int fits = same_format && s.max_num_ref_frames + 2 <= d->n_slots;
+			if (!fits) {
 				if (d->configured && bump_all(d)) return ENOBUFS;   /* frame format change: drain first (headers.c:2005-2007) */
-				ret = configure_sequence(d, &s);
+				ret = configure_sequence(d, &s, same_format);
 				if (ret) return ret;
-				memset(d->pps, 0, sizeof(d->pps));   /* a format change clears the decoder, PPSs included (reference clear_decoder, headers.c:133-141) */
+				if (!same_format) memset(d->pps, 0, sizeof(d->pps));   /* a format change clears the decoder, PPSs included (reference clear_decoder, headers.c:133-141) */
 			}
 			d->sps = s;
 		}

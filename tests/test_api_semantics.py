@@ -220,3 +220,25 @@ def test_application_allocator_is_used_and_balanced(workdir):
         rframes, rallocs, rfree, rleak = decode_with_allocator(data, "ref")
         assert [(f[0], f[1]) for f in rframes] == [(f[0], f[1]) for f in frames]
         assert set(rallocs) == set(allocs), "buffer sizes requested from the application differ from the reference's"
+
+
+def test_sequence_changes_follow_the_reference(workdir):
+    """Several coded video sequences in one stream: new sizes and crops (the reference clears its decoder), and a change of
+    max_num_ref_frames alone (it does not: FrameId numbering and parameter sets continue, edge264_headers.c:2016-2024)."""
+    import subprocess
+    from conftest import ROOT, md5_frames
+    from edge264_b200 import decode_bytes
+    if not have("ref"):
+        pytest.skip("reference library not built")
+    parts = []
+    for k, a in enumerate(["-W 9 -H 7 -n 7 -s 13 --gop IPB --deblock 0", "-W 6 -H 5 -n 6 -s 14 --gop IP --refs 3 --deblock 0 --cavlc",
+                           "-W 9 -H 7 -n 5 -s 15 --gop IPB --refs 4 --deblock 0", "-W 9 -H 7 -n 7 -s 13 --gop IPB --deblock 0",
+                           "-W 9 -H 7 -n 4 -s 16 --gop IP --refs 1 --crop-bottom 4 --deblock 0"]):
+        p = os.path.join(workdir, "seq_%d.264" % k)
+        subprocess.run([os.path.join(ROOT, "tools", "gen264"), "-o", p] + a.split(), check=True, stderr=subprocess.DEVNULL)
+        parts.append(open(p, "rb").read())
+    data = b"".join(parts)
+    ref, rc = decode_bytes(data, "ref")
+    ours, oc = decode_bytes(data, "port")
+    assert [(f[0], f[1], f[2]) for f in ours] == [(f[0], f[1], f[2]) for f in ref]
+    assert md5_frames(ours) == md5_frames(ref) and oc == rc
