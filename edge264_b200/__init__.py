@@ -3,16 +3,13 @@
 The product is the shared library (C ABI identical to the reference's edge264.h, see include/).
 This module only mirrors that interface for tests and benchmarks: same function names, same
 argument meaning, same errno return codes (reference edge264.h:64-70, README.md:159-240).
-`backend="port"` / `"ref"` load the CPU checkers (oracle/) instead — tests only.
+Only the product library is known here; the CPU checkers (oracle/) are bound by tests/checkers.py
+through the same `bind()`.
 """
 import ctypes, errno, os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_LIBS = {
-    "gpu": os.path.join(ROOT, "edge264_b200", "libedge264_b200.so"),
-    "port": os.path.join(ROOT, "oracle", "liboracle_dec.so"),
-    "ref": os.path.join(ROOT, "oracle", "_ref", "libedge264_ref.so"),
-}
+LIB_PATH = os.path.join(ROOT, "edge264_b200", "libedge264_b200.so")
 
 
 class Edge264Frame(ctypes.Structure):
@@ -27,11 +24,15 @@ class Edge264Frame(ctypes.Structure):
 _loaded = {}
 
 
-def load(backend="gpu"):
-    """Load one implementation of the API.  The GPU library is mandatory for backend='gpu': there is no fallback."""
-    if backend in _loaded:
-        return _loaded[backend]
-    path = _LIBS[backend]
+def load():
+    """The product library (CUDA backend).  Mandatory: there is no fallback."""
+    return bind(LIB_PATH)
+
+
+def bind(path):
+    """ctypes prototypes of the seven edge264 entry points for any library that implements them."""
+    if path in _loaded:
+        return _loaded[path]
     if not os.path.exists(path):
         raise OSError(f"{path} is missing — build it with `python __graft_entry__.py build`")
     lib = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
@@ -44,7 +45,7 @@ def load(backend="gpu"):
     lib.edge264_decode_NAL.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.edge264_get_frame.argtypes = [ctypes.c_void_p, ctypes.POINTER(Edge264Frame), ctypes.c_int]
     lib.edge264_return_frame.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-    _loaded[backend] = lib
+    _loaded[path] = lib
     return lib
 
 
@@ -58,15 +59,17 @@ def _frame_bytes(f):
     return bytes(out)
 
 
-def decode_bytes(data, backend="gpu", n_threads=0):
+def decode_bytes(data, lib=None, n_threads=0):
     """Decode an Annex-B byte string with the README loop (reference README.md:117-156).
     Returns (frames, return_codes) where frames = [(FrameId, width, height, i420_bytes), ...]."""
-    lib = load(backend)
+    gpu = lib is None
+    if gpu:
+        lib = load()
     buf = ctypes.create_string_buffer(data, len(data) + 64)
     base = ctypes.addressof(buf); end = base + len(data)
     dec = lib.edge264_alloc(n_threads, None, None, 0, None, None, None)
     if not dec:
-        raise RuntimeError("edge264_alloc failed" + (" (no CUDA device: the GPU backend has no CPU fallback)" if backend == "gpu" else ""))
+        raise RuntimeError("edge264_alloc failed" + (" (no CUDA device: the GPU backend has no CPU fallback)" if gpu else ""))
     nal = base + 3 + (1 if data[2] == 0 else 0)
     frames, codes, f = [], [], Edge264Frame()
     drained = False
@@ -93,7 +96,7 @@ def decode_bytes(data, backend="gpu", n_threads=0):
     return frames, codes
 
 
-def decode_file_hashes(path, backend="gpu"):
+def decode_file_hashes(path, lib=None):
     import hashlib
-    frames, _ = decode_bytes(open(path, "rb").read(), backend)
+    frames, _ = decode_bytes(open(path, "rb").read(), lib)
     return [hashlib.md5(fr[3]).hexdigest() for fr in frames]

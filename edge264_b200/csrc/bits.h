@@ -59,6 +59,10 @@ static inline uint32_t br_ue(BitReader *b) {
 	b->pos += lz + 1;
 	return (uint32_t)(((uint64_t)1 << lz) - 1 + br_u(b, lz));
 }
+/* bounded ue(v) for header fields that land in an int: values above `cap` (codes up to 2^32-2 exist) are clamped to
+ * `cap`, which every caller chooses just above the field's legal range so that its range check fails — the
+ * reference bounds every such read (get_ue16 / get_ue32 with a maximum, edge264_bitstream.c:150-203) */
+static inline int br_ue_i(BitReader *b, int cap) { uint32_t v = br_ue(b); return v > (uint32_t)cap ? cap : (int)v; }
 static inline int32_t br_se(BitReader *b) {
 	uint32_t k = br_ue(b);
 	return (k & 1) ? (int32_t)((k + 1) >> 1) : -(int32_t)(k >> 1);

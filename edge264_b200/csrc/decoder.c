@@ -94,7 +94,7 @@ static void parse_scaling_lists(BitReader *b, uint8_t w4[6][16], uint8_t w8[2][6
 }
 
 static void skip_hrd(BitReader *b) {
-	int cpb_cnt = br_ue(b) + 1;
+	int cpb_cnt = br_ue_i(b, 32) + 1;
 	br_u(b, 8);
 	for (int i = 0; i < cpb_cnt && i < 32; i++) { br_ue(b); br_ue(b); br_u1(b); }
 	br_u(b, 20);
@@ -108,7 +108,7 @@ static int parse_sps(Edge264Decoder *d, BitReader *b, SPS *out) {
 	br_ue(b);   /* seq_parameter_set_id: ignored like the reference (headers.c:1851) */
 	s.log2_max_poc_lsb = 16;
 	if (s.profile_idc != 66 && s.profile_idc != 77 && s.profile_idc != 88) {
-		int chroma_format_idc = br_ue(b);
+		int chroma_format_idc = br_ue_i(b, 4);
 		if (chroma_format_idc != 1) { ret = ENOTSUP; if (chroma_format_idc == 3) br_u1(b); }
 		if (br_ue(b) != 0) ret = ENOTSUP;   /* bit_depth_luma_minus8 */
 		if (br_ue(b) != 0) ret = ENOTSUP;
@@ -121,22 +121,22 @@ static int parse_sps(Edge264Decoder *d, BitReader *b, SPS *out) {
 			parse_scaling_lists(b, s.sl4x4, s.sl8x8, 1);
 		}
 	}
-	s.log2_max_frame_num = br_ue(b) + 4;
-	s.poc_type = br_ue(b);
+	s.log2_max_frame_num = br_ue_i(b, 13) + 4;
+	s.poc_type = br_ue_i(b, 3);
 	if (s.log2_max_frame_num > 16 || s.poc_type > 2) return EBADMSG;
-	if (s.poc_type == 0) { s.log2_max_poc_lsb = br_ue(b) + 4; if (s.log2_max_poc_lsb > 16) return EBADMSG; }
+	if (s.poc_type == 0) { s.log2_max_poc_lsb = br_ue_i(b, 13) + 4; if (s.log2_max_poc_lsb > 16) return EBADMSG; }
 	else if (s.poc_type == 1) {
 		s.delta_pic_order_always_zero_flag = br_u1(b);
 		s.offset_for_non_ref_pic = br_se(b);
 		s.offset_for_top_to_bottom_field = br_se(b);
-		s.num_ref_frames_in_poc_cycle = br_ue(b);
+		s.num_ref_frames_in_poc_cycle = br_ue_i(b, 256);
 		if (s.num_ref_frames_in_poc_cycle > 255) return EBADMSG;
 		for (int i = 0; i < s.num_ref_frames_in_poc_cycle; i++) s.offset_for_ref_frame[i] = br_se(b);
 	}
-	int max_num_ref_frames = br_ue(b);
+	int max_num_ref_frames = br_ue_i(b, 17);
 	s.gaps_allowed = br_u1(b);
-	s.width_mbs = br_ue(b) + 1;
-	s.height_mbs = br_ue(b) + 1;
+	s.width_mbs = br_ue_i(b, 4096) + 1;
+	s.height_mbs = br_ue_i(b, 4096) + 1;
 	if (s.width_mbs > 1023 || s.height_mbs > 1055 || max_num_ref_frames > 16) return EBADMSG;
 	int frame_mbs_only = br_u1(b);
 	if (!frame_mbs_only) { ret = ENOTSUP; br_u1(b); }
@@ -152,10 +152,10 @@ static int parse_sps(Edge264Decoder *d, BitReader *b, SPS *out) {
 	if (br_u1(b)) {   /* frame_cropping_flag; 4:2:0 frame: units of 2 luma samples */
 		/* out-of-range offsets are clamped, not rejected, like the reference's bounded get_ue16 (headers.c:1975-1983) */
 		int limx = s.width_mbs * 8 - 1, limy = s.height_mbs * 8 - 1;
-		int v = (int)br_ue(b); s.crop[0] = (v < 0 || v > limx ? limx : v) * 2;
-		v = (int)br_ue(b); s.crop[1] = (v < 0 || v > limx - s.crop[0] / 2 ? limx - s.crop[0] / 2 : v) * 2;
-		v = (int)br_ue(b); s.crop[2] = (v < 0 || v > limy ? limy : v) * 2;
-		v = (int)br_ue(b); s.crop[3] = (v < 0 || v > limy - s.crop[2] / 2 ? limy - s.crop[2] / 2 : v) * 2;
+		int v = br_ue_i(b, 1 << 20); s.crop[0] = (v < 0 || v > limx ? limx : v) * 2;
+		v = br_ue_i(b, 1 << 20); s.crop[1] = (v < 0 || v > limx - s.crop[0] / 2 ? limx - s.crop[0] / 2 : v) * 2;
+		v = br_ue_i(b, 1 << 20); s.crop[2] = (v < 0 || v > limy ? limy : v) * 2;
+		v = br_ue_i(b, 1 << 20); s.crop[3] = (v < 0 || v > limy - s.crop[2] / 2 ? limy - s.crop[2] / 2 : v) * 2;
 	}
 	if (br_u1(b)) {   /* vui_parameters (E.1.1): walked only to reach bitstream_restriction */
 		if (br_u1(b)) { if (br_u(b, 8) == 255) { br_u(b, 16); br_u(b, 16); } }
@@ -169,7 +169,7 @@ static int parse_sps(Edge264Decoder *d, BitReader *b, SPS *out) {
 		br_u1(b);   /* pic_struct_present_flag */
 		if (br_u1(b)) {
 			br_u1(b); br_ue(b); br_ue(b); br_ue(b); br_ue(b);
-			int reorder = br_ue(b), buffering = br_ue(b);
+			int reorder = br_ue_i(b, 17), buffering = br_ue_i(b, 17);
 			if (reorder > 16 || buffering > 16) return EBADMSG;
 			s.max_dec_frame_buffering = buffering > s.max_num_ref_frames ? buffering : s.max_num_ref_frames;
 			s.max_num_reorder_frames = reorder < s.max_dec_frame_buffering ? reorder : s.max_dec_frame_buffering;
@@ -191,7 +191,7 @@ static int parse_pps(Edge264Decoder *d, BitReader *b) {
 	p.entropy_coding_mode = br_u1(b);
 	p.bottom_field_pic_order_present = br_u1(b);
 	if (br_ue(b) != 0) return ENOTSUP;   /* slice groups: cannot parse further */
-	p.num_ref_idx_default[0] = br_ue(b) + 1; p.num_ref_idx_default[1] = br_ue(b) + 1;
+	p.num_ref_idx_default[0] = br_ue_i(b, 32) + 1; p.num_ref_idx_default[1] = br_ue_i(b, 32) + 1;
 	if (p.num_ref_idx_default[0] > 32 || p.num_ref_idx_default[1] > 32) return EBADMSG;
 	p.weighted_pred_flag = br_u1(b); p.weighted_bipred_idc = br_u(b, 2);
 	int q = br_se(b); if (q < -26 || q > 25) return EBADMSG;
@@ -411,7 +411,11 @@ static void apply_marking(Edge264Decoder *d) {
 static int bump_all(Edge264Decoder *d) {
 	if (d->cur >= 0) finish_picture(d);
 	while (bump_frame(d, -1));
-	return d->outq_n ? ENOBUFS : 0;
+	if (d->outq_n) return ENOBUFS;
+	/* frames the application still holds (borrowed, or handed out until the next decode_NAL) keep their buffers: a
+	 * change of format must wait for them like the reference's `to_get_frames | output_frames` test (headers.c:2005-2007) */
+	for (int i = 0; i < E264_MAX_HOSTBUFS; i++) if (d->hb[i].state == 3 && d->hb[i].borrowed) return ENOBUFS;
+	return 0;
 }
 
 /* keep_numbering: the frame format is unchanged and only the frame pool grows — the reference does not clear its decoder
@@ -456,12 +460,12 @@ static inline int clamp8(int v) { return v < -128 ? -128 : v > 127 ? 127 : v; } 
 static int parse_slice_header(Edge264Decoder *d, BitReader *b, int nal_unit_type, int nal_ref_idc, SliceHeader *h, const PPS **ppps) {
 	const SPS *s = &d->sps;
 	memset(h, 0, sizeof(*h));
-	h->first_mb = br_ue(b);
-	int st = br_ue(b);
+	h->first_mb = br_ue_i(b, 139264);   /* bounded like the reference's get_ue32(139263) (headers.c:968); anything larger fails the first_mb >= total test */
+	int st = br_ue_i(b, 10);
 	if (st > 9) return EBADMSG;
 	if (nal_unit_type == 5 || s->max_num_ref_frames == 0) st = 2;   /* reference headers.c:983 */
 	h->slice_type = st < 5 ? st : st - 5;
-	h->pps_id = br_ue(b);
+	h->pps_id = br_ue_i(b, 256);
 	if (h->slice_type > 2 || h->pps_id >= 4) return ENOTSUP;
 	const PPS *p = &d->pps[h->pps_id];
 	if (!s->valid || !p->valid) return EBADMSG;
@@ -469,7 +473,7 @@ static int parse_slice_header(Edge264Decoder *d, BitReader *b, int nal_unit_type
 	h->frame_num = br_u(b, s->log2_max_frame_num);
 	if (nal_unit_type == 5) h->frame_num = 0;
 	h->idr_pic_id = -1;
-	if (nal_unit_type == 5) h->idr_pic_id = br_ue(b);
+	if (nal_unit_type == 5) h->idr_pic_id = br_ue_i(b, 65536);
 	if (s->poc_type == 0) {
 		h->poc_lsb = br_u(b, s->log2_max_poc_lsb);
 		if (p->bottom_field_pic_order_present) h->delta_poc_bottom = br_se(b);
@@ -481,8 +485,8 @@ static int parse_slice_header(Edge264Decoder *d, BitReader *b, int nal_unit_type
 	if (h->slice_type < 2) {
 		if (h->slice_type == 1) h->direct_spatial = br_u1(b);
 		if (br_u1(b)) {
-			h->num_ref[0] = br_ue(b) + 1;
-			if (h->slice_type == 1) h->num_ref[1] = br_ue(b) + 1;
+			h->num_ref[0] = br_ue_i(b, 32) + 1;
+			if (h->slice_type == 1) h->num_ref[1] = br_ue_i(b, 32) + 1;
 		}
 		if (h->num_ref[0] > 16) h->num_ref[0] = h->num_ref[0] > 32 ? 0 : 16;
 		if (h->num_ref[1] > 16) h->num_ref[1] = h->num_ref[1] > 32 ? 0 : 16;
@@ -493,14 +497,14 @@ static int parse_slice_header(Edge264Decoder *d, BitReader *b, int nal_unit_type
 			for (;;) {
 				unsigned op = br_ue(b);
 				if (op == 3) break;
-				if (op > 5 || n >= 33) return EBADMSG;
-				h->mod[l][n].op = (uint8_t)op; h->mod[l][n].val = br_ue(b); n++;
+				if (op > 5 || n >= 32) return EBADMSG;
+				h->mod[l][n].op = (uint8_t)op; h->mod[l][n].val = (uint32_t)br_ue_i(b, 1 << 20); n++;
 			}
 			h->n_mod[l] = n;
 		}
 		int wp = h->slice_type == 0 ? p->weighted_pred_flag : p->weighted_bipred_idc;
 		if (wp == 1) {
-			h->luma_log2_wd = br_ue(b); h->chroma_log2_wd = br_ue(b);
+			h->luma_log2_wd = br_ue_i(b, 8); h->chroma_log2_wd = br_ue_i(b, 8);
 			if (h->luma_log2_wd > 7 || h->chroma_log2_wd > 7) return EBADMSG;
 			for (int l = 0; l <= h->slice_type; l++) for (int i = 0; i < h->num_ref[l]; i++) {
 				if (br_u1(b)) { h->w[l][i][0] = (int16_t)clamp8(br_se(b)); h->o[l][i][0] = (int16_t)clamp8(br_se(b)); }
@@ -520,20 +524,20 @@ static int parse_slice_header(Edge264Decoder *d, BitReader *b, int nal_unit_type
 				if (op == 0) break;
 				if (op > 6 || n >= 64) return EBADMSG;
 				h->mmco[n].op = (uint8_t)op;
-				if (op == 1 || op == 3) h->mmco[n].a = br_ue(b);
-				if (op == 2 || op == 4 || op == 6) h->mmco[n].a = br_ue(b);
-				if (op == 3) h->mmco[n].b = br_ue(b);
+				if (op == 1 || op == 3) h->mmco[n].a = (uint32_t)br_ue_i(b, 1 << 20);
+				if (op == 2 || op == 4 || op == 6) h->mmco[n].a = (uint32_t)br_ue_i(b, 1 << 20);
+				if (op == 3) h->mmco[n].b = (uint32_t)br_ue_i(b, 1 << 20);
 				n++;
 			}
 			h->n_mmco = n;
 		}
 	}
-	if (p->entropy_coding_mode && h->slice_type != 2) { h->cabac_init_idc = br_ue(b); if (h->cabac_init_idc > 2) return EBADMSG; }
+	if (p->entropy_coding_mode && h->slice_type != 2) { h->cabac_init_idc = br_ue_i(b, 3); if (h->cabac_init_idc > 2) return EBADMSG; }
 	int qd = br_se(b);
 	h->slice_qp = p->pic_init_qp + qd;
 	if (h->slice_qp < 0 || h->slice_qp > 51) return EBADMSG;
 	if (p->deblocking_filter_control_present) {
-		h->deblock_idc = br_ue(b);
+		h->deblock_idc = br_ue_i(b, 3);
 		if (h->deblock_idc > 2) return EBADMSG;
 		if (h->deblock_idc != 1) {
 			int a = br_se(b), bb = br_se(b);
@@ -595,6 +599,7 @@ static void build_ref_lists(Edge264Decoder *d, const SliceHeader *h, int lists[2
 				for (int i = 0; i < d->n_slots; i++) if (i != d->cur && d->pics[i].in_use && d->pics[i].ref == 2 && d->pics[i].long_term_idx == (int)h->mod[l][k].val) { pic = i; break; }
 			}
 			if (pic < 0) continue;
+			if (k >= h->num_ref[l] || k >= 32) break;   /* more operations than list entries: the reference stops at refIdx 32 too (headers.c:817) */
 			int buf = pic, c = k;
 			do { int sw = lists[l][c]; lists[l][c] = buf; buf = sw; } while (++c < h->num_ref[l] && c < 32 && buf != pic);
 		}

@@ -49,6 +49,7 @@ struct E264bDevice {
 	uint64_t launches, h2d_bytes, d2h_bytes;
 	int sm_count;
 	std::vector<std::pair<void *, size_t>> host_free_list;   /* pinned buffers returned by the decoder, reused by the next one */
+	std::vector<std::pair<void *, size_t>> host_live;        /* pinned buffers handed out, with their sizes */
 };
 
 /* Device contexts are pooled per process: creating pinned staging and the frame pool costs tens of
@@ -213,15 +214,23 @@ extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots
 extern "C" void *e264b_host_alloc(E264bDevice *c, size_t bytes) {
 	void *p = NULL;
 	cudaSetDevice(c->dev);
-	for (size_t i = 0; i < c->host_free_list.size(); i++) if (c->host_free_list[i].second == bytes) { p = c->host_free_list[i].first; c->host_free_list.erase(c->host_free_list.begin() + i); return p; }
-	if (cudaHostAlloc(&p, bytes + 16, cudaHostAllocDefault) != cudaSuccess) return NULL;
-	((size_t *)((uint8_t *)p + bytes))[0] = bytes;   /* size tag behind the buffer for host_free */
+	for (size_t i = 0; i < c->host_free_list.size(); i++) if (c->host_free_list[i].second == bytes) {
+		p = c->host_free_list[i].first; c->host_free_list.erase(c->host_free_list.begin() + i);
+		c->host_live.push_back(std::make_pair(p, bytes));
+		return p;
+	}
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return NULL;
+	c->host_live.push_back(std::make_pair(p, bytes));
 	return p;
 }
 extern "C" void e264b_host_free(E264bDevice *c, void *p) {
-	/* all decoder mirrors of one geometry have the same size: keep them for the next decoder */
-	size_t bytes = (size_t)c->g.frame_bytes + 64;
-	c->host_free_list.push_back(std::make_pair(p, bytes));
+	/* decoder mirrors of one geometry have the same size: keep them (with the size they were allocated with) for the next decoder */
+	for (size_t i = 0; i < c->host_live.size(); i++) if (c->host_live[i].first == p) {
+		c->host_free_list.push_back(c->host_live[i]);
+		c->host_live.erase(c->host_live.begin() + i);
+		return;
+	}
+	cudaSetDevice(c->dev); cudaFreeHost(p);   /* not ours to pool */
 }
 
 extern "C" int e264b_acquire_staging(E264bDevice *c, int slot, E264MbRec **recs, int16_t **coefs, uint32_t *cap, E264SliceRec **slices) {
@@ -242,7 +251,7 @@ static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, const E264MbRec *r
 	J.tickets = c->d_sync; J.err = c->d_sync + 3; J.flags = c->d_sync + 4;
 	J.resid = c->st[c->stage].d_resid;
 	J.rows_mode = pd->n_intra * 2 > pd->width_mbs * pd->height_mbs;   /* intra pictures: wavefront of row warps */
-	J.word_loads = 0; J.trace = NULL; J.trace_base = 0; J.phase_slot = 0;
+	J.trace = NULL; J.trace_base = 0; J.phase_slot = 0;
 	{ static int tma = -1; if (tma < 0) { const char *e = getenv("E264B_TMA"); tma = e ? atoi(e) : 1; } J.tmaps = tma ? c->d_tmaps : NULL; }
 	{ static int force = -2; if (force == -2) { const char *e = getenv("E264B_ROWS"); force = e ? atoi(e) : -1; } if (force >= 0) J.rows_mode = force; }
 	if (c->epoch >= (1u << 20)) {   /* row progress counters encode epoch * 2048 + count: restart before it wraps */

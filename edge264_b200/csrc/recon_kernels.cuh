@@ -28,7 +28,6 @@ struct PicJob {
 	unsigned *tickets;    /* [2] zeroed before the picture */
 	unsigned *err;
 	int rows_mode;
-	int word_loads;       /* unused */
 	const void *tmaps;    /* CUtensorMap[6] over the whole frame pool (x, y, slot): luma boxes 48x{21,13,9}, chroma boxes 32x{9,5,3}; NULL = no TMA */
 	int16_t *resid;       /* [nmb][384] residual written by e264_residual_kernel (coded macroblocks only) */
 	unsigned long long *trace;   /* measurement only (E264B_TRACE): [trace_base + kind] = {first warp start, last warp end} in globaltimer ns */

@@ -1,9 +1,11 @@
 /* slice_dec.c — the product-side instantiation of the shared slice-data code (parser direction). */
+#include <pthread.h>
 #include "mb_impl.h"
 
+static pthread_once_t tables_once = PTHREAD_ONCE_INIT;   /* decoders are created and run from many threads at once */
+
 int e264_parse_slice_data(SliceCtx *s) {
-	static int ready;
-	if (!ready) { sx_init_tables(); ready = 1; }
+	pthread_once(&tables_once, sx_init_tables);
 	s->skip_run = -1; s->last_qp_delta_nz = 0; s->prev_mb_skipped = 0;
 	if (s->cabac) {
 		size_t byte = (s->br.pos + 7) >> 3;                 /* cabac_alignment_one_bit */
@@ -13,7 +15,9 @@ int e264_parse_slice_data(SliceCtx *s) {
 	}
 	int total = s->w_mbs * s->h_mbs, n = 0;
 	for (;;) {
-		if (s->mbaddr >= total) { s->error = 1; break; }
+		if (s->mbaddr < 0 || s->mbaddr >= total) { s->error = 1; break; }
+		if (s->mbi[s->mbaddr].slice_id) { s->error = 1; break; }            /* already delivered by another slice of this picture */
+		if (s->n_coefs + 408u > s->coef_cap) { s->error = 2; break; }        /* a macroblock takes at most 16+256+8+128 levels: the pool cannot overflow inside it */
 		int end = sx_one_mb(s);
 		if (s->error) break;
 		n++;

@@ -509,7 +509,7 @@ static int residual_block_cavlc(SliceCtx *s, int nC, int16_t *blk, const uint8_t
  * 4x4 block b at 16+16b or 8x8 block i at 16+64i, chroma DC at 272, chroma AC block j at 280+16j)
  * and copies them into the pool the same way, so both directions produce identical records. */
 static inline int16_t *sx_pool_take(SliceCtx *s, int n, int staging_off) {
-	if (s->n_coefs + (uint32_t)n > s->coef_cap) { s->error = 2; s->n_coefs = s->rec->coef_off; }
+	if (s->n_coefs + (uint32_t)n > s->coef_cap) { s->error = 2; s->n_coefs = s->coef_cap - 408u; }   /* unreachable after the per-macroblock check of the slice loop; stays inside the buffer regardless */
 	int16_t *p = s->coefs + s->n_coefs;
 	s->n_coefs += n;
 #ifndef E264_ENCODER

@@ -10,7 +10,7 @@
  * kernels reconstruct the pixels.
  *
  *   reference interface                       replaced by (this library)
- *   edge264_find_start_code  edge264.c:87     src: edge264_b200/csrc/api.c
+ *   edge264_find_start_code  edge264.c:87     src: edge264_b200/csrc/decoder.c
  *   edge264_alloc            edge264.c:142    idem (n_threads is accepted, ignored: GPU backend)
  *   edge264_flush            edge264.c:261    idem
  *   edge264_free             edge264.c:273    idem

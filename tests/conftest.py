@@ -90,5 +90,5 @@ def md5_frames(frames):
 
 
 def have(backend):
-    from edge264_b200 import _LIBS
+    from checkers import _LIBS
     return os.path.exists(_LIBS[backend])

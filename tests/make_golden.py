@@ -3,7 +3,7 @@
 import json, os, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from conftest import ROOT, STREAMS, DPB_STREAMS, make_stream, md5_frames
-from edge264_b200 import decode_bytes
+from checkers import decode_bytes
 
 out = {}
 tmp = tempfile.mkdtemp()

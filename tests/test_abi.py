@@ -1,7 +1,7 @@
 """The C-ABI libraries load and export every symbol the headers declare (no compute, no GPU)."""
 import ctypes, os, re
 from conftest import ROOT
-from edge264_b200 import Edge264Frame, _LIBS
+from checkers import Edge264Frame, _LIBS
 
 
 def declared(header):
@@ -35,7 +35,7 @@ def test_oracle_library_exports_api():
 
 def test_find_start_code_semantics():
     # reference edge264.c:87-119: pointer to the 00 00 01 (three-byte) or 00 00 00 01 (four-byte) prefix, else `end`
-    from edge264_b200 import load
+    from checkers import load
     for backend in ("port", "ref"):
         if not os.path.exists(_LIBS[backend]):
             continue

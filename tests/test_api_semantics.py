@@ -4,7 +4,7 @@ of a stream (edge264.c:261-270), and the sequence of return codes of edge264_dec
 import ctypes, errno, os
 import pytest
 from conftest import STREAMS, make_stream, have
-from edge264_b200 import load, Edge264Frame, _frame_bytes
+from checkers import load, Edge264Frame, _frame_bytes
 
 
 def decode_borrowing(data, backend, hold, flush_at=None):
@@ -145,7 +145,7 @@ def test_lost_reference_pictures_follow_the_reference(workdir, case):
     except that everything output before the loss must be identical."""
     import subprocess
     from conftest import ROOT
-    from edge264_b200 import decode_bytes
+    from checkers import decode_bytes
     if not have("ref"):
         pytest.skip("reference library not built")
     args, drop = case
@@ -227,7 +227,7 @@ def test_sequence_changes_follow_the_reference(workdir):
     max_num_ref_frames alone (it does not: FrameId numbering and parameter sets continue, edge264_headers.c:2016-2024)."""
     import subprocess
     from conftest import ROOT, md5_frames
-    from edge264_b200 import decode_bytes
+    from checkers import decode_bytes
     if not have("ref"):
         pytest.skip("reference library not built")
     parts = []

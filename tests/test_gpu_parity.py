@@ -3,7 +3,7 @@ reference (when oracle/_ref travelled) and the golden digests — bit-exact, eve
 import json, os, subprocess
 import pytest
 from conftest import ROOT, STREAMS, make_stream, md5_frames, have
-from edge264_b200 import decode_bytes
+from checkers import decode_bytes
 
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "streams.json")))
@@ -32,8 +32,7 @@ FULL = [
 @pytest.mark.parametrize("name,w,h,args", FULL, ids=[s[0] for s in FULL])
 def test_full_size_against_reference(workdir, name, w, h, args):
     """BASELINE.json sizes: compared with the compiled reference decoder (the oracle port is too slow here)."""
-    if not have("ref"):
-        pytest.skip("oracle/_ref missing")
+    assert have("ref"), "oracle/_ref did not travel to this box: the full-size parity legs cannot run (build it with __graft_entry__.build() where /root/reference exists)"
     path = make_stream(workdir, name, w, h, args)
     ref = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_decode"), path, "-q"], capture_output=True, text=True, timeout=600).stdout.strip().splitlines()[-1]
     gpu = subprocess.run([os.path.join(ROOT, "tools", "b200_decode"), path, "-q"], capture_output=True, text=True, timeout=600).stdout.strip().splitlines()[-1]

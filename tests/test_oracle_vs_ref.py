@@ -4,7 +4,7 @@ digests (tests/golden/streams.json, produced by tests/make_golden.py from the re
 import json, os
 import pytest
 from conftest import ROOT, STREAMS, DPB_STREAMS, make_stream, md5_frames, have
-from edge264_b200 import decode_bytes
+from checkers import decode_bytes
 
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "streams.json")))
 

@@ -12,7 +12,7 @@ def _worker(rank, world, port, paths, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, ROOT)
     from edge264_b200.shard import broadcast_streams, max_over_ranks
-    from edge264_b200 import decode_bytes
+    from checkers import decode_bytes
     bufs_all = [open(p, "rb").read() for p in paths] if rank == 0 else None
     mine = broadcast_streams(bufs_all, len(paths) // world, world, rank, dist)
     digests = []

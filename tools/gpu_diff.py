@@ -2,7 +2,8 @@
 """debug helper: first differing sample between the GPU library and the oracle port on a generated stream"""
 import os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from edge264_b200 import decode_bytes
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from checkers import decode_bytes
 import numpy as np
 W, H = int(sys.argv[1]), int(sys.argv[2]); args = sys.argv[3:]
 path = "/tmp/gpudiff.264"

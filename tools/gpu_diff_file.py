@@ -2,7 +2,8 @@
 """debug helper: per-macroblock difference map between the GPU library and another backend for a .264 file"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from edge264_b200 import decode_bytes
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from checkers import decode_bytes
 import numpy as np
 data = open(sys.argv[1], "rb").read(); other = sys.argv[2] if len(sys.argv) > 2 else "ref"
 ref, _ = decode_bytes(data, other)
