@@ -8,7 +8,7 @@ LIB := edge264_b200/libedge264_b200.so
 
 all: $(LIB) tools/gen264 tools/b200_decode tools/libe264bench.so oracle
 
-$(CSRC)/recon.o: $(CSRC)/recon.cu $(CSRC)/recon_kernels.cuh $(wildcard $(CSRC)/*.h) include/e264b_recon.h
+$(CSRC)/recon.o: $(CSRC)/recon.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/e264b_recon.h
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(CSRC)/recon.ptxas.log || (cat $(CSRC)/recon.ptxas.log; false)
 $(CSRC)/decoder.o: $(CSRC)/decoder.c $(wildcard $(CSRC)/*.h)
 	$(CC) $(CFLAGS) -c $< -o $@

@@ -158,6 +158,7 @@ struct Edge264Decoder {
 	/* current picture build-up */
 	MbInfo *mbi; int16_t *coefs; uint32_t coef_cap; uint32_t n_coefs;
 	E264SliceRec *slices; int n_slices;
+	uint32_t *intra_list; int staging;
 	int mbs_done, n_intra, any_deblock;
 	uint16_t slice_counter;
 	/* output */
@@ -181,7 +182,7 @@ typedef struct E264Backend {
 	void *(*host_alloc)(void *ctx, size_t bytes);
 	void  (*host_free)(void *ctx, void *p);
 	/* staging for the next picture: returns pinned host areas the parser fills directly */
-	int  (*acquire_staging)(void *ctx, int slot, E264MbRec **recs, int16_t **coefs, uint32_t *coef_cap, E264SliceRec **slices);
+	int  (*acquire_staging)(void *ctx, int slot, E264Staging *out);
 	/* reconstruct one picture into `pd->dst_slot` and mirror it into host_out; returns a ticket */
 	int  (*submit)(void *ctx, const E264PicDesc *pd, uint8_t *host_out, uint64_t *ticket);
 	int  (*wait)(void *ctx, uint64_t ticket);

@@ -342,7 +342,12 @@ static int finish_picture(Edge264Decoder *d) {
 	E264PicDesc pd; memset(&pd, 0, sizeof(pd));
 	pd.width_mbs = d->w_mbs; pd.height_mbs = d->h_mbs; pd.stride_y = d->stride_y; pd.stride_c = d->stride_c;
 	pd.plane_y = d->plane_y; pd.frame_bytes = d->frame_bytes; pd.dst_slot = d->cur;
-	pd.n_slices = d->n_slices; pd.n_coefs = (int32_t)d->n_coefs; pd.any_deblock = d->any_deblock; pd.n_intra = d->n_intra;
+	pd.n_slices = d->n_slices; pd.n_coefs = (int32_t)d->n_coefs; pd.any_deblock = d->any_deblock; pd.staging = d->staging;
+	{	/* intra macroblocks in raster order: the device draws them from this list, so a waiting macroblock only ever waits for earlier entries */
+		const int total = d->w_mbs * d->h_mbs; int n = 0;
+		for (int a = 0; a < total; a++) if (p->recs[a].kind != MBK_INTER) d->intra_list[n++] = (uint32_t)a;
+		pd.n_intra = n;
+	}
 	int ret = 0;
 	if (p->host_buf >= 0) {
 		uint64_t ticket = 0;
@@ -725,9 +730,10 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 		d->cur = slot; d->cur_idr = idr; d->cur_nal_ref_idc = nal_ref_idc;
 		d->first_sh = *h;
 		for (int i = 0; i < E264_MAX_SLOTS; i++) cp->slot_uid[i] = d->pics[i].in_use ? d->pics[i].uid : -1;
-		uint32_t cap = 0;
-		{ PROF_BEGIN; int ar = d->be->acquire_staging(d->be_ctx, slot, &cp->recs, &d->coefs, &cap, &d->slices); PROF_END(1); if (ar) return ENOMEM; }
-		d->coef_cap = cap; d->n_coefs = 0; d->n_slices = 0; d->mbs_done = 0; d->n_intra = 0; d->any_deblock = 0;
+		E264Staging stg; memset(&stg, 0, sizeof(stg));
+		{ PROF_BEGIN; int ar = d->be->acquire_staging(d->be_ctx, slot, &stg); PROF_END(1); if (ar) return ENOMEM; }
+		cp->recs = stg.recs; d->coefs = stg.coefs; d->slices = stg.slices; d->intra_list = stg.intra_list; d->staging = stg.handle;
+		d->coef_cap = stg.coef_capacity; d->n_coefs = 0; d->n_slices = 0; d->mbs_done = 0; d->n_intra = 0; d->any_deblock = 0;
 		{ PROF_BEGIN; memset(d->mbi, 0, (size_t)d->w_mbs * d->h_mbs * sizeof(MbInfo)); PROF_END(4); }
 		/* records need no clearing: every macroblock of a complete picture rewrites its own (sx_one_mb) */
 		d->slice_counter = 0;

@@ -18,6 +18,7 @@
 #include <vector>
 #include <mutex>
 #include "recon_kernels.cuh"
+#include "deblock_kernels.cuh"
 extern "C" {
 #include "dec.h"
 }
@@ -30,9 +31,11 @@ extern "C" {
 struct Staging {
 	E264MbRec *d_recs; int16_t *d_coefs, *h_coefs; E264SliceRec *d_slices, *h_slices;
 	int16_t *d_resid;            /* residual of the picture in flight: nmb x 384 int16 */
+	E264DbkMb *d_dbk;            /* deblocking digests of the picture in flight */
+	uint32_t *d_intra, *h_intra; /* intra macroblock list */
 	cudaEvent_t done; bool busy;
 };
-struct KeptPic { E264PicDesc pd; E264MbRec *d_recs; int16_t *d_coefs; E264SliceRec *d_slices; };
+struct KeptPic { E264PicDesc pd; E264MbRec *d_recs; int16_t *d_coefs; E264SliceRec *d_slices; uint32_t *d_intra; };
 
 struct E264bDevice {
 	int dev; cudaStream_t stream;
@@ -41,7 +44,8 @@ struct E264bDevice {
 	void *d_tmaps;               /* CUtensorMap[n_slots][6] over the frame pool, or NULL when the geometry does not fit TMA's rules */
 	E264MbRec *h_recs[E264_MAX_SLOTS]; cudaEvent_t rec_up[E264_MAX_SLOTS]; bool rec_busy[E264_MAX_SLOTS];
 	Staging st[NSTAGE]; int stage;
-	unsigned *d_sync;            /* [0..2] tickets (inter, deblock, intra), [3] err, then flags[2*nmb] */
+	unsigned *d_sync;            /* [0..7] tickets (0 inter, 1 deblock, 2 intra), [8] err, [16..) flags[nmb] + deblocking progress[2 * h_mbs] */
+	size_t sync_words;
 	unsigned epoch;
 	cudaEvent_t tick_ev[NTICK]; uint64_t tick_seq;
 	unsigned *h_err;             /* pinned [NTICK]: the device error word as it stood when ticket t % NTICK completed */
@@ -67,12 +71,13 @@ static void free_geometry(E264bDevice *c) {
 	for (int i = 0; i < NSTAGE; i++) {
 		Staging *s = &c->st[i];
 		if (s->d_recs) cudaFree(s->d_recs); if (s->d_coefs) cudaFree(s->d_coefs); if (s->d_slices) cudaFree(s->d_slices); if (s->d_resid) cudaFree(s->d_resid); s->d_resid = NULL;
+		if (s->d_dbk) cudaFree(s->d_dbk); if (s->d_intra) cudaFree(s->d_intra); if (s->h_intra) cudaFreeHost(s->h_intra); s->d_dbk = NULL; s->d_intra = NULL; s->h_intra = NULL;
 		if (s->h_coefs) cudaFreeHost(s->h_coefs); if (s->h_slices) cudaFreeHost(s->h_slices);
 		s->d_recs = NULL; s->d_coefs = NULL; s->d_slices = NULL; s->h_coefs = NULL; s->h_slices = NULL; s->busy = false;
 	}
 	if (c->d_sync) cudaFree(c->d_sync);
 	c->d_sync = NULL;
-	for (auto &k : c->kept) { cudaFree(k.d_recs); cudaFree(k.d_coefs); cudaFree(k.d_slices); }
+	for (auto &k : c->kept) { cudaFree(k.d_recs); cudaFree(k.d_coefs); cudaFree(k.d_slices); cudaFree(k.d_intra); }
 	c->kept.clear();
 }
 
@@ -112,7 +117,7 @@ extern "C" int e264b_create(E264bDevice **out) {
 	return 0;
 }
 
-static void drop_kept(E264bDevice *c) { for (auto &k : c->kept) { cudaFree(k.d_recs); cudaFree(k.d_coefs); cudaFree(k.d_slices); } c->kept.clear(); }
+static void drop_kept(E264bDevice *c) { for (auto &k : c->kept) { cudaFree(k.d_recs); cudaFree(k.d_coefs); cudaFree(k.d_slices); cudaFree(k.d_intra); } c->kept.clear(); }
 
 extern "C" void e264b_destroy(E264bDevice *c) {
 	if (!c) return;
@@ -179,7 +184,7 @@ extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots
 	if (c->d_frames && c->n_slots == n_slots && !memcmp(&c->g, g, sizeof(*g))) {   /* pooled context of the same geometry */
 		CK(cudaStreamSynchronize(c->stream));
 		drop_kept(c);
-		CK(cudaMemsetAsync(c->d_sync, 0, (4 + 2 * c->nmb) * sizeof(unsigned), c->stream));
+		CK(cudaMemsetAsync(c->d_sync, 0, c->sync_words * sizeof(unsigned), c->stream));
 		for (int i = 0; i < NSTAGE; i++) c->st[i].busy = false;
 		for (int i = 0; i < E264_MAX_SLOTS; i++) c->rec_busy[i] = false;
 		c->epoch = 0; c->stage = 0;
@@ -203,9 +208,13 @@ extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots
 		CK(cudaMalloc(&s->d_resid, c->nmb * 384 * sizeof(int16_t)));
 		CK(cudaHostAlloc(&s->h_coefs, (size_t)c->coef_cap * 2 + 64, cudaHostAllocDefault));
 		CK(cudaHostAlloc(&s->h_slices, E264_MAX_SLICES * sizeof(E264SliceRec), cudaHostAllocDefault));
+		CK(cudaMalloc(&s->d_dbk, c->nmb * sizeof(E264DbkMb)));
+		CK(cudaMalloc(&s->d_intra, c->nmb * sizeof(uint32_t)));
+		CK(cudaHostAlloc(&s->h_intra, c->nmb * sizeof(uint32_t), cudaHostAllocDefault));
 	}
-	CK(cudaMalloc(&c->d_sync, (4 + 2 * c->nmb) * sizeof(unsigned)));
-	CK(cudaMemsetAsync(c->d_sync, 0, (4 + 2 * c->nmb) * sizeof(unsigned), c->stream));
+	c->sync_words = 16 + c->nmb + 2 * (size_t)g->height_mbs + 16;
+	CK(cudaMalloc(&c->d_sync, c->sync_words * sizeof(unsigned)));
+	CK(cudaMemsetAsync(c->d_sync, 0, c->sync_words * sizeof(unsigned), c->stream));
 	c->epoch = 0; c->stage = 0;
 	CK(cudaStreamSynchronize(c->stream));
 	return 0;
@@ -233,30 +242,32 @@ extern "C" void e264b_host_free(E264bDevice *c, void *p) {
 	cudaSetDevice(c->dev); cudaFreeHost(p);   /* not ours to pool */
 }
 
-extern "C" int e264b_acquire_staging(E264bDevice *c, int slot, E264MbRec **recs, int16_t **coefs, uint32_t *cap, E264SliceRec **slices) {
+extern "C" int e264b_acquire_staging(E264bDevice *c, int slot, E264Staging *out) {
 	CK(cudaSetDevice(c->dev));
 	c->stage = (c->stage + 1) % NSTAGE;
 	Staging *s = &c->st[c->stage];
 	if (s->busy) { CK(cudaEventSynchronize(s->done)); s->busy = false; }
 	if (c->rec_busy[slot]) { CK(cudaEventSynchronize(c->rec_up[slot])); c->rec_busy[slot] = false; }
-	*recs = c->h_recs[slot]; *coefs = s->h_coefs; *cap = c->coef_cap; *slices = s->h_slices;
+	out->handle = c->stage; out->recs = c->h_recs[slot]; out->coefs = s->h_coefs; out->coef_capacity = c->coef_cap; out->slices = s->h_slices; out->intra_list = s->h_intra;
 	return 0;
 }
 
-static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, const E264MbRec *recs, const int16_t *coefs, const E264SliceRec *slices) {
+static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, int stage, const E264MbRec *recs, const int16_t *coefs, const E264SliceRec *slices, const uint32_t *intra) {
 	PicJob J;
 	J.recs = recs; J.coefs = coefs; J.slices = slices; J.frames = c->d_frames;
 	J.frame_bytes = pd->frame_bytes; J.w_mbs = pd->width_mbs; J.h_mbs = pd->height_mbs;
 	J.stride_y = pd->stride_y; J.stride_c = pd->stride_c; J.plane_y = pd->plane_y; J.dst_slot = pd->dst_slot; J.n_slots = c->n_slots;
-	J.tickets = c->d_sync; J.err = c->d_sync + 3; J.flags = c->d_sync + 4;
-	J.resid = c->st[c->stage].d_resid;
+	J.tickets = c->d_sync; J.err = c->d_sync + 8; J.flags = c->d_sync + 16;
+	J.resid = c->st[stage].d_resid;
+	J.dbk = pd->any_deblock ? c->st[stage].d_dbk : NULL;
+	J.intra_list = intra; J.n_intra = pd->n_intra;
 	J.rows_mode = pd->n_intra * 2 > pd->width_mbs * pd->height_mbs;   /* intra pictures: wavefront of row warps */
 	J.trace = NULL; J.trace_base = 0; J.phase_slot = 0;
 	{ static int tma = -1; if (tma < 0) { const char *e = getenv("E264B_TMA"); tma = e ? atoi(e) : 1; } J.tmaps = tma ? c->d_tmaps : NULL; }
 	{ static int force = -2; if (force == -2) { const char *e = getenv("E264B_ROWS"); force = e ? atoi(e) : -1; } if (force >= 0) J.rows_mode = force; }
 	if (c->epoch >= (1u << 20)) {   /* row progress counters encode epoch * 2048 + count: restart before it wraps */
 		cudaStreamSynchronize(c->stream);
-		cudaMemsetAsync(c->d_sync, 0, (4 + 2 * c->nmb) * sizeof(unsigned), c->stream);
+		cudaMemsetAsync(c->d_sync, 0, c->sync_words * sizeof(unsigned), c->stream);
 		c->epoch = 0;
 	}
 	J.epoch = ++c->epoch;
@@ -267,9 +278,18 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 	int blocks = (nmb + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
 	int cap = c->sm_count * 8;
 	if (blocks > cap) blocks = cap;
-	static int minb = -1;
+	static int minb = -1, dbk_old = -1;
 	if (minb < 0) { const char *e = getenv("E264B_MINB"); minb = e ? atoi(e) : 4; }
-	CK(cudaMemsetAsync(c->d_sync, 0, 3 * sizeof(unsigned), c->stream));
+	if (dbk_old < 0) { const char *e = getenv("E264B_DBK_OLD"); dbk_old = e ? atoi(e) : 0; }
+	/* first on the stream: clears the ticket words (no memset per picture) and, for deblocked pictures, derives every
+	 * macroblock's boundary strengths and filter thresholds — record-only work without dependencies */
+	{
+		PicJob P = J;
+		if (!with_deblock || dbk_old) P.dbk = NULL;
+		int pb = P.dbk ? (nmb + PRE_WARPS - 1) / PRE_WARPS : 1;
+		if (pb > c->sm_count * 4) pb = c->sm_count * 4;
+		e264_prepass_kernel<<<pb, PRE_WARPS * 32, 0, c->stream>>>(P); c->launches++;
+	}
 	if (pd->n_coefs > 0) { e264_residual_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++; }
 	if (pd->n_intra < nmb) {
 		if (minb >= 8) e264_inter_kernel<8><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
@@ -280,12 +300,19 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 		c->launches++;
 	}
 	if (pd->n_intra > 0) {
-		int ib = J.rows_mode ? (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK : blocks;
+		int ib = J.rows_mode ? (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK : (pd->n_intra + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+		if (ib > cap) ib = cap;
 		e264_intra_kernel<<<ib, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++;
 	}
-	if (with_deblock) {   /* one warp per macroblock row */
-		int rb = (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-		e264_deblock_kernel<<<rb, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++;
+	if (with_deblock) {
+		if (dbk_old) {   /* round-1 kernel: one warp per macroblock row */
+			int rb = (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+			e264_deblock_rows_kernel<<<rb, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+		} else {         /* one block per band of 16 rows and kind of plane */
+			int bands = (J.h_mbs + 2 * DBK_PAIRS - 1) / (2 * DBK_PAIRS);
+			e264_deblock_kernel<<<2 * bands, DBK_PAIRS * 32, 0, c->stream>>>(J);
+		}
+		c->launches++;
 	}
 	CK(cudaGetLastError());
 	return 0;
@@ -293,27 +320,31 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 
 extern "C" int e264b_submit(E264bDevice *c, const E264PicDesc *pd, uint8_t *host_out, uint64_t *ticket) {
 	CK(cudaSetDevice(c->dev));
-	Staging *s = &c->st[c->stage];
+	if (pd->staging < 0 || pd->staging >= NSTAGE) return -1;
+	Staging *s = &c->st[pd->staging];
 	size_t rec_bytes = c->nmb * sizeof(E264MbRec), coef_bytes = ((size_t)pd->n_coefs * 2 + 15) & ~(size_t)15, sl_bytes = (size_t)pd->n_slices * sizeof(E264SliceRec);
 	CK(cudaMemcpyAsync(s->d_recs, c->h_recs[pd->dst_slot], rec_bytes, cudaMemcpyHostToDevice, c->stream));
 	CK(cudaEventRecord(c->rec_up[pd->dst_slot], c->stream)); c->rec_busy[pd->dst_slot] = true;
 	if (coef_bytes) CK(cudaMemcpyAsync(s->d_coefs, s->h_coefs, coef_bytes, cudaMemcpyHostToDevice, c->stream));
 	if (sl_bytes) CK(cudaMemcpyAsync(s->d_slices, s->h_slices, sl_bytes, cudaMemcpyHostToDevice, c->stream));
-	c->h2d_bytes += rec_bytes + coef_bytes + sl_bytes;
-	PicJob J = make_job(c, pd, s->d_recs, s->d_coefs, s->d_slices);
+	size_t in_bytes = (size_t)pd->n_intra * sizeof(uint32_t);
+	if (in_bytes) CK(cudaMemcpyAsync(s->d_intra, s->h_intra, in_bytes, cudaMemcpyHostToDevice, c->stream));
+	c->h2d_bytes += rec_bytes + coef_bytes + sl_bytes + in_bytes;
+	PicJob J = make_job(c, pd, pd->staging, s->d_recs, s->d_coefs, s->d_slices, s->d_intra);
 	if (launch_picture(c, J, pd, pd->any_deblock)) return -1;
 	{	/* E264B_DEBUG_SYNC=1: synchronise after every picture and report the device error word (debugging aid) */
 		static int dbg = -1; if (dbg < 0) { const char *e = getenv("E264B_DEBUG_SYNC"); dbg = e ? atoi(e) : 0; }
 		if (dbg) {
 			fprintf(stderr, "e264b: picture slot %d epoch %u (intra %d of %d, coefs %u) launched, waiting...\n", pd->dst_slot, J.epoch, pd->n_intra, J.w_mbs * J.h_mbs, pd->n_coefs);
-			cudaError_t e = cudaStreamSynchronize(c->stream); unsigned v = 0; cudaMemcpy(&v, c->d_sync + 3, sizeof(v), cudaMemcpyDeviceToHost);
+			cudaError_t e = cudaStreamSynchronize(c->stream); unsigned v = 0; cudaMemcpy(&v, c->d_sync + 8, sizeof(v), cudaMemcpyDeviceToHost);
 			fprintf(stderr, "e264b:   -> %s, device error word %u\n", cudaGetErrorString(e), v);
 		}
 	}
 	if (host_out) { CK(cudaMemcpyAsync(host_out, c->d_frames + (size_t)pd->dst_slot * pd->frame_bytes, (size_t)pd->frame_bytes - 16, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (size_t)pd->frame_bytes - 16; }
 	if (c->keep) {
 		KeptPic k; k.pd = *pd;
-		CK(cudaMalloc(&k.d_recs, rec_bytes)); CK(cudaMalloc(&k.d_coefs, coef_bytes + 64)); CK(cudaMalloc(&k.d_slices, sl_bytes + 64));
+		CK(cudaMalloc(&k.d_recs, rec_bytes)); CK(cudaMalloc(&k.d_coefs, coef_bytes + 64)); CK(cudaMalloc(&k.d_slices, sl_bytes + 64)); CK(cudaMalloc(&k.d_intra, in_bytes + 64));
+		if (in_bytes) CK(cudaMemcpyAsync(k.d_intra, s->d_intra, in_bytes, cudaMemcpyDeviceToDevice, c->stream));
 		CK(cudaMemcpyAsync(k.d_recs, s->d_recs, rec_bytes, cudaMemcpyDeviceToDevice, c->stream));
 		if (coef_bytes) CK(cudaMemcpyAsync(k.d_coefs, s->d_coefs, coef_bytes, cudaMemcpyDeviceToDevice, c->stream));
 		if (sl_bytes) CK(cudaMemcpyAsync(k.d_slices, s->d_slices, sl_bytes, cudaMemcpyDeviceToDevice, c->stream));
@@ -321,7 +352,7 @@ extern "C" int e264b_submit(E264bDevice *c, const E264PicDesc *pd, uint8_t *host
 	}
 	CK(cudaEventRecord(s->done, c->stream)); s->busy = true;
 	uint64_t t = ++c->tick_seq;
-	if (c->d_sync) CK(cudaMemcpyAsync(&c->h_err[t % NTICK], c->d_sync + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+	if (c->d_sync) CK(cudaMemcpyAsync(&c->h_err[t % NTICK], c->d_sync + 8, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaEventRecord(c->tick_ev[t % NTICK], c->stream));
 	*ticket = t;
 	return 0;
@@ -351,7 +382,7 @@ extern "C" int e264b_error_flag(E264bDevice *c) {
 	unsigned v = 0;
 	cudaSetDevice(c->dev);
 	cudaStreamSynchronize(c->stream);
-	cudaMemcpy(&v, c->d_sync + 3, sizeof(v), cudaMemcpyDeviceToHost);
+	cudaMemcpy(&v, c->d_sync + 8, sizeof(v), cudaMemcpyDeviceToHost);
 	return (int)v;
 }
 extern "C" void e264b_stats(E264bDevice *c, uint64_t *launches, uint64_t *h2d, uint64_t *d2h) { if (launches) *launches = c->launches; if (h2d) *h2d = c->h2d_bytes; if (d2h) *d2h = c->d2h_bytes; }
@@ -410,11 +441,11 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, float *ms_total, 
 				E264bDevice *c = cs[i];
 				c->epoch = 0;
 				CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-				CK(cudaMemsetAsync(c->d_sync, 0, (4 + 2 * c->nmb) * sizeof(unsigned), c->stream));
+				CK(cudaMemsetAsync(c->d_sync, 0, c->sync_words * sizeof(unsigned), c->stream));
 				for (int r = 0; r < reps; r++)
 					for (size_t k = 0; k < npic; k++) {
 						KeptPic &kp = c->kept[k];
-						PicJob J = make_job(c, &kp.pd, kp.d_recs, kp.d_coefs, kp.d_slices);
+						PicJob J = make_job(c, &kp.pd, kp.pd.staging, kp.d_recs, kp.d_coefs, kp.d_slices, kp.d_intra);
 						if (d_trace && pass == 0) { J.trace = d_trace; J.trace_base = (int)((((size_t)r * npic + k) * n + i) * 4); J.phase_slot = (int)(n_trace * 2); }
 						if (launch_picture(c, J, &kp.pd, pass == 0 ? kp.pd.any_deblock : 0)) return -1;
 					}
@@ -436,7 +467,7 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, float *ms_total, 
 				for (size_t k = 0; k < npic; k++)
 					for (int i = 0; i < n; i++) {
 						KeptPic &kp = cs[i]->kept[k];
-						PicJob J = make_job(cs[i], &kp.pd, kp.d_recs, kp.d_coefs, kp.d_slices);
+						PicJob J = make_job(cs[i], &kp.pd, kp.pd.staging, kp.d_recs, kp.d_coefs, kp.d_slices, kp.d_intra);
 						if (d_trace && pass == 0) { J.trace = d_trace; J.trace_base = (int)((((size_t)r * npic + k) * n + i) * 4); J.phase_slot = (int)(n_trace * 2); }
 						if (launch_picture(cs[i], J, &kp.pd, pass == 0 ? kp.pd.any_deblock : 0)) return -1;
 					}
@@ -480,7 +511,7 @@ static void be_destroy(void *ctx) { e264b_destroy((E264bDevice *)ctx); }
 static int be_configure(void *ctx, const E264PicDesc *g, int n) { return e264b_configure((E264bDevice *)ctx, g, n); }
 static void *be_host_alloc(void *ctx, size_t b) { return e264b_host_alloc((E264bDevice *)ctx, b); }
 static void be_host_free(void *ctx, void *p) { e264b_host_free((E264bDevice *)ctx, p); }
-static int be_acquire(void *ctx, int slot, E264MbRec **r, int16_t **c, uint32_t *cap, E264SliceRec **s) { return e264b_acquire_staging((E264bDevice *)ctx, slot, r, c, cap, s); }
+static int be_acquire(void *ctx, int slot, E264Staging *out) { return e264b_acquire_staging((E264bDevice *)ctx, slot, out); }
 static int be_submit(void *ctx, const E264PicDesc *pd, uint8_t *out, uint64_t *t) { return e264b_submit((E264bDevice *)ctx, pd, out, t); }
 static int be_wait(void *ctx, uint64_t t) { return e264b_wait((E264bDevice *)ctx, t); }
 static int be_fill(void *ctx, int slot, int y, int c) { return e264b_fill_slot((E264bDevice *)ctx, slot, y, c); }

@@ -23,11 +23,14 @@ struct PicJob {
 	const E264MbRec *recs; const int16_t *coefs; const E264SliceRec *slices;
 	uint8_t *frames;
 	int frame_bytes, w_mbs, h_mbs, stride_y, stride_c, plane_y, dst_slot, n_slots;
-	unsigned *flags;      /* [2][nmb]: recon done / deblock done == epoch */
+	unsigned *flags;      /* [nmb] "reconstructed" == epoch, then [2][h_mbs] deblocking progress of luma / chroma rows (epoch * 2048 + macroblocks stored) */
 	unsigned epoch;
-	unsigned *tickets;    /* [2] zeroed before the picture */
+	unsigned *tickets;    /* [8] zeroed by e264_prepass_kernel: 0 inter, 1 deblock, 2 intra */
 	unsigned *err;
 	int rows_mode;
+	struct E264DbkMb *dbk;        /* [nmb] deblocking digests written by e264_prepass_kernel; NULL = picture is not deblocked */
+	const uint32_t *intra_list;   /* addresses of the intra macroblocks in raster order */
+	int n_intra;
 	const void *tmaps;    /* CUtensorMap[6] over the whole frame pool (x, y, slot): luma boxes 48x{21,13,9}, chroma boxes 32x{9,5,3}; NULL = no TMA */
 	int16_t *resid;       /* [nmb][384] residual written by e264_residual_kernel (coded macroblocks only) */
 	unsigned long long *trace;   /* measurement only (E264B_TRACE): [trace_base + kind] = {first warp start, last warp end} in globaltimer ns */
@@ -957,9 +960,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_intra_kernel(PicJob
 			if (t >= (unsigned)J.h_mbs) break;
 			for (int mbx = 0; mbx < J.w_mbs; mbx++) intra_mb(ws, J, dst, (int)t * J.w_mbs + mbx, mbx, (int)t, lane, true);
 		} else {
-			if (t >= (unsigned)nmb) break;
-			if (J.recs[t].kind == MBK_INTER) continue;
-			intra_mb(ws, J, dst, (int)t, (int)t % J.w_mbs, (int)t / J.w_mbs, lane, false);
+			if (t >= (unsigned)J.n_intra) break;
+			const int mb = (int)__ldg(J.intra_list + t);
+			if (mb >= nmb) continue;
+			intra_mb(ws, J, dst, mb, mb % J.w_mbs, mb / J.w_mbs, lane, false);
 		}
 	}
 }
@@ -1036,7 +1040,7 @@ __device__ __forceinline__ void filter_chroma(uint8_t *pix, int step, int bs, in
  * stay in shared memory and only the row above is a cross-warp dependency, published as a per-row
  * progress counter (value = epoch * 2048 + macroblocks finished).  Row y may process macroblock x once
  * row y-1 has finished x+1 (its left-edge filter touches columns 13..15 of macroblock x above us). */
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_deblock_kernel(PicJob J) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_deblock_rows_kernel(PicJob J) {   /* round-1 kernel, kept for A/B runs (E264B_DBK_OLD=1) */
 	TraceScope trace_(J, 3);
 	__shared__ DbSmem smem[WARPS_PER_BLOCK];
 	const int lane = threadIdx.x & 31;

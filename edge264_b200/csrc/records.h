@@ -92,8 +92,21 @@ typedef struct E264PicDesc {
 	int32_t n_slices;
 	int32_t n_coefs;              /* int16 entries used in the coefficient pool */
 	int32_t any_deblock;          /* at least one macroblock has MBF_DEBLOCK */
-	int32_t n_intra;              /* number of intra macroblocks (scheduling hint) */
+	int32_t n_intra;              /* number of intra macroblocks = entries of the staging's intra_list */
+	int32_t staging;              /* handle of the staging area the picture was written into (E264Staging.handle) */
 } E264PicDesc;
+
+/* Host-visible staging of one picture, handed out by the backend (pinned memory for the CUDA backend): the parser
+ * writes records, levels and slice records straight into it; intra_list receives the addresses of the picture's intra
+ * macroblocks in raster order (the device schedules them from it). */
+typedef struct E264Staging {
+	int32_t handle;
+	uint32_t coef_capacity;       /* int16 entries in coefs */
+	struct E264MbRec *recs;
+	int16_t *coefs;
+	struct E264SliceRec *slices;
+	uint32_t *intra_list;
+} E264Staging;
 
 static inline int e264_blk_x(int b) { return ((b & 1) | ((b >> 1) & 2)); }          /* z-order -> 4x4 column */
 static inline int e264_blk_y(int b) { return (((b >> 1) & 1) | ((b >> 2) & 2)); }   /* z-order -> 4x4 row    */

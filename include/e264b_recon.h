@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-struct E264MbRec; struct E264SliceRec; struct E264PicDesc; struct Edge264Decoder;
+struct E264MbRec; struct E264SliceRec; struct E264PicDesc; struct E264Staging; struct Edge264Decoder;
 typedef struct E264bDevice E264bDevice;
 
 int   e264b_create(E264bDevice **out);              /* device = $E264B_DEVICE (default 0); fails without a GPU */
@@ -31,8 +31,7 @@ void  e264b_destroy(E264bDevice *dev);
 int   e264b_configure(E264bDevice *dev, const struct E264PicDesc *geometry, int n_slots);
 void *e264b_host_alloc(E264bDevice *dev, size_t bytes);       /* pinned host memory */
 void  e264b_host_free(E264bDevice *dev, void *p);
-int   e264b_acquire_staging(E264bDevice *dev, int slot, struct E264MbRec **recs, int16_t **coefs,
-                            uint32_t *coef_capacity, struct E264SliceRec **slices);
+int   e264b_acquire_staging(E264bDevice *dev, int slot, struct E264Staging *out);   /* pinned areas the parser fills; out->handle goes back in E264PicDesc.staging */
 int   e264b_submit(E264bDevice *dev, const struct E264PicDesc *pic, uint8_t *host_out, uint64_t *ticket);
 int   e264b_wait(E264bDevice *dev, uint64_t ticket);
 int   e264b_fill_slot(E264bDevice *dev, int slot, int luma, int chroma);

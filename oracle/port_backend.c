@@ -15,13 +15,14 @@ typedef struct PortCtx {
 	E264MbRec *recs[E264_MAX_SLOTS];
 	int16_t *coefs; uint32_t coef_cap;
 	E264SliceRec *slices;
+	uint32_t *intra_list;
 	int cur_slot;
 } PortCtx;
 
 static int port_create(void **ctx) { *ctx = calloc(1, sizeof(PortCtx)); return *ctx ? 0 : -1; }
 static void port_free_all(PortCtx *c) {
 	free(c->frames_alloc); for (int i = 0; i < E264_MAX_SLOTS; i++) { free(c->recs[i]); c->recs[i] = NULL; }
-	free(c->coefs); free(c->slices); c->frames_alloc = NULL; c->coefs = NULL; c->slices = NULL;
+	free(c->coefs); free(c->slices); free(c->intra_list); c->frames_alloc = NULL; c->coefs = NULL; c->slices = NULL; c->intra_list = NULL;
 }
 static void port_destroy(void *ctx) { port_free_all((PortCtx *)ctx); free(ctx); }
 static int port_configure(void *ctx, const E264PicDesc *g, int n_slots) {
@@ -37,13 +38,15 @@ static int port_configure(void *ctx, const E264PicDesc *g, int n_slots) {
 	c->coef_cap = (uint32_t)(nmb * 408);
 	c->coefs = (int16_t *)calloc(c->coef_cap, sizeof(int16_t));
 	c->slices = (E264SliceRec *)calloc(E264_MAX_SLICES, sizeof(E264SliceRec));
-	return c->coefs && c->slices ? 0 : -1;
+	c->intra_list = (uint32_t *)calloc(nmb, sizeof(uint32_t));
+	return c->coefs && c->slices && c->intra_list ? 0 : -1;
 }
 static void *port_host_alloc(void *ctx, size_t bytes) { (void)ctx; return calloc(bytes, 1); }
 static void port_host_free(void *ctx, void *p) { (void)ctx; free(p); }
-static int port_acquire(void *ctx, int slot, E264MbRec **recs, int16_t **coefs, uint32_t *cap, E264SliceRec **slices) {
+static int port_acquire(void *ctx, int slot, E264Staging *out) {
 	PortCtx *c = (PortCtx *)ctx;
-	*recs = c->recs[slot]; *coefs = c->coefs; *cap = c->coef_cap; *slices = c->slices; c->cur_slot = slot;
+	out->handle = 0; out->recs = c->recs[slot]; out->coefs = c->coefs; out->coef_capacity = c->coef_cap; out->slices = c->slices; out->intra_list = c->intra_list;
+	c->cur_slot = slot;
 	return 0;
 }
 static int port_submit(void *ctx, const E264PicDesc *pd, uint8_t *host_out, uint64_t *ticket) {
