@@ -54,6 +54,18 @@ typedef struct MbInfo {
 	uint8_t  mvd[2][16][2] __attribute__((aligned(2)));   /* |mvd| clipped to 255 per list/blk/comp (CABAC ctxIdxInc); filled pairwise as 16-bit words */
 } MbInfo;
 
+/* Neighbourhood of the macroblock being parsed, laid out so that motion-vector prediction and the mvd context are
+ * plain index arithmetic: entry (x4, y4) of the 4x4-block grid, x4 in -1..4, y4 in -1..3, sits at (y4 + 1) * 8 + x4 + 1.
+ * Row -1 and column -1 are copied from the neighbouring macroblocks' records when an inter macroblock starts (the
+ * reference keeps the same information in its mvs/refIdx neighbour offsets, edge264_internal.h:128-143,
+ * edge264_mvpred.c:44-71); the interior is written as partitions are parsed and flushed to the record at the end. */
+typedef struct MvCache {
+	uint32_t mv[2][40];       /* (uint16)x | y << 16; 0 where the list is not used or the block is unavailable */
+	int8_t   ref[2][40];      /* reference index; -1 list not used / intra; -2 not available */
+	uint16_t mvd[2][40];      /* |mvd_x| | |mvd_y| << 8, each clipped to 255 */
+} MvCache;
+#define MC_IDX(x4, y4) (((y4) + 1) * 8 + (x4) + 1)
+
 typedef struct SliceHeader {
 	int first_mb, slice_type, pps_id, frame_num, idr_pic_id, poc_lsb, delta_poc_bottom, delta_poc[2];
 	int direct_spatial, num_ref[2];
@@ -119,6 +131,7 @@ typedef struct SliceCtx {
 	int skip_run, prev_mb_skipped;
 	int n_intra;
 	int error;
+	MvCache mc;
 } SliceCtx;
 
 /* host mirror of an output picture */

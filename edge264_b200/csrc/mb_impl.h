@@ -26,45 +26,102 @@ typedef struct MbSyn {
 
 typedef struct NbMv { int avail, ref; int mv[2]; } NbMv;
 
-static inline void sx_nb(SliceCtx *s, int list, int x4, int y4, NbMv *o) {
-	MbInfo *m; E264MbRec *r;
-	int z = sx_locate(s, x4, y4, &m, &r);
-	o->mv[0] = o->mv[1] = 0; o->ref = -1; o->avail = 0;
-	if (!m) return;
-	o->avail = 1;
-	int ref = r->ref_idx[list][z >> 2];
-	if (ref >= 0) { o->ref = ref; o->mv[0] = r->mv[list][z][0]; o->mv[1] = r->mv[list][z][1]; }
+/* ---- neighbour cache (dec.h MvCache) ---- */
+static const uint8_t sx_mc_of_z[16] = {   /* cache index of luma4x4BlkIdx z */
+	MC_IDX(0, 0), MC_IDX(1, 0), MC_IDX(0, 1), MC_IDX(1, 1), MC_IDX(2, 0), MC_IDX(3, 0), MC_IDX(2, 1), MC_IDX(3, 1),
+	MC_IDX(0, 2), MC_IDX(1, 2), MC_IDX(0, 3), MC_IDX(1, 3), MC_IDX(2, 2), MC_IDX(3, 2), MC_IDX(2, 3), MC_IDX(3, 3)};
+/* bit wi (0: w4 = 1, 1: w4 = 2, 2: w4 = 4) of entry z: the block right of and above a partition of that width starting at
+ * z lies inside this macroblock but later in decoding order, or right of the macroblock in its own row: neighbour C is
+ * not available and D takes its place (6.4.11.7) */
+static uint8_t sx_c_later[16];
+static void sx_init_c_later(void) {
+	for (int z = 0; z < 16; z++) {
+		int x4 = e264_blk_x(z), y4 = e264_blk_y(z), m = 0;
+		for (int wi = 0; wi < 3; wi++) {
+			int cx = x4 + (1 << wi), cy = y4 - 1;
+			if (cy >= 0 && (cx >= 4 || e264_blk_z(cx, cy) > z)) m |= 1 << wi;
+		}
+		sx_c_later[z] = (uint8_t)m;
+	}
+}
+
+static inline void sx_cache_nb(SliceCtx *s, int l, int idx, const MbInfo *m, const E264MbRec *r, int z) {
+	MvCache *c = &s->mc;
+	if (!m) { c->mv[l][idx] = 0; c->ref[l][idx] = -2; c->mvd[l][idx] = 0; return; }
+	int ref = r->ref_idx[l][z >> 2];
+	c->ref[l][idx] = (int8_t)ref;
+	c->mv[l][idx] = ref >= 0 ? ((const uint32_t *)r->mv[l])[z] : 0;
+	c->mvd[l][idx] = ((const uint16_t *)m->mvd[l])[z];
+}
+/* the four neighbours 16x16 prediction looks at (P_Skip, spatial direct, 16x16 partitions): A0, B0, C, D */
+static inline void sx_cache_corners(SliceCtx *s, int nl) {
+	for (int l = 0; l < nl; l++) {
+		sx_cache_nb(s, l, MC_IDX(-1, 0), s->A, s->recA, 5);
+		sx_cache_nb(s, l, MC_IDX(0, -1), s->B, s->recB, 10);
+		sx_cache_nb(s, l, MC_IDX(4, -1), s->C, s->recC, 10);
+		sx_cache_nb(s, l, MC_IDX(-1, -1), s->D, s->recD, 15);
+	}
+}
+static inline void sx_cache_fill(SliceCtx *s, int nl) {
+	MvCache *c = &s->mc;
+	sx_cache_corners(s, nl);
+	for (int l = 0; l < nl; l++) {
+		sx_cache_nb(s, l, MC_IDX(-1, 1), s->A, s->recA, 7); sx_cache_nb(s, l, MC_IDX(-1, 2), s->A, s->recA, 13); sx_cache_nb(s, l, MC_IDX(-1, 3), s->A, s->recA, 15);
+		sx_cache_nb(s, l, MC_IDX(1, -1), s->B, s->recB, 11); sx_cache_nb(s, l, MC_IDX(2, -1), s->B, s->recB, 14); sx_cache_nb(s, l, MC_IDX(3, -1), s->B, s->recB, 15);
+		for (int y = 0; y < 4; y++) {
+			int i = MC_IDX(0, y);
+			c->mv[l][i] = c->mv[l][i + 1] = c->mv[l][i + 2] = c->mv[l][i + 3] = c->mv[l][i + 4] = 0;
+			c->ref[l][i] = c->ref[l][i + 1] = c->ref[l][i + 2] = c->ref[l][i + 3] = -1; c->ref[l][i + 4] = -2;   /* x4 = 4 in the own row: not decoded yet */
+			c->mvd[l][i] = c->mvd[l][i + 1] = c->mvd[l][i + 2] = c->mvd[l][i + 3] = 0;
+		}
+	}
+}
+/* blocks derived in direct mode were written to the record: mirror them (they are neighbours of what follows) */
+static inline void sx_cache_from_rec(SliceCtx *s, int mask8) {
+	MvCache *c = &s->mc; const E264MbRec *r = s->rec;
+	for (int l = 0; l < 2; l++) for (int z = 0; z < 16; z++) if ((mask8 >> (z >> 2)) & 1) {
+		c->mv[l][sx_mc_of_z[z]] = ((const uint32_t *)r->mv[l])[z]; c->ref[l][sx_mc_of_z[z]] = r->ref_idx[l][z >> 2];
+	}
+}
+/* interior -> record / MbInfo at the end of an inter macroblock */
+static inline void sx_cache_flush(SliceCtx *s, int nl) {
+	const MvCache *c = &s->mc;
+	for (int l = 0; l < nl; l++) {
+		uint32_t *mv = (uint32_t *)s->rec->mv[l]; uint16_t *mvd = (uint16_t *)s->cur->mvd[l];
+		for (int z = 0; z < 16; z++) { mv[z] = c->mv[l][sx_mc_of_z[z]]; mvd[z] = c->mvd[l][sx_mc_of_z[z]]; }
+	}
 }
 static inline int sx_median(int a, int b, int c) { int mx = a > b ? a : b, mn = a < b ? a : b; return c > mx ? mx : c < mn ? mn : c; }
 
-/* 8.4.1.3: prediction for the partition whose top-left 4x4 is (x4,y4), w4 wide.
+/* 8.4.1.3: prediction for the partition whose top-left 4x4 is (x4,y4), w4 wide; the cache holds its neighbourhood.
  * shape: 0 generic, 1 = 16x8, 2 = 8x16 (directional rules) */
-static void sx_mvpred(SliceCtx *s, int list, int x4, int y4, int w4, int ref, int shape, int mvp[2]) {
-	NbMv A, B, C;
-	sx_nb(s, list, x4 - 1, y4, &A);
-	sx_nb(s, list, x4, y4 - 1, &B);
-	int cx = x4 + w4, cy = y4 - 1;
-	int c_in_cur_later = cy >= 0 && cx < 4 && e264_blk_z(cx, cy) > e264_blk_z(x4, y4);
-	if (c_in_cur_later) C.avail = 0; else sx_nb(s, list, cx, cy, &C);
-	if (!C.avail) sx_nb(s, list, x4 - 1, y4 - 1, &C);
-	if (shape == 1) {
-		if (y4 == 0) { if (B.ref == ref) { mvp[0] = B.mv[0]; mvp[1] = B.mv[1]; return; } }
-		else if (A.ref == ref) { mvp[0] = A.mv[0]; mvp[1] = A.mv[1]; return; }
-	} else if (shape == 2) {
-		if (x4 == 0) { if (A.ref == ref) { mvp[0] = A.mv[0]; mvp[1] = A.mv[1]; return; } }
-		else if (C.ref == ref) { mvp[0] = C.mv[0]; mvp[1] = C.mv[1]; return; }
+static inline void sx_mvpred(SliceCtx *s, int list, int x4, int y4, int w4, int ref, int shape, int mvp[2]) {
+	const MvCache *c = &s->mc;
+	const int8_t *rf = c->ref[list]; const uint32_t *mv = c->mv[list];
+	const int idx = MC_IDX(x4, y4);
+	int ic = idx - 8 + w4;
+	if (rf[ic] == -2 || ((sx_c_later[e264_blk_z(x4, y4)] >> (w4 >> 1)) & 1)) ic = idx - 9;
+	const int ra = rf[idx - 1], rb = rf[idx - 8], rc = rf[ic];
+	uint32_t pick;
+	if (shape == 1 && (y4 == 0 ? rb == ref : ra == ref)) pick = y4 == 0 ? mv[idx - 8] : mv[idx - 1];
+	else if (shape == 2 && (x4 == 0 ? ra == ref : rc == ref)) pick = x4 == 0 ? mv[idx - 1] : mv[ic];
+	else if (rb == -2 && rc == -2 && ra != -2) pick = mv[idx - 1];
+	else {
+		const int ea = ra == ref, eb = rb == ref, ec = rc == ref;
+		if (ea + eb + ec == 1) pick = ea ? mv[idx - 1] : eb ? mv[idx - 8] : mv[ic];
+		else {
+			const uint32_t a = mv[idx - 1], b = mv[idx - 8], cc = mv[ic];
+			mvp[0] = sx_median((int16_t)a, (int16_t)b, (int16_t)cc);
+			mvp[1] = sx_median((int16_t)(a >> 16), (int16_t)(b >> 16), (int16_t)(cc >> 16));
+			return;
+		}
 	}
-	if (!B.avail && !C.avail && A.avail) { mvp[0] = A.mv[0]; mvp[1] = A.mv[1]; return; }
-	int n = (A.ref == ref) + (B.ref == ref) + (C.ref == ref);
-	if (n == 1) {
-		const NbMv *p = A.ref == ref ? &A : B.ref == ref ? &B : &C;
-		mvp[0] = p->mv[0]; mvp[1] = p->mv[1]; return;
-	}
-	mvp[0] = sx_median(A.mv[0], B.mv[0], C.mv[0]);
-	mvp[1] = sx_median(A.mv[1], B.mv[1], C.mv[1]);
+	mvp[0] = (int16_t)pick; mvp[1] = (int16_t)(pick >> 16);
 }
 
-/* z-order makes 16x16, 16x8 and 8x8 partitions contiguous runs of the per-4x4 arrays */
+static inline void sx_cache_rect32(uint32_t *a, int idx, int w4, int h4, uint32_t v) { for (int y = 0; y < h4; y++) for (int x = 0; x < w4; x++) a[idx + y * 8 + x] = v; }
+static inline void sx_cache_rect16(uint16_t *a, int idx, int w4, int h4, uint16_t v) { for (int y = 0; y < h4; y++) for (int x = 0; x < w4; x++) a[idx + y * 8 + x] = v; }
+/* z-order makes 16x16, 16x8 and 8x8 partitions contiguous runs of the per-4x4 arrays (record side: skip and direct) */
 static inline void sx_fill_mv(SliceCtx *s, int list, int x4, int y4, int w4, int h4, int mvx, int mvy) {
 	uint32_t v = (uint16_t)mvx | ((uint32_t)(uint16_t)mvy << 16);
 	uint32_t *dst = (uint32_t *)s->rec->mv[list];
@@ -73,29 +130,26 @@ static inline void sx_fill_mv(SliceCtx *s, int list, int x4, int y4, int w4, int
 	if (w4 == 2 && h4 == 2) { int z0 = e264_blk_z(x4, y4); dst[z0] = dst[z0 + 1] = dst[z0 + 2] = dst[z0 + 3] = v; return; }
 	for (int y = y4; y < y4 + h4; y++) for (int x = x4; x < x4 + w4; x++) dst[e264_blk_z(x, y)] = v;
 }
-static inline void sx_fill_mvd(SliceCtx *s, int list, int x4, int y4, int w4, int h4, int dx, int dy) {
-	int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
-	if (ax > 255) ax = 255;
-	if (ay > 255) ay = 255;
-	uint16_t v = (uint16_t)(ax | (ay << 8));
-	uint16_t *dst = (uint16_t *)s->cur->mvd[list];
-	if (w4 == 4 && h4 == 4) { for (int z = 0; z < 16; z++) dst[z] = v; return; }
-	if (w4 == 4 && h4 == 2) { int z0 = y4 * 4; for (int z = z0; z < z0 + 8; z++) dst[z] = v; return; }
-	if (w4 == 2 && h4 == 2) { int z0 = e264_blk_z(x4, y4); dst[z0] = dst[z0 + 1] = dst[z0 + 2] = dst[z0 + 3] = v; return; }
-	for (int y = y4; y < y4 + h4; y++) for (int x = x4; x < x4 + w4; x++) dst[e264_blk_z(x, y)] = v;
-}
+/* reference index of an 8x8 quadrant: record and cache */
 static inline void sx_set_ref(SliceCtx *s, int list, int i8, int ref) {
 	s->rec->ref_idx[list][i8] = (int8_t)ref;
 	s->rec->ref_pic[list][i8] = ref >= 0 ? s->ref_slot[list][ref & 31] : -1;
+	int8_t *rf = s->mc.ref[list] + MC_IDX((i8 & 1) * 2, (i8 >> 1) * 2);
+	rf[0] = rf[1] = rf[8] = rf[9] = (int8_t)ref;
 }
 
 /* P_Skip (8.4.1.1) */
 static void sx_p_skip_motion(SliceCtx *s) {
-	NbMv A, B; int mvp[2] = {0, 0};
-	sx_nb(s, 0, -1, 0, &A); sx_nb(s, 0, 0, -1, &B);
-	if (s->A && s->B && !(A.ref == 0 && A.mv[0] == 0 && A.mv[1] == 0) && !(B.ref == 0 && B.mv[0] == 0 && B.mv[1] == 0))
+	int mvp[2] = {0, 0};
+	sx_cache_corners(s, 1);
+	const MvCache *c = &s->mc;
+	const int ia = MC_IDX(-1, 0), ib = MC_IDX(0, -1);
+	if (s->A && s->B && !(c->ref[0][ia] == 0 && c->mv[0][ia] == 0) && !(c->ref[0][ib] == 0 && c->mv[0][ib] == 0))
 		sx_mvpred(s, 0, 0, 0, 4, 0, 0, mvp);
-	for (int i = 0; i < 4; i++) { sx_set_ref(s, 0, i, 0); sx_set_ref(s, 1, i, -1); }
+	for (int i = 0; i < 4; i++) {
+		s->rec->ref_idx[0][i] = 0; s->rec->ref_pic[0][i] = s->ref_slot[0][0];
+		s->rec->ref_idx[1][i] = -1; s->rec->ref_pic[1][i] = -1;
+	}
 	sx_fill_mv(s, 0, 0, 0, 4, 4, mvp[0], mvp[1]);
 }
 
@@ -117,11 +171,12 @@ static void sx_direct_motion(SliceCtx *s, int mask8) {
 	static const uint8_t corner[4] = {0, 5, 10, 15};
 	if (s->direct_spatial) {
 		int ref[2], mvp[2][2] = {{0, 0}, {0, 0}};
+		const MvCache *c = &s->mc;     /* corners filled by the caller */
 		for (int l = 0; l < 2; l++) {
-			NbMv A, B, C;
-			sx_nb(s, l, -1, 0, &A); sx_nb(s, l, 0, -1, &B); sx_nb(s, l, 4, -1, &C);
-			if (!C.avail) sx_nb(s, l, -1, -1, &C);
-			ref[l] = sx_minpos(A.ref, sx_minpos(B.ref, C.ref));
+			int ic = MC_IDX(4, -1);
+			if (c->ref[l][ic] == -2) ic = MC_IDX(-1, -1);
+			int ra = c->ref[l][MC_IDX(-1, 0)], rb = c->ref[l][MC_IDX(0, -1)], rc = c->ref[l][ic];
+			ref[l] = sx_minpos(ra < 0 ? -1 : ra, sx_minpos(rb < 0 ? -1 : rb, rc < 0 ? -1 : rc));
 		}
 		if (ref[0] < 0 && ref[1] < 0) ref[0] = ref[1] = 0;
 		else for (int l = 0; l < 2; l++) if (ref[l] >= 0) sx_mvpred(s, l, 0, 0, 4, ref[l], 0, mvp[l]);
@@ -192,7 +247,7 @@ static void sx_skip_mb(SliceCtx *s) {
 	r->kind = MBK_INTER; r->flags |= MBF_SKIP;
 	memset(m->ipm, 2, 16);
 	if (s->slice_type == SLICE_P) sx_p_skip_motion(s);
-	else { m->is_direct = 1; m->direct8 = 15; sx_direct_motion(s, 15); }
+	else { m->is_direct = 1; m->direct8 = 15; if (s->direct_spatial) sx_cache_corners(s, 2); sx_direct_motion(s, 15); }
 	s->last_qp_delta_nz = 0;
 	r->coef_off = s->n_coefs;
 	sx_finish_rec(s, s->qp);
@@ -203,19 +258,45 @@ static const uint8_t sx_b_part_pred[9][2] = {{1, 1}, {2, 2}, {1, 2}, {2, 1}, {1,
 static const uint8_t sx_b_sub_pred[13] = {0, 1, 2, 3, 1, 1, 2, 2, 3, 3, 1, 2, 3};
 static const uint8_t sx_b_sub_shape[13] = {0, 0, 0, 0, 1, 2, 1, 2, 1, 2, 3, 3, 3};   /* 0 8x8, 1 8x4, 2 4x8, 3 4x4 */
 
+/* mvd_lX (9.3.2.3 UEG3, 9.3.3.1.1.7) on the register-resident engine; absum = |mvd| of the neighbours A and B */
+#define SE_EGK_BYP_R(k0, v) ({ int k_ = (k0), val_ = 0, v_ = (v); (void)v_; \
+	while (AE_BYP_R(ENCV(v_ >= (1 << k_)))) { val_ += 1 << k_; v_ -= ENCV(1 << k_); if (++k_ > 24) { s->error = 1; break; } } \
+	while (k_--) val_ += AE_BYP_R(ENCV((v_ >> k_) & 1)) << k_; \
+	val_; })
+#define SE_MVD_R(comp, absum, v) ({ const int base_ = (comp) ? 47 : 40, sum_ = (absum), w_ = (v); (void)w_; \
+	const int a_ = ENCV(w_ < 0 ? -w_ : w_); (void)a_; int n_ = 0; \
+	if (AE_R(base_ + (sum_ < 3 ? 0 : sum_ > 32 ? 2 : 1), ENCV(a_ > 0))) { \
+		int ctx_ = base_ + 3; n_ = 1; \
+		while (n_ < 9 && AE_R(ctx_, ENCV(a_ > n_))) { if (n_ < 4) ctx_++; n_++; } \
+		if (n_ >= 9) n_ = 9 + SE_EGK_BYP_R(3, ENCV(a_ - 9)); \
+		if (AE_BYP_R(ENCV(w_ < 0))) n_ = -n_; \
+	} \
+	n_; })
+
 /* mvd + prediction for one (sub-)partition */
 static void sx_mv_part(SliceCtx *s, int list, int x4, int y4, int w4, int h4, int ref, int shape) {
 	int mvp[2];
 	sx_mvpred(s, list, x4, y4, w4, ref, shape, mvp);
-	MbInfo *ma, *mb; E264MbRec *r;
-	int za = sx_locate(s, x4 - 1, y4, &ma, &r), zb = sx_locate(s, x4, y4 - 1, &mb, &r);
-	int sx = (ma ? ma->mvd[list][za][0] : 0) + (mb ? mb->mvd[list][zb][0] : 0);
-	int sy = (ma ? ma->mvd[list][za][1] : 0) + (mb ? mb->mvd[list][zb][1] : 0);
+	MvCache *c = &s->mc;
+	const int idx = MC_IDX(x4, y4);
+	const unsigned na = c->mvd[list][idx - 1], nb = c->mvd[list][idx - 8];
+	const int sx = (int)(na & 255) + (int)(nb & 255), sy = (int)(na >> 8) + (int)(nb >> 8);
 	int z = e264_blk_z(x4, y4); (void)z;
-	int dx = se_mvd(s, 0, sx, ENCV(SYN(mv[list][z][0]) - mvp[0]));
-	int dy = se_mvd(s, 1, sy, ENCV(SYN(mv[list][z][1]) - mvp[1]));
-	sx_fill_mv(s, list, x4, y4, w4, h4, mvp[0] + dx, mvp[1] + dy);
-	sx_fill_mvd(s, list, x4, y4, w4, h4, dx, dy);
+	int dx, dy;
+	if (!s->cabac) {
+		dx = VLC_SE(ENCV(SYN(mv[list][z][0]) - mvp[0]));
+		dy = VLC_SE(ENCV(SYN(mv[list][z][1]) - mvp[1]));
+	} else {
+		CR_BEGIN
+		dx = SE_MVD_R(0, sx, ENCV(SYN(mv[list][z][0]) - mvp[0]));
+		dy = SE_MVD_R(1, sy, ENCV(SYN(mv[list][z][1]) - mvp[1]));
+		CR_OUT
+	}
+	int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
+	if (ax > 255) ax = 255;
+	if (ay > 255) ay = 255;
+	sx_cache_rect32(c->mv[list], idx, w4, h4, (uint16_t)(mvp[0] + dx) | ((uint32_t)(uint16_t)(mvp[1] + dy) << 16));
+	sx_cache_rect16(c->mvd[list], idx, w4, h4, (uint16_t)(ax | (ay << 8)));
 }
 
 static void sx_intra_common_tail(SliceCtx *s, int is_i16, int cbp_known, int cbp);
@@ -302,9 +383,11 @@ static void sx_macroblock(SliceCtx *s) {
 	/* ---- inter ---- */
 	r->kind = MBK_INTER;
 	int is_b = st == SLICE_B;
+	const int nl = is_b ? 2 : 1;
 	int no_sub8 = 1;      /* noSubMbPartSizeLessThan8x8Flag */
 	if (is_b && mbt == 0) {                    /* B_Direct_16x16 */
 		m->is_direct = 1; m->direct8 = 15;
+		if (s->direct_spatial) sx_cache_corners(s, 2);
 		sx_direct_motion(s, 15);
 		no_sub8 = s->direct_8x8_inference;
 	} else if ((!is_b && mbt >= 3) || (is_b && mbt == 22)) {   /* 8x8 sub-macroblocks */
@@ -317,7 +400,8 @@ static void sx_macroblock(SliceCtx *s) {
 			if (is_b && sub[i] == 0) { m->direct8 |= 1 << i; if (!s->direct_8x8_inference) no_sub8 = 0; }
 			else if (shape8[i]) no_sub8 = 0;
 		}
-		if (m->direct8) sx_direct_motion(s, m->direct8);
+		sx_cache_fill(s, nl);
+		if (m->direct8) { sx_direct_motion(s, m->direct8); sx_cache_from_rec(s, m->direct8); }
 		for (int l = 0; l < 2; l++) for (int i = 0; i < 4; i++) {
 			if (!(pred8[i] & (1 << l))) continue;
 			int ref = 0;
@@ -335,6 +419,7 @@ static void sx_macroblock(SliceCtx *s) {
 			default: for (int j = 0; j < 4; j++) sx_mv_part(s, l, x0 + (j & 1), y0 + (j >> 1), 1, 1, ref, 0);
 			}
 		}
+		sx_cache_flush(s, nl);
 	} else {
 		/* 16x16, 16x8, 8x16 */
 		int shape, p0, p1;
@@ -343,6 +428,7 @@ static void sx_macroblock(SliceCtx *s) {
 		else { shape = 1 + ((mbt - 4) & 1); p0 = sx_b_part_pred[(mbt - 4) >> 1][0]; p1 = sx_b_part_pred[(mbt - 4) >> 1][1]; }
 		int nparts = shape ? 2 : 1;
 		int pp[2] = {p0, p1}, refs[2][2] = {{-1, -1}, {-1, -1}};
+		sx_cache_fill(s, nl);
 		for (int l = 0; l < 2; l++) for (int p = 0; p < nparts; p++) {
 			if (!(pp[p] & (1 << l))) continue;
 			int ref = 0;
@@ -360,6 +446,7 @@ static void sx_macroblock(SliceCtx *s) {
 			else if (shape == 1) sx_mv_part(s, l, 0, p * 2, 4, 2, refs[l][p], 1);
 			else sx_mv_part(s, l, p * 2, 0, 2, 4, refs[l][p], 2);
 		}
+		sx_cache_flush(s, nl);
 	}
 	int cbp = se_coded_block_pattern(s, ENCV(SYN(cbp)), 0);
 	m->cbp = (uint8_t)cbp;

@@ -232,17 +232,6 @@ static int se_egk_bypass(SliceCtx *s, int k, int v) {
 	while (k--) val += AE_BYP(ENCV((v >> k) & 1)) << k;
 	return val;
 }
-/* one mvd component; absum = sum of |mvd| of the neighbouring partitions A and B */
-static int se_mvd(SliceCtx *s, int comp, int absum, int v) {
-	if (!s->cabac) return VLC_SE(v);
-	int base = comp ? 47 : 40;
-	int a = ENCV(v < 0 ? -v : v);
-	if (!AE(base + (absum < 3 ? 0 : absum > 32 ? 2 : 1), ENCV(a > 0))) return 0;
-	int n = 1, ctx = base + 3;
-	while (n < 9 && AE(ctx, ENCV(a > n))) { if (n < 4) ctx++; n++; }
-	if (n >= 9) n = 9 + se_egk_bypass(s, 3, ENCV(a - 9));
-	return AE_BYP(ENCV(v < 0)) ? -n : n;
-}
 static int se_coded_block_pattern(SliceCtx *s, int v, int is_intra) {
 	if (!s->cabac) {
 #ifdef E264_ENCODER
@@ -524,8 +513,10 @@ static inline int16_t *sx_pool_take(SliceCtx *s, int n, int staging_off) {
 static const uint8_t sx_scan_dc2x2[4] = {0, 1, 2, 3};
 static uint8_t sx_scan_ac[15];          /* zigzag positions 1..15 */
 static uint8_t sx_scan8x8_cavlc[4][16]; /* zigzag8x8[4k+i] */
+static void sx_init_c_later(void);
 static void sx_init_tables(void) {
 	cabac_build_tables();
+	sx_init_c_later();
 	for (int k = 0; k < 15; k++) sx_scan_ac[k] = h264_zigzag4x4[k + 1];
 	for (int i = 0; i < 4; i++) for (int k = 0; k < 16; k++) sx_scan8x8_cavlc[i][k] = h264_zigzag8x8[4 * k + i];
 #ifndef E264_ENCODER
