@@ -6,6 +6,7 @@
 #define E264B_DEC_H
 #include <stdint.h>
 #include <stddef.h>
+#include <pthread.h>
 #include "records.h"
 #include "bits.h"
 #include "cabac.h"
@@ -134,6 +135,37 @@ typedef struct SliceCtx {
 	MvCache mc;
 } SliceCtx;
 
+/* One slice waiting to be parsed (threaded mode): its own copy of the RBSP and a slice context prepared by the header
+ * parser.  dep = the picture whose records a B slice reads as co-located motion (must be completely parsed first). */
+struct PicBuild;
+typedef struct SliceJob {
+	struct SliceJob *next;
+	uint8_t *rbsp;
+	struct PicBuild *dep; uint64_t dep_seq;
+	int col_slot;
+	int32_t col_slot_uid[E264_MAX_SLOTS];
+	SliceCtx sc;
+} SliceJob;
+
+/* One picture between its first slice header and its submission to the backend.  The synchronous decoder has one;
+ * with worker threads (edge264_alloc n_threads != 0) several pictures are parsed at the same time, like the
+ * reference's slice tasks (edge264_internal.h:223-261, worker_loop edge264_headers.c:450-603). */
+typedef struct PicBuild {
+	MbInfo *mbi;
+	E264MbRec *recs; int16_t *coefs; uint32_t coef_cap, n_coefs;
+	E264SliceRec *slices; int n_slices;
+	uint32_t *intra_list; int staging;
+	int mbs_done, n_intra, any_deblock; uint16_t slice_counter;
+	int slot, host_buf, conceal_ref, error;
+	/* threaded mode */
+	int in_use, closed, running, parsed;
+	uint64_t seq;
+	E264PicDesc pd;           /* filled when parsed: what goes to the backend when the picture's turn comes */
+	SliceJob *head, *tail;
+} PicBuild;
+#define E264_MAX_BUILDS 6
+#define E264_MAX_THREADS 4
+
 /* host mirror of an output picture */
 typedef struct HostBuf {
 	uint8_t *p;           /* pinned (or user) memory, frame layout of the reference */
@@ -169,11 +201,18 @@ struct Edge264Decoder {
 	SliceHeader sh;                    /* header of the slice being parsed */
 	SliceHeader first_sh;              /* header of the first slice of the current picture (marking) */
 	/* current picture build-up */
-	MbInfo *mbi; int16_t *coefs; uint32_t coef_cap; uint32_t n_coefs;
-	E264SliceRec *slices; int n_slices;
-	uint32_t *intra_list; int staging;
-	int mbs_done, n_intra, any_deblock;
-	uint16_t slice_counter;
+	PicBuild *pb;                      /* the picture slices are being added to (NULL between pictures) */
+	PicBuild builds[E264_MAX_BUILDS];
+	int n_builds;
+	/* worker threads (0 = synchronous parsing inside edge264_decode_NAL) */
+	int n_threads, stop;
+	pthread_t threads[E264_MAX_THREADS];
+	pthread_mutex_t lock, be_lock;     /* lock: builds, queues, hb[].submitted; be_lock: backend calls from several threads */
+	pthread_cond_t work_cv, done_cv;
+	uint64_t next_seq, submit_seq;     /* pictures are submitted to the backend in decoding order */
+	int submitting;                    /* a thread is inside the backend with picture submit_seq */
+	int slot_users[E264_MAX_SLOTS];    /* builds still reading or writing the records of a frame slot */
+	PicBuild *slot_build[E264_MAX_SLOTS]; uint64_t slot_build_seq[E264_MAX_SLOTS];
 	/* output */
 	HostBuf hb[E264_MAX_HOSTBUFS];
 	int outq[E264_MAX_HOSTBUFS]; int outq_n;

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include "dec.h"
 #include "h264_tables.h"
 
@@ -244,7 +245,9 @@ static int hostbuf_acquire(Edge264Decoder *d) {
 			if (!smp) return -1;
 			d->hb[i].p = (uint8_t *)smp; d->hb[i].mbs = mbs;
 		} else {
+			if (d->n_threads) pthread_mutex_lock(&d->be_lock);
 			d->hb[i].p = (uint8_t *)d->be->host_alloc(d->be_ctx, bytes);
+			if (d->n_threads) pthread_mutex_unlock(&d->be_lock);
 			if (!d->hb[i].p) return -1;
 		}
 		return i;
@@ -308,20 +311,18 @@ static void apply_marking(Edge264Decoder *d);
  * picture (a P_Skip with zero motion), or DC intra prediction when there is none.  The reference blends an
  * error-probability-weighted intra DC / re-runs P_Skip (recover_slice, edge264_headers.c:295-430); matching its
  * concealed samples is not attempted, only a deterministic, safe picture. */
-static void conceal_missing(Edge264Decoder *d) {
+static void conceal_missing(Edge264Decoder *d, PicBuild *pb) {
 	const int total = d->w_mbs * d->h_mbs;
-	Pic *cp = &d->pics[d->cur];
-	int ref = -1, best = -1;
-	for (int i = 0; i < d->n_slots; i++) if (i != d->cur && d->pics[i].in_use && d->pics[i].ref && !d->pics[i].nonexisting && d->pics[i].uid > best) { best = d->pics[i].uid; ref = i; }
-	if (d->n_slices == 0) {   /* not one slice arrived: a neutral slice record for the concealed macroblocks to point to */
-		E264SliceRec *sr = &d->slices[0];
+	const int ref = pb->conceal_ref;
+	if (pb->n_slices == 0) {   /* not one slice arrived: a neutral slice record for the concealed macroblocks to point to */
+		E264SliceRec *sr = &pb->slices[0];
 		memset(sr, 0, sizeof(*sr));
 		memset(sr->scaling4x4, 16, sizeof(sr->scaling4x4)); memset(sr->scaling8x8, 16, sizeof(sr->scaling8x8));
-		d->n_slices = 1;
+		pb->n_slices = 1;
 	}
 	for (int a = 0; a < total; a++) {
-		if (d->mbi[a].slice_id) continue;
-		E264MbRec *r = cp->recs + a;
+		if (pb->mbi[a].slice_id) continue;
+		E264MbRec *r = pb->recs + a;
 		memset(r, 0, sizeof(*r));
 		r->qp[0] = r->qp[1] = r->qp[2] = 26;
 		memset(r->ref_idx, -1, sizeof(r->ref_idx)); memset(r->ref_pic, -1, sizeof(r->ref_pic));
@@ -330,36 +331,194 @@ static void conceal_missing(Edge264Decoder *d) {
 			for (int i8 = 0; i8 < 4; i8++) { r->ref_idx[0][i8] = 0; r->ref_pic[0][i8] = (int8_t)ref; }
 		} else {
 			r->kind = MBK_I16x16; r->i16_mode = IMODE(2, 1 | 2 | 8); r->chroma_mode = IMODE(0, 1 | 2 | 8);
-			d->n_intra++;
 		}
 	}
 }
 
+/* the frame slot a lost macroblock is copied from: the most recent reference picture (header-time state) */
+static int conceal_reference(Edge264Decoder *d) {
+	int ref = -1, best = -1;
+	for (int i = 0; i < d->n_slots; i++) if (i != d->cur && d->pics[i].in_use && d->pics[i].ref && !d->pics[i].nonexisting && d->pics[i].uid > best) { best = d->pics[i].uid; ref = i; }
+	return ref;
+}
+
+/* data side of a finished picture: conceal what no slice delivered and list the intra macroblocks (build_finalize: the
+ * records are complete afterwards), then hand the picture to the backend (build_submit).  Both run in the calling
+ * thread (synchronous mode) or in a worker once every slice is parsed. */
+static void build_finalize(Edge264Decoder *d, PicBuild *pb, E264PicDesc *pd) {
+	if (pb->mbs_done < d->w_mbs * d->h_mbs) conceal_missing(d, pb);
+	memset(pd, 0, sizeof(*pd));
+	pd->width_mbs = d->w_mbs; pd->height_mbs = d->h_mbs; pd->stride_y = d->stride_y; pd->stride_c = d->stride_c;
+	pd->plane_y = d->plane_y; pd->frame_bytes = d->frame_bytes; pd->dst_slot = pb->slot;
+	pd->n_slices = pb->n_slices; pd->n_coefs = (int32_t)pb->n_coefs; pd->any_deblock = pb->any_deblock; pd->staging = pb->staging;
+	/* intra macroblocks in raster order: the device draws them from this list, so a waiting macroblock only ever waits for earlier entries */
+	const int total = d->w_mbs * d->h_mbs; int n = 0;
+	for (int a = 0; a < total; a++) if (pb->recs[a].kind != MBK_INTER) pb->intra_list[n++] = (uint32_t)a;
+	pd->n_intra = n;
+}
+static int build_submit(Edge264Decoder *d, PicBuild *pb, const E264PicDesc *pd, uint64_t *ticket) {
+	*ticket = 0;
+	if (pb->host_buf < 0) return 0;
+	int r;
+	{ PROF_BEGIN; r = d->be->submit(d->be_ctx, pd, d->hb[pb->host_buf].p, ticket); PROF_END(2); }
+	return r ? EIO : 0;
+}
+
+static void close_picture_threaded(Edge264Decoder *d);
+
 static int finish_picture(Edge264Decoder *d) {
 	if (d->cur < 0) return 0;
 	Pic *p = &d->pics[d->cur];
-	if (d->mbs_done < d->w_mbs * d->h_mbs) conceal_missing(d);
-	E264PicDesc pd; memset(&pd, 0, sizeof(pd));
-	pd.width_mbs = d->w_mbs; pd.height_mbs = d->h_mbs; pd.stride_y = d->stride_y; pd.stride_c = d->stride_c;
-	pd.plane_y = d->plane_y; pd.frame_bytes = d->frame_bytes; pd.dst_slot = d->cur;
-	pd.n_slices = d->n_slices; pd.n_coefs = (int32_t)d->n_coefs; pd.any_deblock = d->any_deblock; pd.staging = d->staging;
-	{	/* intra macroblocks in raster order: the device draws them from this list, so a waiting macroblock only ever waits for earlier entries */
-		const int total = d->w_mbs * d->h_mbs; int n = 0;
-		for (int a = 0; a < total; a++) if (p->recs[a].kind != MBK_INTER) d->intra_list[n++] = (uint32_t)a;
-		pd.n_intra = n;
-	}
 	int ret = 0;
-	if (p->host_buf >= 0) {
-		uint64_t ticket = 0;
-		{ PROF_BEGIN; if (d->be->submit(d->be_ctx, &pd, d->hb[p->host_buf].p, &ticket)) ret = EIO; PROF_END(2); }
-		d->hb[p->host_buf].ticket = ticket; d->hb[p->host_buf].submitted = 1;
-		if (!p->needed_for_output) p->host_buf = -1;   /* already in the output queue */
+	if (d->n_threads) close_picture_threaded(d);
+	else {
+		PicBuild *pb = d->pb;
+		pb->conceal_ref = conceal_reference(d);
+		if (p->host_buf >= 0) {
+			uint64_t ticket = 0; E264PicDesc pd;
+			build_finalize(d, pb, &pd);
+			ret = build_submit(d, pb, &pd, &ticket);
+			d->hb[p->host_buf].ticket = ticket; __atomic_store_n(&d->hb[p->host_buf].submitted, 1, __ATOMIC_RELEASE);
+		}
+		pb->in_use = 0;
 	}
+	d->pb = NULL;
+	if (p->host_buf >= 0 && !p->needed_for_output) p->host_buf = -1;   /* already in the output queue */
 	apply_marking(d);
 	int c = d->cur;
 	d->cur = -1;
 	slot_release_if_unused(d, c);
 	return ret;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* worker threads: several pictures parsed at the same time                                      */
+/* ------------------------------------------------------------------------------------------ */
+/* The calling thread parses headers, runs the decoded-picture-buffer logic and queues slices; workers parse slice
+ * data.  One worker owns a picture at a time (its slices share the coefficient pool and run in order); pictures are
+ * handed to the backend strictly in decoding order.  A B slice waits until its co-located picture is completely
+ * parsed (its records are the motion data direct prediction reads); nothing else depends on another picture at parse
+ * time — pixels are the device's business.  Reference counterpart: task dependencies + worker_loop,
+ * edge264_internal.h:1196-1226, edge264_headers.c:450-603. */
+static PicBuild *build_acquire(Edge264Decoder *d, int slot) {
+	if (!d->n_threads) { PicBuild *pb = &d->builds[0]; pb->in_use = 1; return pb; }
+	pthread_mutex_lock(&d->lock);
+	PicBuild *pb = NULL;
+	for (;;) {
+		/* the slot's records may still be written by its previous picture's parser or read as co-located motion */
+		if (d->slot_users[slot] == 0) for (int i = 0; i < d->n_builds && !pb; i++) if (!d->builds[i].in_use) pb = &d->builds[i];
+		if (pb) break;
+		pthread_cond_wait(&d->done_cv, &d->lock);
+	}
+	MbInfo *mbi = pb->mbi;
+	memset(pb, 0, sizeof(*pb));
+	pb->mbi = mbi; pb->in_use = 1; pb->seq = d->next_seq++;
+	d->slot_users[slot]++; d->slot_build[slot] = pb; d->slot_build_seq[slot] = pb->seq;
+	pthread_mutex_unlock(&d->lock);
+	return pb;
+}
+static void slice_enqueue(Edge264Decoder *d, PicBuild *pb, SliceJob *job, int col_slot) {
+	pthread_mutex_lock(&d->lock);
+	job->next = NULL; job->dep = NULL; job->dep_seq = 0; job->col_slot = col_slot;
+	if (col_slot >= 0) {
+		d->slot_users[col_slot]++;
+		if (d->slot_build[col_slot] && d->slot_build[col_slot] != pb) { job->dep = d->slot_build[col_slot]; job->dep_seq = d->slot_build_seq[col_slot]; }
+	}
+	if (pb->tail) pb->tail->next = job; else pb->head = job;
+	pb->tail = job;
+	pthread_cond_broadcast(&d->work_cv);
+	pthread_mutex_unlock(&d->lock);
+}
+static void close_picture_threaded(Edge264Decoder *d) {
+	pthread_mutex_lock(&d->lock);
+	d->pb->conceal_ref = conceal_reference(d);
+	d->pb->closed = 1;
+	pthread_cond_broadcast(&d->work_cv);
+	pthread_mutex_unlock(&d->lock);
+}
+/* wait until every picture has been parsed and handed to the backend (flush, end of stream, format change) */
+static void threads_drain(Edge264Decoder *d) {
+	if (!d->n_threads) return;
+	pthread_mutex_lock(&d->lock);
+	for (;;) {
+		int busy = 0;
+		for (int i = 0; i < d->n_builds; i++) busy |= d->builds[i].in_use;
+		if (!busy) break;
+		pthread_cond_wait(&d->done_cv, &d->lock);
+	}
+	pthread_mutex_unlock(&d->lock);
+}
+static inline int job_ready(const SliceJob *j) { return !j->dep || j->dep->seq != j->dep_seq || j->dep->parsed || !j->dep->in_use; }
+static void *worker_main(void *arg) {
+	Edge264Decoder *d = (Edge264Decoder *)arg;
+	pthread_mutex_lock(&d->lock);
+	for (;;) {
+		PicBuild *pb = NULL;
+		while (!d->stop) {
+			for (int i = 0; i < d->n_builds; i++) {     /* the oldest picture with something to do */
+				PicBuild *b = &d->builds[i];
+				if (!b->in_use || b->running || b->parsed) continue;
+				if (!(b->head ? job_ready(b->head) : b->closed)) continue;
+				if (!pb || b->seq < pb->seq) pb = b;
+			}
+			if (pb) break;
+			pthread_cond_wait(&d->work_cv, &d->lock);
+		}
+		if (d->stop) break;
+		pb->running = 1;
+		while (pb->head && job_ready(pb->head)) {
+			SliceJob *job = pb->head;
+			pb->head = job->next; if (!pb->head) pb->tail = NULL;
+			pthread_mutex_unlock(&d->lock);
+			job->sc.n_coefs = pb->n_coefs;      /* the slices of a picture share one coefficient pool */
+			int n = e264_parse_slice_data(&job->sc);
+			pb->n_coefs = job->sc.n_coefs; pb->n_intra += job->sc.n_intra;
+			if (n > 0) pb->mbs_done += n;
+			if (job->sc.error) pb->error = job->sc.error;
+			free(job->rbsp);
+			pthread_mutex_lock(&d->lock);
+			if (job->col_slot >= 0) { d->slot_users[job->col_slot]--; pthread_cond_broadcast(&d->done_cv); }
+			free(job);
+		}
+		if (!pb->head && pb->closed) {
+			pthread_mutex_unlock(&d->lock);
+			build_finalize(d, pb, &pb->pd);
+			pthread_mutex_lock(&d->lock);
+			pb->parsed = 1; pb->running = 0;      /* its records are complete: B pictures may read them */
+			pthread_cond_broadcast(&d->work_cv);
+			/* hand parsed pictures to the backend in decoding order; whoever completes the oldest one also sends the
+			 * ones that were waiting behind it, so no worker ever sleeps on the order */
+			while (!d->submitting) {
+				PicBuild *q = NULL;
+				for (int i = 0; i < d->n_builds; i++) if (d->builds[i].in_use && d->builds[i].parsed && d->builds[i].seq == d->submit_seq) q = &d->builds[i];
+				if (!q) break;
+				uint64_t ticket = 0;
+				d->submitting = 1;
+				pthread_mutex_unlock(&d->lock);
+				pthread_mutex_lock(&d->be_lock);
+				build_submit(d, q, &q->pd, &ticket);
+				pthread_mutex_unlock(&d->be_lock);
+				pthread_mutex_lock(&d->lock);
+				if (q->host_buf >= 0) { d->hb[q->host_buf].ticket = ticket; __atomic_store_n(&d->hb[q->host_buf].submitted, 1, __ATOMIC_RELEASE); }
+				d->submit_seq++; d->submitting = 0;
+				d->slot_users[q->slot]--;
+				q->in_use = 0;
+				pthread_cond_broadcast(&d->done_cv);
+			}
+		} else pb->running = 0;               /* more slices to come, or the next one waits for its co-located picture */
+	}
+	pthread_mutex_unlock(&d->lock);
+	return NULL;
+}
+static void threads_stop(Edge264Decoder *d) {
+	if (!d->n_threads) return;
+	threads_drain(d);
+	pthread_mutex_lock(&d->lock);
+	d->stop = 1;
+	pthread_cond_broadcast(&d->work_cv); pthread_cond_broadcast(&d->done_cv);
+	pthread_mutex_unlock(&d->lock);
+	for (int i = 0; i < d->n_threads; i++) pthread_join(d->threads[i], NULL);
+	d->n_threads = 0;
 }
 
 /* 8.2.5 decoded reference picture marking, applied when the picture is complete.  Mirrors the
@@ -415,6 +574,7 @@ static void apply_marking(Edge264Decoder *d) {
 /* ------------------------------------------------------------------------------------------ */
 static int bump_all(Edge264Decoder *d) {
 	if (d->cur >= 0) finish_picture(d);
+	threads_drain(d);
 	while (bump_frame(d, -1));
 	if (d->outq_n) return ENOBUFS;
 	/* frames the application still holds (borrowed, or handed out until the next decode_NAL) keep their buffers: a
@@ -432,15 +592,28 @@ static int configure_sequence(Edge264Decoder *d, const SPS *s, int keep_numberin
 	d->stride_c = w; if (!(d->stride_c & 4095)) d->stride_c += 16;       /* headers.c:2035-2037 pads by 8; 16 keeps both chroma planes 8-byte aligned for vector stores and TMA */
 	d->plane_y = d->stride_y * h; d->plane_c = d->stride_c * (h >> 1);
 	d->frame_bytes = d->plane_y + d->plane_c + 16;
-	d->n_slots = s->max_num_ref_frames + 2;
+	if (d->n_threads) pthread_mutex_lock(&d->lock);      /* idle workers scan builds[0..n_builds) */
+	d->n_builds = d->n_threads ? d->n_threads + 2 : 1;
+	if (d->n_builds > E264_MAX_BUILDS) d->n_builds = E264_MAX_BUILDS;
+	if (d->n_threads) pthread_mutex_unlock(&d->lock);
+	/* a picture keeps its slot (and the slot's record buffer) until it is handed to the device: parsing ahead needs one spare slot per picture in flight */
+	d->n_slots = s->max_num_ref_frames + 2 + (d->n_threads ? d->n_builds : 0);
 	if (d->n_slots > E264_MAX_SLOTS) d->n_slots = E264_MAX_SLOTS;
 	E264PicDesc g; memset(&g, 0, sizeof(g));
 	g.width_mbs = d->w_mbs; g.height_mbs = d->h_mbs; g.stride_y = d->stride_y; g.stride_c = d->stride_c; g.plane_y = d->plane_y; g.frame_bytes = d->frame_bytes;
+	g.staging = d->n_threads ? (d->n_threads + 2 > E264_MAX_BUILDS ? E264_MAX_BUILDS : d->n_threads + 2) + 2 : 0;   /* staging areas wanted: one per picture being parsed + two in flight on the device; 0 = the backend's default */
 	hostbufs_free_all(d);
 	if (d->be->configure(d->be_ctx, &g, d->n_slots)) return ENOMEM;
-	free(d->mbi);
-	d->mbi = (MbInfo *)calloc((size_t)d->w_mbs * d->h_mbs, sizeof(MbInfo));
-	if (!d->mbi) return ENOMEM;
+	int oom = 0;
+	if (d->n_threads) pthread_mutex_lock(&d->lock);
+	for (int i = 0; i < E264_MAX_BUILDS; i++) {
+		free(d->builds[i].mbi); memset(&d->builds[i], 0, sizeof(d->builds[i]));
+		if (i < d->n_builds && !(d->builds[i].mbi = (MbInfo *)calloc((size_t)d->w_mbs * d->h_mbs, sizeof(MbInfo)))) oom = 1;
+	}
+	d->pb = NULL;
+	memset(d->slot_users, 0, sizeof(d->slot_users)); memset(d->slot_build, 0, sizeof(d->slot_build));
+	if (d->n_threads) pthread_mutex_unlock(&d->lock);
+	if (oom) return ENOMEM;
 	memset(d->pics, 0, sizeof(d->pics));
 	for (int i = 0; i < E264_MAX_SLOTS; i++) d->pics[i].host_buf = -1;
 	d->cur = -1;
@@ -615,11 +788,21 @@ static void build_ref_lists(Edge264Decoder *d, const SliceHeader *h, int lists[2
 /* slice NAL                                                                                    */
 /* ------------------------------------------------------------------------------------------ */
 static int find_free_slot(Edge264Decoder *d) {
+	if (d->n_threads) {   /* prefer a slot no parser is still using: taking a busy one would wait for its picture to be submitted */
+		int pick = -1;
+		pthread_mutex_lock(&d->lock);
+		for (int i = 0; i < d->n_slots && pick < 0; i++) if (!d->pics[i].in_use && d->slot_users[i] == 0) pick = i;
+		pthread_mutex_unlock(&d->lock);
+		if (pick >= 0) return pick;
+	}
 	for (int i = 0; i < d->n_slots; i++) if (!d->pics[i].in_use) return i;
 	return -1;
 }
 
-static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, BitReader *b) {
+static PicBuild *build_acquire(Edge264Decoder *d, int slot);
+static void slice_enqueue(Edge264Decoder *d, PicBuild *pb, SliceJob *job, int col_slot);
+
+static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, BitReader *b, SliceJob *job) {
 	SliceHeader *h = &d->sh;
 	const PPS *p = NULL;
 	int ret = parse_slice_header(d, b, nal_unit_type, nal_ref_idc, h, &p);
@@ -638,7 +821,14 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 	}
 
 	if (d->cur < 0) {
-		if (d->outq_n > 16) return ENOBUFS;
+		if (d->outq_n > 16) {
+			if (d->n_threads) {   /* the frame the application is told to fetch may still be with a parser: wait for it here, not in a polling loop */
+				pthread_mutex_lock(&d->lock);
+				while (!__atomic_load_n(&d->hb[d->outq[0]].submitted, __ATOMIC_ACQUIRE)) pthread_cond_wait(&d->done_cv, &d->lock);
+				pthread_mutex_unlock(&d->lock);
+			}
+			return ENOBUFS;
+		}
 		int hbuf = hostbuf_acquire(d);
 		if (hbuf < 0) return ENOBUFS;
 		/* frame_num and POC (8.2.1), with absolute (unwrapped) frame numbers like the reference (headers.c:1059) */
@@ -682,6 +872,7 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 				for (int i = 0; i < d->n_slots; i++) if (d->pics[i].in_use && d->pics[i].ref == 1 && (old < 0 || d->pics[i].frame_num < d->pics[old].frame_num)) old = i;
 				d->pics[old].ref = 0; slot_release_if_unused(d, old);
 			}
+			if (gap_frames > 0) threads_drain(d);   /* the fills below go straight to the device: every earlier picture must be on its way first */
 			for (int fn = frame_num_abs - gap_frames; fn < frame_num_abs; fn++) {
 				int sl = find_free_slot(d);
 				while (sl < 0 && bump_frame(d, -1)) sl = find_free_slot(d);
@@ -698,7 +889,7 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 				}
 				np->poc = np->poc_dec = np->poc_top = np->poc_top_dec = npoc;
 				for (int i = 0; i < E264_MAX_SLOTS; i++) np->slot_uid[i] = -1;
-				if (d->be->fill_slot) d->be->fill_slot(d->be_ctx, sl, 0, 0);
+				if (d->be->fill_slot) { if (d->n_threads) pthread_mutex_lock(&d->be_lock); d->be->fill_slot(d->be_ctx, sl, 0, 0); if (d->n_threads) pthread_mutex_unlock(&d->be_lock); }
 			}
 			d->prev_ref_frame_num = frame_num_abs - 1;   /* the last inserted frame is the previous reference frame now (headers.c:1131) */
 		}
@@ -730,13 +921,23 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 		d->cur = slot; d->cur_idr = idr; d->cur_nal_ref_idc = nal_ref_idc;
 		d->first_sh = *h;
 		for (int i = 0; i < E264_MAX_SLOTS; i++) cp->slot_uid[i] = d->pics[i].in_use ? d->pics[i].uid : -1;
+		PicBuild *pb = build_acquire(d, slot);     /* threaded mode: may wait for a parser to finish */
 		E264Staging stg; memset(&stg, 0, sizeof(stg));
-		{ PROF_BEGIN; int ar = d->be->acquire_staging(d->be_ctx, slot, &stg); PROF_END(1); if (ar) return ENOMEM; }
-		cp->recs = stg.recs; d->coefs = stg.coefs; d->slices = stg.slices; d->intra_list = stg.intra_list; d->staging = stg.handle;
-		d->coef_cap = stg.coef_capacity; d->n_coefs = 0; d->n_slices = 0; d->mbs_done = 0; d->n_intra = 0; d->any_deblock = 0;
-		{ PROF_BEGIN; memset(d->mbi, 0, (size_t)d->w_mbs * d->h_mbs * sizeof(MbInfo)); PROF_END(4); }
+		int ar;
+		{ PROF_BEGIN; if (d->n_threads) pthread_mutex_lock(&d->be_lock); ar = d->be->acquire_staging(d->be_ctx, slot, &stg); if (d->n_threads) pthread_mutex_unlock(&d->be_lock); PROF_END(1); }
+		if (ar) {   /* give the build back as if it had never been taken (no later picture exists yet) */
+			if (d->n_threads) { pthread_mutex_lock(&d->lock); d->next_seq--; d->slot_users[slot]--; d->slot_build[slot] = NULL; pb->in_use = 0; pthread_mutex_unlock(&d->lock); }
+			else pb->in_use = 0;
+			cp->in_use = 0; d->cur = -1; d->hb[hbuf].state = 0;
+			return ENOMEM;
+		}
+		cp->recs = stg.recs;
+		pb->recs = stg.recs; pb->coefs = stg.coefs; pb->slices = stg.slices; pb->intra_list = stg.intra_list; pb->staging = stg.handle;
+		pb->coef_cap = stg.coef_capacity; pb->n_coefs = 0; pb->n_slices = 0; pb->mbs_done = 0; pb->n_intra = 0; pb->any_deblock = 0; pb->error = 0;
+		pb->slot = slot; pb->host_buf = hbuf; pb->conceal_ref = -1; pb->slice_counter = 0;
+		{ PROF_BEGIN; memset(pb->mbi, 0, (size_t)d->w_mbs * d->h_mbs * sizeof(MbInfo)); PROF_END(4); }
 		/* records need no clearing: every macroblock of a complete picture rewrites its own (sx_one_mb) */
-		d->slice_counter = 0;
+		d->pb = pb;
 
 		/* IDR / MMCO5: every earlier picture leaves in output order first (reference headers.c:632, 680) */
 		int has_mmco5 = 0;
@@ -762,27 +963,29 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 		if (has_mmco5) d->prev_ref_frame_num = 0;
 	}
 
-	if (d->n_slices >= E264_MAX_SLICES) return ENOTSUP;
+	PicBuild *pb = d->pb;
+	if (pb->n_slices >= E264_MAX_SLICES) return ENOTSUP;
 	Pic *cp = &d->pics[d->cur];
 	int total = d->w_mbs * d->h_mbs;
 	if (h->first_mb >= total) return EBADMSG;
 
 	/* slice record: deblocking, weights, scaling lists */
-	E264SliceRec *sr = &d->slices[d->n_slices];
+	E264SliceRec *sr = &pb->slices[pb->n_slices];
 	memset(sr, 0, sizeof(*sr));
 	sr->filter_offset_a = (int8_t)h->filter_offset_a; sr->filter_offset_b = (int8_t)h->filter_offset_b;
 	sr->deblock_idc = (uint8_t)h->deblock_idc; sr->slice_type = (uint8_t)h->slice_type;
 	merge_scaling(s, p, sr);
 
-	SliceCtx *c = &d->sc;
+	SliceCtx *c = job ? &job->sc : &d->sc;
+	int col_slot = -1;
 	c->cabac = p->entropy_coding_mode;
 	c->w_mbs = d->w_mbs; c->h_mbs = d->h_mbs;
-	c->slice_type = h->slice_type; c->slice_id = ++d->slice_counter; c->slice_idx = d->n_slices;
+	c->slice_type = h->slice_type; c->slice_id = ++pb->slice_counter; c->slice_idx = pb->n_slices;
 	c->num_ref[0] = h->num_ref[0]; c->num_ref[1] = h->num_ref[1];
 	c->direct_spatial = h->direct_spatial; c->direct_8x8_inference = s->direct_8x8_inference; c->transform_8x8_mode = p->transform_8x8_mode;
 	c->qp = h->slice_qp; c->chroma_qp_offset[0] = p->chroma_qp_index_offset[0]; c->chroma_qp_offset[1] = p->chroma_qp_index_offset[1];
 	c->deblock_idc = h->deblock_idc; c->cur_poc = cp->poc_dec;
-	c->mbi = d->mbi; c->recs = cp->recs; c->coefs = d->coefs; c->n_coefs = d->n_coefs; c->coef_cap = d->coef_cap;
+	c->mbi = pb->mbi; c->recs = pb->recs; c->coefs = pb->coefs; c->n_coefs = job ? 0 : pb->n_coefs; c->coef_cap = pb->coef_cap;   /* threaded: the worker continues the pool where the previous slice ended */
 	c->col_recs = NULL; c->col_slot_uid = NULL; c->error = 0; c->n_intra = 0;
 	memset(c->ref_slot, -1, sizeof(c->ref_slot)); memset(c->ref_long, 0, sizeof(c->ref_long));
 	for (int l = 0; l < 2; l++) for (int i = 0; i < 32; i++) { c->ref_uid[l][i] = -1; c->ref_poc[l][i] = 0; }
@@ -794,7 +997,13 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 			if (sl < 0) continue;   /* missing reference: MC will read slot -1 -> treated as the current slot by the backend */
 			c->ref_slot[l][i] = (int8_t)sl; c->ref_uid[l][i] = d->pics[sl].uid; c->ref_poc[l][i] = d->pics[sl].poc; c->ref_long[l][i] = d->pics[sl].ref == 2;
 		}
-		if (h->slice_type == 1 && lists[1][0] >= 0) { c->col_recs = d->pics[lists[1][0]].recs; c->col_slot_uid = d->pics[lists[1][0]].slot_uid; if (d->pics[lists[1][0]].nonexisting) c->col_recs = NULL; }
+		if (h->slice_type == 1 && lists[1][0] >= 0) {
+			c->col_recs = d->pics[lists[1][0]].recs; c->col_slot_uid = d->pics[lists[1][0]].slot_uid;
+			if (d->pics[lists[1][0]].nonexisting) c->col_recs = NULL; else col_slot = lists[1][0];
+			if (job) {   /* the co-located picture's Pic entry may be recycled before this slice is parsed: keep a private copy of the uid table */
+				memcpy(job->col_slot_uid, d->pics[lists[1][0]].slot_uid, sizeof(job->col_slot_uid)); c->col_slot_uid = job->col_slot_uid;
+			}
+		}
 		int wp = h->slice_type == 0 ? p->weighted_pred_flag : p->weighted_bipred_idc;
 		sr->wp_mode = (uint8_t)wp; sr->luma_log2_wd = (uint8_t)h->luma_log2_wd; sr->chroma_log2_wd = (uint8_t)h->chroma_log2_wd;
 		if (wp == 1) for (int l = 0; l < 2; l++) for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) { sr->wp_w[l][i][k] = h->w[l][i][k]; sr->wp_o[l][i][k] = h->o[l][i][k]; }
@@ -817,18 +1026,22 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 			}
 		}
 	}
-	d->n_slices++;
-	if (h->deblock_idc != 1) d->any_deblock = 1;
+	pb->n_slices++;
+	if (h->deblock_idc != 1) pb->any_deblock = 1;
 
 	/* slice data */
 	c->br = *b;
 	c->mbaddr = h->first_mb;
 	c->cabac_init_idc_col = h->slice_type == 2 ? 0 : 1 + h->cabac_init_idc;
+	if (job) {   /* threaded mode: a worker parses the slice data; the picture is closed by the next picture's first slice or a flush */
+		slice_enqueue(d, pb, job, col_slot);
+		return 0;
+	}
 	int n; { PROF_BEGIN; n = e264_parse_slice_data(c); PROF_END(0); }
-	d->n_coefs = c->n_coefs; d->n_intra += c->n_intra;
-	if (n > 0) d->mbs_done += n;
+	pb->n_coefs = c->n_coefs; pb->n_intra += c->n_intra;
+	if (n > 0) pb->mbs_done += n;
 	if (c->error) ret = c->error == 2 ? ENOMEM : EBADMSG;
-	if (d->mbs_done >= total) { int r2 = finish_picture(d); if (!ret) ret = r2; }
+	if (pb->mbs_done >= total) { int r2 = finish_picture(d); if (!ret) ret = r2; }
 	return ret;
 }
 
@@ -837,7 +1050,7 @@ static int decode_slice(Edge264Decoder *d, int nal_unit_type, int nal_ref_idc, B
 /* ------------------------------------------------------------------------------------------ */
 Edge264Decoder *edge264_alloc(int n_threads, Edge264LogCb log_cb, void *log_arg, int log_mbs,
                               Edge264AllocCb alloc_cb, Edge264FreeCb free_cb, void *alloc_arg) {
-	(void)n_threads; (void)log_mbs;
+	(void)log_mbs;
 	if (prof_on < 0) { const char *e = getenv("E264_HOST_PROFILE"); prof_on = e && atoi(e); }
 	if (log_cb) return NULL;   /* like a reference build without the logs variant (edge264.c:217-220) */
 	Edge264Decoder *d = (Edge264Decoder *)calloc(1, sizeof(*d));
@@ -847,11 +1060,24 @@ Edge264Decoder *edge264_alloc(int n_threads, Edge264LogCb log_cb, void *log_arg,
 	d->cur = -1; d->pending_release = -1; d->prev_ref_frame_num = -1; d->q_prev_ref_frame_num = -1;
 	d->be = e264_default_backend();
 	if (!d->be || d->be->create(&d->be_ctx)) { free(d); return NULL; }
+	d->n_builds = 1;
+	/* n_threads as in the reference (edge264.c:223-257): 0 = parse inside edge264_decode_NAL, < 0 = one worker per CPU up
+	 * to the limit, > 0 = that many workers (here they parse slice data ahead; reconstruction is the device's) */
+	if (n_threads < 0) { long n = sysconf(_SC_NPROCESSORS_ONLN); n_threads = n < 1 ? 1 : (int)n; }
+	if (n_threads > E264_MAX_THREADS) n_threads = E264_MAX_THREADS;
+	if (n_threads > 0) {
+		pthread_mutex_init(&d->lock, NULL); pthread_mutex_init(&d->be_lock, NULL);
+		pthread_cond_init(&d->work_cv, NULL); pthread_cond_init(&d->done_cv, NULL);
+		d->n_threads = n_threads;
+		for (int i = 0; i < n_threads; i++) if (pthread_create(&d->threads[i], NULL, worker_main, d)) { d->n_threads = i; threads_stop(d); d->be->destroy(d->be_ctx); free(d); return NULL; }
+	}
 	return d;
 }
 
 void edge264_flush(Edge264Decoder *d) {
 	if (!d) return;
+	if (d->cur >= 0 && d->n_threads) finish_picture(d);
+	threads_drain(d);
 	/* drop every picture and the sequence state, keep parameter sets (reference edge264.c:261-270 clears them too) */
 	for (int i = 0; i < E264_MAX_SLOTS; i++) { d->pics[i].in_use = 0; d->pics[i].host_buf = -1; }
 	for (int i = 0; i < E264_MAX_HOSTBUFS; i++) if (d->hb[i].state != 3 || !d->hb[i].borrowed) d->hb[i].state = 0;
@@ -866,9 +1092,11 @@ void edge264_free(Edge264Decoder **pd) {
 	if (!pd || !(d = *pd)) return;
 	*pd = NULL;
 	if (prof_on > 0) { for (int i = 0; i < 6; i++) if (prof_n[i]) fprintf(stderr, "host profile: %-18s %8.3f ms total %6ld calls %8.1f us/call\n", prof_names[i], 1e3 * prof_t[i], prof_n[i], 1e6 * prof_t[i] / prof_n[i]); memset(prof_t, 0, sizeof(prof_t)); memset(prof_n, 0, sizeof(prof_n)); }
+	if (d->n_threads) { if (d->cur >= 0) finish_picture(d); threads_stop(d); }
 	hostbufs_free_all(d);
 	d->be->destroy(d->be_ctx);
-	free(d->mbi); free(d->rbsp); free(d);
+	for (int i = 0; i < E264_MAX_BUILDS; i++) free(d->builds[i].mbi);
+	free(d->rbsp); free(d);
 }
 
 int edge264_decode_NAL(Edge264Decoder *d, const uint8_t *buf, const uint8_t *end, Edge264UnrefCb unref_cb, void *unref_arg) {
@@ -880,6 +1108,19 @@ int edge264_decode_NAL(Edge264Decoder *d, const uint8_t *buf, const uint8_t *end
 	}
 	int nal_ref_idc = buf[0] >> 5, nal_unit_type = buf[0] & 31;
 	size_t n = (size_t)(end - buf) - 1;
+	if (d->n_threads && (nal_unit_type == 1 || nal_unit_type == 5)) {   /* the slice is parsed later, from its own copy of the payload */
+		SliceJob *job = (SliceJob *)calloc(1, sizeof(SliceJob));
+		uint8_t *rb = job ? (uint8_t *)malloc(n + 64) : NULL;
+		if (!rb) { free(job); return ENOMEM; }
+		size_t rn = e264_unescape(rb, buf + 1, n);
+		memset(rb + rn, 0, 32);
+		job->rbsp = rb;
+		BitReader b; br_init(&b, rb, rn);
+		int ret = decode_slice(d, nal_unit_type, nal_ref_idc, &b, job);
+		if (ret) { free(rb); free(job); }      /* not queued */
+		else if (unref_cb) unref_cb(0, unref_arg);
+		return ret;
+	}
 	if (d->rbsp_cap < n + 64) { free(d->rbsp); d->rbsp_cap = n * 2 + 4096; d->rbsp = (uint8_t *)malloc(d->rbsp_cap); if (!d->rbsp) { d->rbsp_cap = 0; return ENOMEM; } }
 	size_t rn = e264_unescape(d->rbsp, buf + 1, n);
 	memset(d->rbsp + rn, 0, 32);
@@ -887,7 +1128,7 @@ int edge264_decode_NAL(Edge264Decoder *d, const uint8_t *buf, const uint8_t *end
 	int ret;
 	switch (nal_unit_type) {
 	case 1: case 5:
-		ret = decode_slice(d, nal_unit_type, nal_ref_idc, &b);
+		ret = decode_slice(d, nal_unit_type, nal_ref_idc, &b, NULL);
 		if (ret == 0 && unref_cb) unref_cb(0, unref_arg);   /* parsing is synchronous: the NAL bytes are no longer needed */
 		return ret;
 	case 7: {
@@ -918,7 +1159,7 @@ int edge264_get_frame(Edge264Decoder *d, Edge264Frame *out, int borrow) {
 	if (d->outq_n == 0) return ENOMSG;
 	int hbuf = d->outq[0];
 	HostBuf *hb = &d->hb[hbuf];
-	if (!hb->submitted) return ENOMSG;   /* queued at insertion but still being parsed */
+	if (!__atomic_load_n(&hb->submitted, __ATOMIC_ACQUIRE)) return ENOMSG;   /* queued at insertion but still being parsed */
 	{ PROF_BEGIN; int wr = d->be->wait(d->be_ctx, hb->ticket); PROF_END(3); if (wr) return EIO; }
 	memmove(d->outq, d->outq + 1, (size_t)(--d->outq_n) * sizeof(int));
 	*out = d->out_fmt;

@@ -24,7 +24,7 @@ extern "C" {
 }
 #include "../../include/e264b_recon.h"
 
-#define NSTAGE 4
+#define NSTAGE 8            /* staging areas allocated at most; a decoder uses n_stage of them */
 #define NTICK 64
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "edge264_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -1; } } while (0)
 
@@ -43,7 +43,7 @@ struct E264bDevice {
 	uint8_t *d_frames;
 	void *d_tmaps;               /* CUtensorMap[n_slots][6] over the frame pool, or NULL when the geometry does not fit TMA's rules */
 	E264MbRec *h_recs[E264_MAX_SLOTS]; cudaEvent_t rec_up[E264_MAX_SLOTS]; bool rec_busy[E264_MAX_SLOTS];
-	Staging st[NSTAGE]; int stage;
+	Staging st[NSTAGE]; int stage, n_stage;
 	unsigned *d_sync;            /* [0..7] tickets (0 inter, 1 deblock, 2 intra), [8] err, [16..) flags[nmb] + deblocking progress[2 * h_mbs] */
 	size_t sync_words;
 	unsigned epoch;
@@ -194,13 +194,14 @@ extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots
 	for (auto &h : c->host_free_list) cudaFreeHost(h.first);
 	c->host_free_list.clear();
 	c->g = *g; c->n_slots = n_slots; c->nmb = (size_t)g->width_mbs * g->height_mbs;
+	c->n_stage = g->staging > 0 ? (g->staging < NSTAGE ? g->staging : NSTAGE) : 4;   /* 4 for a synchronous parser; more when pictures are parsed ahead */
 	c->coef_cap = (uint32_t)(c->nmb * 408);
 	size_t pool = (size_t)g->frame_bytes * n_slots;
 	CK(cudaMalloc(&c->d_frames, pool + 256));
 	CK(cudaMemsetAsync(c->d_frames, 128, pool + 256, c->stream));
 	if (build_tensor_maps(c)) return -1;
 	for (int i = 0; i < n_slots; i++) CK(cudaHostAlloc(&c->h_recs[i], c->nmb * sizeof(E264MbRec), cudaHostAllocDefault));
-	for (int i = 0; i < NSTAGE; i++) {
+	for (int i = 0; i < c->n_stage; i++) {
 		Staging *s = &c->st[i];
 		CK(cudaMalloc(&s->d_recs, c->nmb * sizeof(E264MbRec)));
 		CK(cudaMalloc(&s->d_coefs, (size_t)c->coef_cap * 2 + 64));
@@ -244,7 +245,7 @@ extern "C" void e264b_host_free(E264bDevice *c, void *p) {
 
 extern "C" int e264b_acquire_staging(E264bDevice *c, int slot, E264Staging *out) {
 	CK(cudaSetDevice(c->dev));
-	c->stage = (c->stage + 1) % NSTAGE;
+	c->stage = (c->stage + 1) % c->n_stage;
 	Staging *s = &c->st[c->stage];
 	if (s->busy) { CK(cudaEventSynchronize(s->done)); s->busy = false; }
 	if (c->rec_busy[slot]) { CK(cudaEventSynchronize(c->rec_up[slot])); c->rec_busy[slot] = false; }
@@ -320,7 +321,7 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 
 extern "C" int e264b_submit(E264bDevice *c, const E264PicDesc *pd, uint8_t *host_out, uint64_t *ticket) {
 	CK(cudaSetDevice(c->dev));
-	if (pd->staging < 0 || pd->staging >= NSTAGE) return -1;
+	if (pd->staging < 0 || pd->staging >= c->n_stage) return -1;
 	Staging *s = &c->st[pd->staging];
 	size_t rec_bytes = c->nmb * sizeof(E264MbRec), coef_bytes = ((size_t)pd->n_coefs * 2 + 15) & ~(size_t)15, sl_bytes = (size_t)pd->n_slices * sizeof(E264SliceRec);
 	CK(cudaMemcpyAsync(s->d_recs, c->h_recs[pd->dst_slot], rec_bytes, cudaMemcpyHostToDevice, c->stream));

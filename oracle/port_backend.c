@@ -9,20 +9,24 @@
 
 void port_recon_picture(uint8_t *frames, const E264PicDesc *pd, const E264MbRec *recs, const int16_t *coefs, const E264SliceRec *slices);
 
+#define PORT_NSTAGE 8
 typedef struct PortCtx {
 	E264PicDesc g; int n_slots;
 	uint8_t *frames_alloc, *frames;
 	E264MbRec *recs[E264_MAX_SLOTS];
-	int16_t *coefs; uint32_t coef_cap;
-	E264SliceRec *slices;
-	uint32_t *intra_list;
+	/* staging areas, handed out round robin like the CUDA runtime's (a threaded decoder fills several pictures at once) */
+	int16_t *coefs[PORT_NSTAGE]; uint32_t coef_cap;
+	E264SliceRec *slices[PORT_NSTAGE];
+	uint32_t *intra_list[PORT_NSTAGE];
+	int stage, n_stage;
 	int cur_slot;
 } PortCtx;
 
 static int port_create(void **ctx) { *ctx = calloc(1, sizeof(PortCtx)); return *ctx ? 0 : -1; }
 static void port_free_all(PortCtx *c) {
 	free(c->frames_alloc); for (int i = 0; i < E264_MAX_SLOTS; i++) { free(c->recs[i]); c->recs[i] = NULL; }
-	free(c->coefs); free(c->slices); free(c->intra_list); c->frames_alloc = NULL; c->coefs = NULL; c->slices = NULL; c->intra_list = NULL;
+	for (int i = 0; i < PORT_NSTAGE; i++) { free(c->coefs[i]); free(c->slices[i]); free(c->intra_list[i]); c->coefs[i] = NULL; c->slices[i] = NULL; c->intra_list[i] = NULL; }
+	c->frames_alloc = NULL;
 }
 static void port_destroy(void *ctx) { port_free_all((PortCtx *)ctx); free(ctx); }
 static int port_configure(void *ctx, const E264PicDesc *g, int n_slots) {
@@ -36,16 +40,22 @@ static int port_configure(void *ctx, const E264PicDesc *g, int n_slots) {
 	size_t nmb = (size_t)g->width_mbs * g->height_mbs;
 	for (int i = 0; i < n_slots; i++) if (!(c->recs[i] = (E264MbRec *)calloc(nmb, sizeof(E264MbRec)))) return -1;
 	c->coef_cap = (uint32_t)(nmb * 408);
-	c->coefs = (int16_t *)calloc(c->coef_cap, sizeof(int16_t));
-	c->slices = (E264SliceRec *)calloc(E264_MAX_SLICES, sizeof(E264SliceRec));
-	c->intra_list = (uint32_t *)calloc(nmb, sizeof(uint32_t));
-	return c->coefs && c->slices && c->intra_list ? 0 : -1;
+	c->n_stage = g->staging > 0 ? (g->staging < PORT_NSTAGE ? g->staging : PORT_NSTAGE) : 2;
+	c->stage = 0;
+	for (int i = 0; i < c->n_stage; i++) {
+		c->coefs[i] = (int16_t *)calloc(c->coef_cap, sizeof(int16_t));
+		c->slices[i] = (E264SliceRec *)calloc(E264_MAX_SLICES, sizeof(E264SliceRec));
+		c->intra_list[i] = (uint32_t *)calloc(nmb, sizeof(uint32_t));
+		if (!c->coefs[i] || !c->slices[i] || !c->intra_list[i]) return -1;
+	}
+	return 0;
 }
 static void *port_host_alloc(void *ctx, size_t bytes) { (void)ctx; return calloc(bytes, 1); }
 static void port_host_free(void *ctx, void *p) { (void)ctx; free(p); }
 static int port_acquire(void *ctx, int slot, E264Staging *out) {
 	PortCtx *c = (PortCtx *)ctx;
-	out->handle = 0; out->recs = c->recs[slot]; out->coefs = c->coefs; out->coef_capacity = c->coef_cap; out->slices = c->slices; out->intra_list = c->intra_list;
+	c->stage = (c->stage + 1) % c->n_stage;
+	out->handle = c->stage; out->recs = c->recs[slot]; out->coefs = c->coefs[c->stage]; out->coef_capacity = c->coef_cap; out->slices = c->slices[c->stage]; out->intra_list = c->intra_list[c->stage];
 	c->cur_slot = slot;
 	return 0;
 }
@@ -66,7 +76,8 @@ static int port_submit(void *ctx, const E264PicDesc *pd, uint8_t *host_out, uint
 		}
 	}
 	pic_no++;
-	if (!getenv("E264_NULL_RECON")) port_recon_picture(c->frames, pd, c->recs[pd->dst_slot], c->coefs, c->slices);
+	if (pd->staging < 0 || pd->staging >= c->n_stage) return -1;
+	if (!getenv("E264_NULL_RECON")) port_recon_picture(c->frames, pd, c->recs[pd->dst_slot], c->coefs[pd->staging], c->slices[pd->staging]);
 	if (!getenv("E264_NULL_RECON")) memcpy(host_out, c->frames + (size_t)pd->dst_slot * pd->frame_bytes, (size_t)pd->frame_bytes);
 	*ticket = 0;
 	return 0;

@@ -37,7 +37,10 @@ static uint64_t frame_sum(const Edge264Frame *f) {
 static void decode_stream(Job *j) {
 	const uint8_t *buf = j->buf, *end = buf + j->size;
 	const uint8_t *nal = buf + 3 + (buf[2] == 0);
-	Edge264Decoder *dec = edge264_alloc(0, NULL, NULL, 0, NULL, NULL, NULL);
+	/* E264_BENCH_DEC_THREADS: n_threads of every decoder (0 = parse inside decode_NAL; the GPU library parses pictures ahead on
+	 * worker threads otherwise; the reference's threaded mode hangs here, SURVEY section 0.7, so its arm stays at 0) */
+	const char *nt = getenv("E264_BENCH_DEC_THREADS");
+	Edge264Decoder *dec = edge264_alloc(nt ? atoi(nt) : 0, NULL, NULL, 0, NULL, NULL, NULL);
 	Edge264Frame f; int res, drained = 0; long frames = 0; uint64_t sum = 0;
 	if (!dec) { j->last_ret = -1; return; }
 	for (;;) {
