@@ -49,7 +49,7 @@ __device__ int dbk_bs_pair(const E264MbRec *p, int bp, const E264MbRec *q, int b
 
 #define PRE_WARPS 4
 __global__ void __launch_bounds__(PRE_WARPS * 32) e264_prepass_kernel(PicJob J) {
-	TraceScope trace_(J, 0);
+	TraceScope trace_(J, 4);
 	__shared__ uint4 recs[PRE_WARPS][3][12];
 	__shared__ __align__(16) E264DbkMb dgs[PRE_WARPS];
 	if (blockIdx.x == 0 && threadIdx.x < 8) J.tickets[threadIdx.x] = 0;    /* the kernels behind us on the stream draw from zero */

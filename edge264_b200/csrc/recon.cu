@@ -409,10 +409,17 @@ extern "C" double e264b_kept_algorithmic_bytes(E264bDevice *c, double *recon_byt
 	return rec + db;
 }
 
-/* replay the kept pictures of several decoders concurrently (one stream each), `reps` times;
- * returns the elapsed device time in ms between a start event and the last stream's end */
-extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, float *ms_total, float *ms_recon_only, uint64_t *launches) {
-	if (n <= 0) return -1;
+/* Replay the kept pictures of several decoders concurrently (one CUDA stream each), `reps` times, and return the
+ * elapsed device time between a start event and the last stream's end.  `threads` host threads issue the launches
+ * (each owns a share of the streams): one thread alone tops out near 40-50 thousand launches per second and would
+ * make the result a CPU number.  Every kernel stamps its first block's start and last block's end (%globaltimer)
+ * into a trace array during the timed pass; stats->kernel_ms[k] is the sum over launches of that span per kernel
+ * kind (0 residual, 1 inter, 2 intra, 3 deblock, 4 prepass) — spans of concurrent launches overlap, so their sum may
+ * exceed the elapsed time.  E264B_TRACE=<file> also dumps the spans. */
+#include <thread>
+extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264bReplayStats *stats) {
+	if (n <= 0 || !stats) return -1;
+	memset(stats, 0, sizeof(*stats));
 	CK(cudaSetDevice(cs[0]->dev));
 	cudaEvent_t start, stop; std::vector<cudaEvent_t> ends(n);
 	CK(cudaEventCreate(&start)); CK(cudaEventCreate(&stop));
@@ -420,75 +427,49 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, float *ms_total, 
 	size_t npic = cs[0]->kept.size();
 	for (int i = 1; i < n; i++) if (cs[i]->kept.size() < npic) npic = cs[i]->kept.size();
 	uint64_t l0 = 0; for (int i = 0; i < n; i++) l0 += cs[i]->launches;
-	/* E264B_TRACE=<file>: per-launch first-start / last-end device timestamps of the full pass, for timeline analysis */
-	const char *trace_path = getenv("E264B_TRACE");
-	unsigned long long *d_trace = NULL; size_t n_trace = (size_t)reps * npic * n * 4;
-	if (trace_path) {
+	const int NK = 5;
+	size_t n_trace = (size_t)reps * npic * n * NK;
+	unsigned long long *d_trace = NULL;
+	{
 		std::vector<unsigned long long> init(n_trace * 2);
 		for (size_t i = 0; i < n_trace; i++) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; }
 		CK(cudaMalloc(&d_trace, n_trace * 16 + 128)); CK(cudaMemcpy(d_trace, init.data(), n_trace * 16, cudaMemcpyHostToDevice)); CK(cudaMemset(d_trace + n_trace * 2, 0, 128));
 	}
-	/* The replay is launch-rate bound when one host thread feeds 32 streams kernel by kernel (measured: 0.8 ms idle
-	 * between a stream's pictures), so each stream's whole sequence is captured into one CUDA graph and the timed
-	 * region launches n graphs.  Epochs restart at 1 inside a graph; its first node clears the sync words, so a graph
-	 * can be launched repeatedly.  E264B_GRAPH=1 selects it; measured on B200 the graphs run only ~8 streams concurrently (7.5k fps against 7.9k kernel by
-	 * kernel), so kernel-by-kernel launching stays the default. */
-	static int use_graph = -1;
-	if (use_graph < 0) { const char *e = getenv("E264B_GRAPH"); use_graph = e ? atoi(e) : 0; }
-	for (int pass = 0; pass < (ms_recon_only ? 2 : 1); pass++) {
-		std::vector<cudaGraphExec_t> execs;
-		if (use_graph) {
-			for (int i = 0; i < n; i++) {
-				E264bDevice *c = cs[i];
-				c->epoch = 0;
-				CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-				CK(cudaMemsetAsync(c->d_sync, 0, c->sync_words * sizeof(unsigned), c->stream));
-				for (int r = 0; r < reps; r++)
-					for (size_t k = 0; k < npic; k++) {
-						KeptPic &kp = c->kept[k];
-						PicJob J = make_job(c, &kp.pd, kp.pd.staging, kp.d_recs, kp.d_coefs, kp.d_slices, kp.d_intra);
-						if (d_trace && pass == 0) { J.trace = d_trace; J.trace_base = (int)((((size_t)r * npic + k) * n + i) * 4); J.phase_slot = (int)(n_trace * 2); }
-						if (launch_picture(c, J, &kp.pd, pass == 0 ? kp.pd.any_deblock : 0)) return -1;
-					}
-				cudaGraph_t g; cudaGraphExec_t ge;
-				CK(cudaStreamEndCapture(c->stream, &g));
-				CK(cudaGraphInstantiate(&ge, g, 0));
-				CK(cudaGraphDestroy(g));
-				CK(cudaGraphUpload(ge, c->stream));
-				execs.push_back(ge);
-			}
-			for (int i = 0; i < n; i++) CK(cudaStreamSynchronize(cs[i]->stream));
-		}
-		CK(cudaEventRecord(start, cs[0]->stream));
-		for (int i = 1; i < n; i++) CK(cudaStreamWaitEvent(cs[i]->stream, start, 0));
-		if (use_graph) {
-			for (int i = 0; i < n; i++) CK(cudaGraphLaunch(execs[i], cs[i]->stream));
-		} else {
-			for (int r = 0; r < reps; r++)
-				for (size_t k = 0; k < npic; k++)
-					for (int i = 0; i < n; i++) {
-						KeptPic &kp = cs[i]->kept[k];
-						PicJob J = make_job(cs[i], &kp.pd, kp.pd.staging, kp.d_recs, kp.d_coefs, kp.d_slices, kp.d_intra);
-						if (d_trace && pass == 0) { J.trace = d_trace; J.trace_base = (int)((((size_t)r * npic + k) * n + i) * 4); J.phase_slot = (int)(n_trace * 2); }
-						if (launch_picture(cs[i], J, &kp.pd, pass == 0 ? kp.pd.any_deblock : 0)) return -1;
-					}
-		}
-		for (int i = 1; i < n; i++) { CK(cudaEventRecord(ends[i], cs[i]->stream)); CK(cudaStreamWaitEvent(cs[0]->stream, ends[i], 0)); }
-		CK(cudaEventRecord(stop, cs[0]->stream));
-		CK(cudaEventSynchronize(stop));
-		float ms = 0; CK(cudaEventElapsedTime(&ms, start, stop));
-		if (pass == 0) { if (ms_total) *ms_total = ms; uint64_t l1 = 0; for (int i = 0; i < n; i++) l1 += cs[i]->launches; if (launches) *launches = l1 - l0; }
-		else *ms_recon_only = ms;
-		for (auto ge : execs) cudaGraphExecDestroy(ge);
-	}
-	if (d_trace) {
-		std::vector<unsigned long long> h(n_trace * 2 + 16);
-		CK(cudaMemcpy(h.data(), d_trace, n_trace * 16 + 128, cudaMemcpyDeviceToHost)); cudaFree(d_trace);
-		{ unsigned long long tot = 0; for (int i = 0; i < 10; i++) tot += h[n_trace * 2 + i]; if (tot) { fprintf(stderr, "inter kernel phase clocks (%% of warp time):"); for (int i = 0; i < 10; i++) fprintf(stderr, " p%d=%.1f", i, 100.0 * h[n_trace * 2 + i] / tot); fprintf(stderr, "  total warp-cycles %llu\n", tot); } }
+	if (threads < 1) threads = 1;
+	if (threads > n) threads = n;
+	CK(cudaEventRecord(start, cs[0]->stream));
+	for (int i = 1; i < n; i++) CK(cudaStreamWaitEvent(cs[i]->stream, start, 0));
+	std::vector<int> rc(threads, 0);
+	auto issue = [&](int t) {
+		cudaSetDevice(cs[0]->dev);
+		for (int r = 0; r < reps; r++)
+			for (size_t k = 0; k < npic; k++)
+				for (int i = t; i < n; i += threads) {
+					KeptPic &kp = cs[i]->kept[k];
+					PicJob J = make_job(cs[i], &kp.pd, kp.pd.staging, kp.d_recs, kp.d_coefs, kp.d_slices, kp.d_intra);
+					J.trace = d_trace; J.trace_base = (int)((((size_t)r * npic + k) * n + i) * NK); J.phase_slot = (int)(n_trace * 2);
+					if (launch_picture(cs[i], J, &kp.pd, kp.pd.any_deblock)) { rc[t] = -1; return; }
+				}
+	};
+	if (threads == 1) issue(0);
+	else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(issue, t); for (auto &x : th) x.join(); }
+	for (int t = 0; t < threads; t++) if (rc[t]) return -1;
+	for (int i = 1; i < n; i++) { CK(cudaEventRecord(ends[i], cs[i]->stream)); CK(cudaStreamWaitEvent(cs[0]->stream, ends[i], 0)); }
+	CK(cudaEventRecord(stop, cs[0]->stream));
+	CK(cudaEventSynchronize(stop));
+	CK(cudaEventElapsedTime(&stats->ms_total, start, stop));
+	{ uint64_t l1 = 0; for (int i = 0; i < n; i++) l1 += cs[i]->launches; stats->launches = l1 - l0; }
+	stats->threads = threads;
+	std::vector<unsigned long long> h(n_trace * 2 + 16);
+	CK(cudaMemcpy(h.data(), d_trace, n_trace * 16 + 128, cudaMemcpyDeviceToHost)); cudaFree(d_trace);
+	for (size_t j = 0; j < n_trace; j++) if (h[2 * j + 1] && h[2 * j] != ~0ull) { stats->kernel_ms[j % NK] += 1e-6 * (double)(h[2 * j + 1] - h[2 * j]); stats->kernel_launches[j % NK]++; }
+	{ unsigned long long tot = 0; for (int i = 0; i < 10; i++) tot += h[n_trace * 2 + i]; if (tot) { fprintf(stderr, "inter kernel phase clocks (%% of warp time):"); for (int i = 0; i < 10; i++) fprintf(stderr, " p%d=%.1f", i, 100.0 * h[n_trace * 2 + i] / tot); fprintf(stderr, "  total warp-cycles %llu\n", tot); } }
+	const char *trace_path = getenv("E264B_TRACE");
+	if (trace_path) {
 		FILE *f = fopen(trace_path, "w");
 		if (f) {
 			fprintf(f, "rep,pic,stream,kind,start_ns,end_ns\n");
-			for (size_t j = 0; j < n_trace; j++) if (h[2 * j + 1]) fprintf(f, "%zu,%zu,%zu,%zu,%llu,%llu\n", j / 4 / n / npic, j / 4 / n % npic, j / 4 % n, j % 4, h[2 * j], h[2 * j + 1]);
+			for (size_t j = 0; j < n_trace; j++) if (h[2 * j + 1]) fprintf(f, "%zu,%zu,%zu,%zu,%llu,%llu\n", j / NK / n / npic, j / NK / n % npic, j / NK % n, j % NK, h[2 * j], h[2 * j + 1]);
 			fclose(f);
 		}
 	}

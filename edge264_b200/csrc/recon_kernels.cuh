@@ -33,7 +33,7 @@ struct PicJob {
 	int n_intra;
 	const void *tmaps;    /* CUtensorMap[6] over the whole frame pool (x, y, slot): luma boxes 48x{21,13,9}, chroma boxes 32x{9,5,3}; NULL = no TMA */
 	int16_t *resid;       /* [nmb][384] residual written by e264_residual_kernel (coded macroblocks only) */
-	unsigned long long *trace;   /* measurement only (E264B_TRACE): [trace_base + kind] = {first warp start, last warp end} in globaltimer ns */
+	unsigned long long *trace;   /* measurement only (e264b_replay): [trace_base + kind] = {first block start, last block end} in globaltimer ns; kinds: 0 residual, 1 inter, 2 intra, 3 deblock, 4 prepass */
 	int trace_base;
 	int phase_slot;              /* index into trace[] of the 10 phase counters (E264B_PHASES builds) */
 };
@@ -86,8 +86,9 @@ __device__ __forceinline__ int norm8(int m, int i, int j) {
 struct TraceScope {
 	unsigned long long *t;
 	__device__ __forceinline__ static unsigned long long now() { unsigned long long v; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)); return v; }
-	__device__ __forceinline__ TraceScope(const PicJob &J, int kind) { t = J.trace ? J.trace + 2 * (J.trace_base + kind) : nullptr; if (t && (threadIdx.x & 31) == 0) atomicMin(t, now()); }
-	__device__ __forceinline__ ~TraceScope() { if (t && (threadIdx.x & 31) == 0) atomicMax(t + 1, now()); }
+	/* one thread per block: two atomics per block keep the timed replay undisturbed (a block's first warp starts it, its exit is within one macroblock of the block's end) */
+	__device__ __forceinline__ TraceScope(const PicJob &J, int kind) { t = J.trace ? J.trace + 2 * (J.trace_base + kind) : nullptr; if (t && threadIdx.x == 0) atomicMin(t, now()); }
+	__device__ __forceinline__ ~TraceScope() { if (t && threadIdx.x == 0) atomicMax(t + 1, now()); }
 };
 
 /* -DE264B_PHASES (measurement builds only): per-phase clock accumulation in the inter kernel; lane 0 of each warp

@@ -42,7 +42,14 @@ void  e264b_stats(E264bDevice *dev, uint64_t *kernel_launches, uint64_t *h2d_byt
  * are retained so the kernels can be re-run with inputs resident in HBM */
 int      e264b_kept_count(E264bDevice *dev);
 double   e264b_kept_algorithmic_bytes(E264bDevice *dev, double *recon_bytes, double *deblock_bytes, uint64_t *macroblocks);
-int      e264b_replay(E264bDevice **devs, int n, int reps, float *ms_total, float *ms_recon_only, uint64_t *kernel_launches);
+typedef struct E264bReplayStats {
+	float    ms_total;             /* device time from the common start to the last stream's end */
+	int      threads;              /* host threads that issued the launches */
+	uint64_t launches;
+	double   kernel_ms[5];         /* per kernel kind (0 residual, 1 inter, 2 intra, 3 deblock, 4 prepass): sum over launches of last-block-end minus first-block-start */
+	uint64_t kernel_launches[5];
+} E264bReplayStats;
+int      e264b_replay(E264bDevice **devs, int n, int reps, int threads, E264bReplayStats *stats);
 uint64_t e264b_slot_hash(E264bDevice *dev, int slot);
 E264bDevice *e264b_of_decoder(struct Edge264Decoder *dec);
 

@@ -57,11 +57,13 @@ def test_replay_reproduces_decode(workdir):
         bench.e264bench_run(bufs, sizes, 1, 1, 1, frames, sums, decs)
         dev = core.e264b_of_decoder(decs[0])
         before = [core.e264b_slot_hash(dev, s) for s in range(4)]
-        devs = (ctypes.c_void_p * 1)(dev); ms = ctypes.c_float(); nl = ctypes.c_uint64()
-        assert core.e264b_replay(devs, 1, 2, ctypes.byref(ms), None, ctypes.byref(nl)) == 0
+        import bench
+        devs = (ctypes.c_void_p * 1)(dev); st = bench.ReplayStats()
+        assert core.e264b_replay(devs, 1, 2, 1, ctypes.byref(st)) == 0
         assert [core.e264b_slot_hash(dev, s) for s in range(4)] == before
-        # per picture: residual (if coded), inter (if any), intra (if any), deblock -> 2..4 launches, replayed twice
-        assert 2 * 2 * frames[0] <= nl.value <= 2 * 4 * frames[0] and core.e264b_error_flag(dev) == 0
+        # per picture: pre-pass, residual (if coded), inter (if any), intra (if any), deblock -> 3..5 launches, replayed twice
+        assert 2 * 3 * frames[0] <= st.launches <= 2 * 5 * frames[0] and core.e264b_error_flag(dev) == 0
+        assert sum(st.kernel_launches) == st.launches and all(st.kernel_ms[k] > 0 for k in (3, 4))
         bench.e264bench_free(decs, 1)
     finally:
         os.environ["E264B_KEEP"] = "0"

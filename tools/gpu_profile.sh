@@ -10,7 +10,7 @@ python - <<'PY' > gpurun_out/scaling_$1.txt 2>&1
 import ctypes, os, sys, time
 sys.path.insert(0, '.')
 import bench
-bufs = bench.generate_streams([2000 + i for i in range(16)], 60, '/tmp/e264_bench')
+bufs = bench.generate_streams(bench.CONFIGS['1080p'], [2000 + i for i in range(16)], 60, '/tmp/e264_bench')
 for name, path in (("reference", "oracle/_ref/libe264bench_ref.so"), ("b200", "tools/libe264bench.so")):
     lib = bench.BenchLib(path)
     for th in (8, 16, 32, 64):
