@@ -44,7 +44,7 @@ struct E264bDevice {
 	void *d_tmaps;               /* CUtensorMap[n_slots][6] over the frame pool, or NULL when the geometry does not fit TMA's rules */
 	E264MbRec *h_recs[E264_MAX_SLOTS]; cudaEvent_t rec_up[E264_MAX_SLOTS]; bool rec_busy[E264_MAX_SLOTS];
 	Staging st[NSTAGE]; int stage, n_stage;
-	unsigned *d_sync;            /* [0..7] tickets (0 inter, 1 deblock, 2 intra), [8] err, [16..) flags[nmb] + deblocking progress[2 * h_mbs] */
+	unsigned *d_sync;            /* [0..7] tickets (0 inter, 1 deblock, 2 intra), [8] err, [16..) flags[nmb] + row progress[3 * h_mbs] */
 	size_t sync_words;
 	unsigned epoch;
 	cudaEvent_t tick_ev[NTICK]; uint64_t tick_seq;
@@ -213,7 +213,7 @@ extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots
 		CK(cudaMalloc(&s->d_intra, c->nmb * sizeof(uint32_t)));
 		CK(cudaHostAlloc(&s->h_intra, c->nmb * sizeof(uint32_t), cudaHostAllocDefault));
 	}
-	c->sync_words = 16 + c->nmb + 2 * (size_t)g->height_mbs + 16;
+	c->sync_words = 16 + c->nmb + 3 * (size_t)g->height_mbs + 16;
 	CK(cudaMalloc(&c->d_sync, c->sync_words * sizeof(unsigned)));
 	CK(cudaMemsetAsync(c->d_sync, 0, c->sync_words * sizeof(unsigned), c->stream));
 	c->epoch = 0; c->stage = 0;

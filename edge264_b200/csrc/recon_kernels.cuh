@@ -23,7 +23,7 @@ struct PicJob {
 	const E264MbRec *recs; const int16_t *coefs; const E264SliceRec *slices;
 	uint8_t *frames;
 	int frame_bytes, w_mbs, h_mbs, stride_y, stride_c, plane_y, dst_slot, n_slots;
-	unsigned *flags;      /* [nmb] "reconstructed" == epoch, then [2][h_mbs] deblocking progress of luma / chroma rows (epoch * 2048 + macroblocks stored) */
+	unsigned *flags;      /* [nmb] "reconstructed" == epoch, then [3][h_mbs] row progress (epoch * 2048 + macroblocks done): deblocking luma, deblocking chroma, intra pictures */
 	unsigned epoch;
 	unsigned *tickets;    /* [8] zeroed by e264_prepass_kernel: 0 inter, 1 deblock, 2 intra */
 	unsigned *err;
@@ -115,6 +115,22 @@ __device__ __forceinline__ bool wait_flag(const unsigned *flags, int idx, unsign
 	unsigned spins = 0;
 	long long t0 = 0;
 	while (*f != epoch) {
+		__nanosleep(64);
+		if ((++spins & 63) == 0) {
+			if (*(const volatile unsigned *)err) return false;
+			if (t0 == 0) t0 = clock64();
+			else if (clock64() - t0 > 400000000ll) { atomicExch(err, 1u); return false; }
+		}
+	}
+	return true;
+}
+
+/* spin until *p - need >= 0 (counters carry the picture epoch in their upper bits), bounded like wait_flag */
+__device__ __forceinline__ bool wait_progress(const unsigned *p, unsigned need, unsigned *err) {
+	const volatile unsigned *f = p;
+	unsigned spins = 0;
+	long long t0 = 0;
+	while ((int)(*f - need) < 0) {
 		__nanosleep(64);
 		if ((++spins & 63) == 0) {
 			if (*(const volatile unsigned *)err) return false;
@@ -912,7 +928,11 @@ __device__ __forceinline__ void intra_mb(WarpSmem *ws, const PicJob &J, uint8_t 
 				if (ok && mby > 0 && mbx > 0) ok = wait_flag(J.flags, mb - J.w_mbs - 1, J.epoch, J.err);
 				if (ok && mby > 0) ok = wait_flag(J.flags, mb - J.w_mbs, J.epoch, J.err);
 			}
-			if (ok && mby > 0) ok = wait_flag(J.flags, mbx < J.w_mbs - 1 ? mb - J.w_mbs + 1 : mb - J.w_mbs, J.epoch, J.err);
+			if (rows_mode) {
+				/* the warp of the row above must have passed C (or the end of its row): its counter orders B and D before
+				 * it, whatever kernel reconstructed C — the flag of an inter C says nothing about an intra B */
+				if (mby > 0) ok = wait_progress(J.flags + J.w_mbs * J.h_mbs + 2 * J.h_mbs + mby - 1, J.epoch * 2048u + (unsigned)min(mbx + 2, J.w_mbs), J.err);
+			} else if (ok && mby > 0) ok = wait_flag(J.flags, mbx < J.w_mbs - 1 ? mb - J.w_mbs + 1 : mb - J.w_mbs, J.epoch, J.err);
 			__threadfence();
 		}
 		__syncwarp();
@@ -942,7 +962,10 @@ __device__ __forceinline__ void intra_mb(WarpSmem *ws, const PicJob &J, uint8_t 
 		else if (lane < 24) CT(0, -1, lane - 16) = v;
 		if (lane < 8) CT(1, -1, lane) = v2;
 	}
-	if (kind != MBK_INTER && lane == 0) { __threadfence(); *(volatile unsigned *)(J.flags + mb) = J.epoch; }
+	if (lane == 0) {
+		if (kind != MBK_INTER) { __threadfence(); *(volatile unsigned *)(J.flags + mb) = J.epoch; }
+		if (rows_mode) *(volatile unsigned *)(J.flags + J.w_mbs * J.h_mbs + 2 * J.h_mbs + mby) = J.epoch * 2048u + (unsigned)mbx + 1u;   /* after the fence above when this macroblock wrote samples */
+	}
 	__syncwarp();
 }
 

@@ -34,6 +34,10 @@ STREAMS = [
     # 4096 samples wide: the reference pads such strides (edge264_headers.c:2027-2037); ours pads differently,
     # only the samples and the reported strides matter
     ("wide_256x2",       256, 2, "-n 5 -s 24 --gop IPB --deblock 0"),
+    # intra-heavy P/B pictures with inter macroblocks in between: the intra-picture wavefront (one warp per row) runs over
+    # pictures where a neighbour may have been reconstructed by either kernel
+    ("pb_intra_heavy",   20, 12, "-n 8 -s 77 --gop IPB --intra-pct 70 --deblock 0 --slices 3 --t8x8 50"),
+    ("pb_intra_half",    13, 9,  "-n 9 -s 78 --gop IP --intra-pct 50 --deblock 0 --refs 2 --cavlc"),
     # long-term references, list modification, memory-management operations (more of these, CPU side, in DPB_STREAMS)
     ("dpb_mmco_cabac",   4, 3, "-n 40 -s 101 --gop IP --refs 4 --idr 17 --dpb --deblock 0"),
     # B pictures used as references (verified on the B200 like the one above; its siblings run CPU side)

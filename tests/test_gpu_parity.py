@@ -2,14 +2,19 @@
 reference (when oracle/_ref travelled) and the golden digests — bit-exact, every frame."""
 import json, os, subprocess
 import pytest
-from conftest import ROOT, STREAMS, make_stream, md5_frames, have
+from conftest import ROOT, STREAMS, DPB_STREAMS, make_stream, md5_frames, have
 from checkers import decode_bytes
 
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "streams.json")))
 
 
-@pytest.mark.parametrize("name,w,h,args", STREAMS, ids=[s[0] for s in STREAMS])
+# the decoded-picture-buffer streams too: slices of different types in one picture put intra and inter macroblocks side by
+# side in every proportion (an intra-heavy P picture once took the intra-picture wavefront past a neighbour still in work)
+ALL_STREAMS = STREAMS + DPB_STREAMS
+
+
+@pytest.mark.parametrize("name,w,h,args", ALL_STREAMS, ids=[s[0] for s in ALL_STREAMS])
 def test_gpu_matches_oracle_and_golden(workdir, name, w, h, args):
     data = open(make_stream(workdir, name, w, h, args), "rb").read()
     gpu, codes = decode_bytes(data, "gpu")
@@ -57,8 +62,9 @@ def test_replay_reproduces_decode(workdir):
         bench.e264bench_run(bufs, sizes, 1, 1, 1, frames, sums, decs)
         dev = core.e264b_of_decoder(decs[0])
         before = [core.e264b_slot_hash(dev, s) for s in range(4)]
-        import bench
-        devs = (ctypes.c_void_p * 1)(dev); st = bench.ReplayStats()
+        import bench as benchmod      # (the local name `bench` is the driver library)
+        devs = (ctypes.c_void_p * 1)(dev); st = benchmod.ReplayStats()
+        core.e264b_replay.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(benchmod.ReplayStats)]
         assert core.e264b_replay(devs, 1, 2, 1, ctypes.byref(st)) == 0
         assert [core.e264b_slot_hash(dev, s) for s in range(4)] == before
         # per picture: pre-pass, residual (if coded), inter (if any), intra (if any), deblock -> 3..5 launches, replayed twice
