@@ -1,0 +1,229 @@
+/* inter_kernels.cuh — inter macroblocks: inverse transform + motion compensation + weighting + residual in ONE kernel.
+ *
+ * One warp per macroblock (tickets), one THREAD per (4x4 luma block, reference list): lane = list * 16 + luma4x4BlkIdx.
+ * The thread loads its own 9x9 luma window and two 3x3 chroma windows of the reference picture straight into
+ * registers (aligned 32-bit loads + funnel shifts; the windows of neighbouring blocks overlap in L1/L2), interpolates
+ * its 4x4 + 2x2 + 2x2 samples with the register arithmetic of mc_math.cuh (dp4a tap sums), and the list-1 thread hands
+ * its prediction to the list-0 thread with shuffles for the weighted combination (reference edge264_inter.c:416-1251:
+ * per-partition SIMD interpolation + five weighting schemes; here the unit is always the 4x4 block, which is what the
+ * record carries a vector for — partition shapes never reach the device).
+ * The macroblock's coefficient run (16..816 bytes) arrives by cp.async.bulk on an mbarrier one macroblock ahead and is
+ * inverse-transformed in shared memory (residual_stage), so the residual never travels through global memory.
+ * Round 1's kernel (rectangles regrouped on the device, windows by cp.async.bulk.tensor into shared memory, one output
+ * sample per lane and loop iteration) needed ~3600 warp instructions per macroblock; it stays selectable with
+ * E264B_INTER_OLD=1 for A/B runs. */
+#pragma once
+#include "recon_kernels.cuh"
+#include "mc_math.cuh"
+
+struct __align__(16) InterStage {
+	uint4 rec4[12];
+	int16_t coef[RES_COEF_MAX];
+};
+
+__device__ __forceinline__ uint32_t ldg32(const uint8_t *p) { return __ldg((const uint32_t *)p); }
+
+/* the thread's 9x9 luma window at (X0, Y0) = top-left of the window (block position + integer vector - 2) */
+__device__ __forceinline__ void mc_load_luma(const uint8_t *ref, int stride, int W, int H, int X0, int Y0, uint32_t w[9][3]) {
+	if (X0 >= 0 && X0 + 9 <= W) {
+		const int al = X0 & ~3, sh = (X0 & 3) * 8;
+#pragma unroll
+		for (int r = 0; r < 9; r++) {
+			const int yy = min(max(Y0 + r, 0), H - 1);
+			const uint8_t *p = ref + (size_t)yy * stride + al;
+			const uint32_t a0 = ldg32(p), a1 = ldg32(p + 4), a2 = ldg32(p + 8);
+			w[r][0] = __funnelshift_r(a0, a1, sh); w[r][1] = __funnelshift_r(a1, a2, sh); w[r][2] = a2 >> sh;
+		}
+	} else {   /* the window reaches over the left or right picture edge: samples are replicated (8.4.2.2.1) */
+#pragma unroll
+		for (int r = 0; r < 9; r++) {
+			const int yy = min(max(Y0 + r, 0), H - 1);
+			const uint8_t *p = ref + (size_t)yy * stride;
+			uint32_t v[3] = {0, 0, 0};
+#pragma unroll
+			for (int k = 0; k < 9; k++) v[k >> 2] |= (uint32_t)__ldg(p + min(max(X0 + k, 0), W - 1)) << (8 * (k & 3));
+			w[r][0] = v[0]; w[r][1] = v[1]; w[r][2] = v[2];
+		}
+	}
+}
+/* the thread's 3x3 window of one chroma plane (rows alternate Cb | Cr inside stride_c; `plane` points at the plane's column 0) */
+__device__ __forceinline__ void mc_load_chroma(const uint8_t *plane, int stride, int Wc, int Hc, int X0, int Y0, uint32_t c[3]) {
+	if (X0 >= 0 && X0 + 3 <= Wc) {
+		const int al = X0 & ~3, sh = (X0 & 3) * 8;
+#pragma unroll
+		for (int r = 0; r < 3; r++) {
+			const uint8_t *p = plane + (size_t)min(max(Y0 + r, 0), Hc - 1) * stride + al;
+			c[r] = __funnelshift_r(ldg32(p), ldg32(p + 4), sh);
+		}
+	} else {
+#pragma unroll
+		for (int r = 0; r < 3; r++) {
+			const uint8_t *p = plane + (size_t)min(max(Y0 + r, 0), Hc - 1) * stride;
+			c[r] = (uint32_t)__ldg(p + min(max(X0, 0), Wc - 1)) | (uint32_t)__ldg(p + min(max(X0 + 1, 0), Wc - 1)) << 8 | (uint32_t)__ldg(p + min(max(X0 + 2, 0), Wc - 1)) << 16;
+		}
+	}
+}
+
+/* 8.4.2.3 on four packed samples; mode 1 default average (handled by the caller), 2 explicit weight on one prediction,
+ * 3 weighted sum of both */
+__device__ __forceinline__ uint32_t wp_word(uint32_t a, uint32_t b, int mode, int w0, int w1, int o, int lw) {
+	uint32_t r = 0;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int pa = (a >> (8 * k)) & 255, pb = (b >> (8 * k)) & 255;
+		int v;
+		if (mode == 2) v = (lw >= 1 ? ((pa * w1 + (1 << (lw - 1))) >> lw) : pa * w1) + o;
+		else v = ((pa * w0 + pb * w1 + (1 << lw)) >> (lw + 1)) + o;
+		r |= (uint32_t)min(max(v, 0), 255) << (8 * k);
+	}
+	return r;
+}
+/* prediction + residual of four packed samples; res points at four int16 (8-byte aligned) */
+__device__ __forceinline__ uint32_t add_res4(uint32_t p, const int16_t *res) {
+	const uint2 rr = *(const uint2 *)res;
+	const int r0 = (short)(rr.x & 0xffff), r1 = (short)(rr.x >> 16), r2 = (short)(rr.y & 0xffff), r3 = (short)(rr.y >> 16);
+	return mc_pack4(clip255((short)((int)(p & 255) + r0)), clip255((short)((int)((p >> 8) & 255) + r1)),
+	                clip255((short)((int)((p >> 16) & 255) + r2)), clip255((short)((int)(p >> 24) + r3)));
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) e264_inter4_kernel(PicJob J) {
+	TraceScope trace_(J, 1);
+	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
+	__shared__ InterStage stage[WARPS_PER_BLOCK][2];
+	__shared__ __align__(8) unsigned long long bars[WARPS_PER_BLOCK][2];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	WarpSmem *ws = &smem[w];
+	const int nmb = J.w_mbs * J.h_mbs;
+	const int W = J.w_mbs * 16, H = J.h_mbs * 16;
+	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
+	if (lane == 0) {
+		mbar_init(&bars[w][0], 1); mbar_init(&bars[w][1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	__syncwarp();
+	/* stage s <- macroblock m: record through the read-only path; the coefficient run of a coded inter macroblock by the
+	 * TMA unit (bulk copy, completion counted in bytes on the warp's mbarrier).  Returns 1 inter, 2 inter with coefficients. */
+	auto issue = [&](int m, int s) -> int {
+		InterStage *st = &stage[w][s];
+		if (lane < 12) st->rec4[lane] = __ldg((const uint4 *)(J.recs + m) + lane);
+		__syncwarp();
+		const E264MbRec *r = (const E264MbRec *)st->rec4;
+		if (r->kind != MBK_INTER) return 0;
+		if (r->coded == 0) return 1;
+		if (lane == 0) tma_bulk_g2s(st->coef, J.coefs + r->coef_off, (unsigned)rec_coef_count(r) * 2u, &bars[w][s]);
+		return 2;
+	};
+	unsigned parity[2] = {0, 0};
+	/* tickets are drawn two macroblocks ahead: one is being prefetched while one is computed */
+	unsigned tnext = 0;
+	if (lane == 0) tnext = atomicAdd(J.tickets, 1u);
+	unsigned t = __shfl_sync(0xffffffffu, tnext, 0);
+	int s = 0, what = 0;
+	if (t < (unsigned)nmb) {
+		what = issue((int)t, 0);
+		if (lane == 0) tnext = atomicAdd(J.tickets, 1u);
+	}
+	while (t < (unsigned)nmb) {
+		const unsigned t2 = __shfl_sync(0xffffffffu, tnext, 0);
+		int what2 = 0;
+		if (t2 < (unsigned)nmb) {
+			what2 = issue((int)t2, s ^ 1);
+			if (lane == 0) tnext = atomicAdd(J.tickets, 1u);
+		}
+		if (what) {
+			const int mb = (int)t, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
+			InterStage *st = &stage[w][s];
+			const E264MbRec *r = (const E264MbRec *)st->rec4;
+			const E264SliceRec *sr = J.slices + r->slice_idx;
+			/* ---- this thread's block: list l, luma4x4BlkIdx z ---- */
+			const int l = lane >> 4, z = lane & 15, bx = blk_x(z), by = blk_y(z), i8 = z >> 2;
+			const int ref_idx = r->ref_idx[l][i8];
+			uint32_t py[4] = {0, 0, 0, 0}, pcb = 0, pcr = 0;
+			if (ref_idx >= 0) {
+				int slot = r->ref_pic[l][i8];
+				if (slot < 0 || slot >= J.n_slots) slot = J.dst_slot;
+				const uint8_t *ref = J.frames + (size_t)slot * J.frame_bytes;
+				const int mvx = r->mv[l][z][0], mvy = r->mv[l][z][1];
+				uint32_t win[9][3];
+				mc_load_luma(ref, J.stride_y, W, H, mbx * 16 + bx * 4 + (mvx >> 2) - 2, mby * 16 + by * 4 + (mvy >> 2) - 2, win);
+				uint32_t cb[3], cr[3];
+				const uint8_t *cplane = ref + J.plane_y;
+				const int cx = mbx * 8 + bx * 2 + (mvx >> 3), cy = mby * 8 + by * 2 + (mvy >> 3);
+				mc_load_chroma(cplane, J.stride_c, W >> 1, H >> 1, cx, cy, cb);
+				mc_load_chroma(cplane + (J.stride_c >> 1), J.stride_c, W >> 1, H >> 1, cx, cy, cr);
+				mc_luma4x4(win, mvx & 3, mvy & 3, py);
+				pcb = mc_chroma2x2(cb[0], cb[1], cb[2], mvx & 7, mvy & 7);
+				pcr = mc_chroma2x2(cr[0], cr[1], cr[2], mvx & 7, mvy & 7);
+			}
+			/* ---- the inverse transform of this macroblock (all lanes), while the loads above drain ---- */
+			if (what == 2) {
+				if (!mbar_wait(&bars[w][s], parity[s])) { if (lane == 0) atomicExch(J.err, 4u); break; }
+				parity[s] ^= 1;
+				residual_stage(ws, r, sr, st->coef, lane);
+			}
+			/* ---- list 1 -> list 0 thread, weighting, residual, tile ---- */
+			uint32_t qy[4], qcb, qcr;
+#pragma unroll
+			for (int k = 0; k < 4; k++) qy[k] = __shfl_xor_sync(0xffffffffu, py[k], 16);
+			qcb = __shfl_xor_sync(0xffffffffu, pcb, 16); qcr = __shfl_xor_sync(0xffffffffu, pcr, 16);
+			const int other = __shfl_xor_sync(0xffffffffu, ref_idx, 16);
+			if (lane < 16) {
+				const int r0 = ref_idx, r1 = other;
+				const int wpm = sr->wp_mode;
+				if (r0 >= 0 && r1 >= 0) {
+					if (wpm == WP_DEFAULT) {
+#pragma unroll
+						for (int k = 0; k < 4; k++) py[k] = mc_avg4(py[k], qy[k]);
+						pcb = mc_avg4(pcb, qcb); pcr = mc_avg4(pcr, qcr);
+					} else {
+						int w0[3], w1[3], o[3], lw[3];
+#pragma unroll
+						for (int c = 0; c < 3; c++) {
+							if (wpm == WP_EXPLICIT) { w0[c] = sr->wp_w[0][r0 & 15][c]; w1[c] = sr->wp_w[1][r1 & 15][c]; o[c] = (sr->wp_o[0][r0 & 15][c] + sr->wp_o[1][r1 & 15][c] + 1) >> 1; lw[c] = c ? sr->chroma_log2_wd : sr->luma_log2_wd; }
+							else { w1[c] = sr->implicit_w1[r0 & 15][r1 & 15]; w0[c] = 64 - w1[c]; o[c] = 0; lw[c] = 5; }
+						}
+#pragma unroll
+						for (int k = 0; k < 4; k++) py[k] = wp_word(py[k], qy[k], 3, w0[0], w1[0], o[0], lw[0]);
+						pcb = wp_word(pcb, qcb, 3, w0[1], w1[1], o[1], lw[1]); pcr = wp_word(pcr, qcr, 3, w0[2], w1[2], o[2], lw[2]);
+					}
+				} else {
+					if (r0 < 0) {
+#pragma unroll
+						for (int k = 0; k < 4; k++) py[k] = qy[k];
+						pcb = qcb; pcr = qcr;
+					}
+					if (wpm == WP_EXPLICIT && (r0 >= 0 || r1 >= 0)) {
+						const int ll = r0 >= 0 ? 0 : 1, ri = (ll ? r1 : r0) & 15;
+#pragma unroll
+						for (int k = 0; k < 4; k++) py[k] = wp_word(py[k], 0, 2, 0, sr->wp_w[ll][ri][0], sr->wp_o[ll][ri][0], sr->luma_log2_wd);
+						pcb = wp_word(pcb, 0, 2, 0, sr->wp_w[ll][ri][1], sr->wp_o[ll][ri][1], sr->chroma_log2_wd);
+						pcr = wp_word(pcr, 0, 2, 0, sr->wp_w[ll][ri][2], sr->wp_o[ll][ri][2], sr->chroma_log2_wd);
+					}
+				}
+				if (what == 2) {
+#pragma unroll
+					for (int k = 0; k < 4; k++) py[k] = add_res4(py[k], ws->res + (by * 4 + k) * 16 + bx * 4);
+					{	/* chroma: two samples per row */
+						const int16_t *rc = ws->res + 256 + (by * 2) * 8 + bx * 2;
+						const uint32_t a = *(const uint32_t *)rc, b = *(const uint32_t *)(rc + 8), c2 = *(const uint32_t *)(rc + 64), d = *(const uint32_t *)(rc + 72);
+						pcb = mc_pack4(clip255((short)((int)(pcb & 255) + (short)(a & 0xffff))), clip255((short)((int)((pcb >> 8) & 255) + (short)(a >> 16))),
+						               clip255((short)((int)((pcb >> 16) & 255) + (short)(b & 0xffff))), clip255((short)((int)(pcb >> 24) + (short)(b >> 16))));
+						pcr = mc_pack4(clip255((short)((int)(pcr & 255) + (short)(c2 & 0xffff))), clip255((short)((int)((pcr >> 8) & 255) + (short)(c2 >> 16))),
+						               clip255((short)((int)((pcr >> 16) & 255) + (short)(d & 0xffff))), clip255((short)((int)(pcr >> 24) + (short)(d >> 16))));
+					}
+				}
+#pragma unroll
+				for (int k = 0; k < 4; k++) *(uint32_t *)&YT(bx * 4, by * 4 + k) = py[k];
+				*(uint16_t *)&CT(0, bx * 2, by * 2) = (uint16_t)pcb; *(uint16_t *)&CT(0, bx * 2, by * 2 + 1) = (uint16_t)(pcb >> 16);
+				*(uint16_t *)&CT(1, bx * 2, by * 2) = (uint16_t)pcr; *(uint16_t *)&CT(1, bx * 2, by * 2 + 1) = (uint16_t)(pcr >> 16);
+			}
+			__syncwarp();
+			store_mb(ws, J, dst + (size_t)(mby * 16) * J.stride_y + mbx * 16, dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8, lane);
+			if (lane == 0) J.flags[mb] = J.epoch;     /* visible to the intra kernel through the kernel boundary */
+			__syncwarp();
+		}
+		t = t2; what = what2; s ^= 1;
+	}
+}

@@ -19,6 +19,7 @@
 #include <mutex>
 #include "recon_kernels.cuh"
 #include "deblock_kernels.cuh"
+#include "inter_kernels.cuh"
 extern "C" {
 #include "dec.h"
 }
@@ -264,6 +265,7 @@ static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, int stage, const E
 	J.intra_list = intra; J.n_intra = pd->n_intra;
 	J.rows_mode = pd->n_intra * 2 > pd->width_mbs * pd->height_mbs;   /* intra pictures: wavefront of row warps */
 	J.trace = NULL; J.trace_base = 0; J.phase_slot = 0;
+	{ static int old = -1; if (old < 0) { const char *e = getenv("E264B_INTER_OLD"); old = e ? atoi(e) : 0; } J.resid_inter = old; }
 	{ static int tma = -1; if (tma < 0) { const char *e = getenv("E264B_TMA"); tma = e ? atoi(e) : 1; } J.tmaps = tma ? c->d_tmaps : NULL; }
 	{ static int force = -2; if (force == -2) { const char *e = getenv("E264B_ROWS"); force = e ? atoi(e) : -1; } if (force >= 0) J.rows_mode = force; }
 	if (c->epoch >= (1u << 20)) {   /* row progress counters encode epoch * 2048 + count: restart before it wraps */
@@ -291,13 +293,19 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 		if (pb > c->sm_count * 4) pb = c->sm_count * 4;
 		e264_prepass_kernel<<<pb, PRE_WARPS * 32, 0, c->stream>>>(P); c->launches++;
 	}
-	if (pd->n_coefs > 0) { e264_residual_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++; }
+	/* inter macroblocks transform their own coefficients; the residual kernel serves the intra kernel (and the round-1 inter kernel) */
+	if (pd->n_coefs > 0 && (J.resid_inter || pd->n_intra > 0)) { e264_residual_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++; }
 	if (pd->n_intra < nmb) {
-		if (minb >= 8) e264_inter_kernel<8><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
-		else if (minb >= 6) e264_inter_kernel<6><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
-		else if (minb >= 5) e264_inter_kernel<5><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
-		else if (minb == 4) e264_inter_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
-		else e264_inter_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+		if (J.resid_inter) {
+			if (minb >= 8) e264_inter_kernel<8><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+			else if (minb >= 6) e264_inter_kernel<6><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+			else if (minb >= 5) e264_inter_kernel<5><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+			else if (minb == 4) e264_inter_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+			else e264_inter_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+		} else {
+			if (minb >= 6) e264_inter4_kernel<6><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+			else e264_inter4_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+		}
 		c->launches++;
 	}
 	if (pd->n_intra > 0) {

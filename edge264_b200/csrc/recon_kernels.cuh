@@ -28,6 +28,7 @@ struct PicJob {
 	unsigned *tickets;    /* [8] zeroed by e264_prepass_kernel: 0 inter, 1 deblock, 2 intra */
 	unsigned *err;
 	int rows_mode;
+	int resid_inter;      /* e264_residual_kernel also transforms inter macroblocks (only the round-1 inter kernel reads them from J.resid) */
 	struct E264DbkMb *dbk;        /* [nmb] deblocking digests written by e264_prepass_kernel; NULL = picture is not deblocked */
 	const uint32_t *intra_list;   /* addresses of the intra macroblocks in raster order */
 	int n_intra;
@@ -819,7 +820,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_residual_kernel(Pic
 		if (lane < 12) st->rec4[lane] = __ldg((const uint4 *)(J.recs + m) + lane);
 		__syncwarp();
 		const E264MbRec *r = (const E264MbRec *)st->rec4;
-		const bool on = r->coded != 0 && r->kind != MBK_IPCM;
+		const bool on = r->coded != 0 && r->kind != MBK_IPCM && (J.resid_inter || r->kind != MBK_INTER);
 		if (on && lane == 0) tma_bulk_g2s(st->coef, J.coefs + r->coef_off, (unsigned)rec_coef_count(r) * 2u, &bars[w][s]);
 		return on;
 	};
