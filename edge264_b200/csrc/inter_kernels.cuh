@@ -116,22 +116,17 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) e264_inter4_kernel
 		return 2;
 	};
 	unsigned parity[2] = {0, 0};
-	/* tickets are drawn two macroblocks ahead: one is being prefetched while one is computed */
-	unsigned tnext = 0;
-	if (lane == 0) tnext = atomicAdd(J.tickets, 1u);
-	unsigned t = __shfl_sync(0xffffffffu, tnext, 0);
+	/* macroblocks are dealt out by warp number: a shared ticket counter serialises in L2 (~10 cycles per atomic on one
+	 * address: 13 000 atomics per 1080p picture were most of the round-1 kernel's 77 us) and inter macroblocks cost about
+	 * the same, so a static deal balances well enough */
+	const unsigned step = gridDim.x * WARPS_PER_BLOCK;
+	unsigned t = blockIdx.x * WARPS_PER_BLOCK + w;
 	int s = 0, what = 0;
-	if (t < (unsigned)nmb) {
-		what = issue((int)t, 0);
-		if (lane == 0) tnext = atomicAdd(J.tickets, 1u);
-	}
+	if (t < (unsigned)nmb) what = issue((int)t, 0);
 	while (t < (unsigned)nmb) {
-		const unsigned t2 = __shfl_sync(0xffffffffu, tnext, 0);
+		const unsigned t2 = t + step;
 		int what2 = 0;
-		if (t2 < (unsigned)nmb) {
-			what2 = issue((int)t2, s ^ 1);
-			if (lane == 0) tnext = atomicAdd(J.tickets, 1u);
-		}
+		if (t2 < (unsigned)nmb) what2 = issue((int)t2, s ^ 1);
 		if (what) {
 			const int mb = (int)t, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
 			InterStage *st = &stage[w][s];
