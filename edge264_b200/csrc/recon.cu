@@ -499,6 +499,63 @@ extern "C" uint64_t e264b_slot_hash(E264bDevice *c, int slot) {
 	return x;
 }
 
+/* ---- known-answer entry point (tests/test_kat.py -m gpu): the reference's own KAT inputs through the DEVICE functions ----
+ * fn 0 intra4x4, 1 intra8x8, 2 intra16x16, 3 chroma: `in` is the 32-byte-stride border buffer of edge264_check.c:173-180
+ * (sample (0,0) at in + 80), mode = prediction mode | unavailable bits << 4; the block is predicted into the same layout.
+ * fn 4 inter luma: `in` is the 21x21 source of edge264_check.c:286-290, mode = xFrac | yFrac << 2, w x h output samples. */
+__global__ void e264_kat_kernel(int fn, int imode, const uint8_t *in, uint8_t *out, int w, int h) {
+	__shared__ WarpSmem wsm;
+	__shared__ E264MbRec rec;
+	WarpSmem *ws = &wsm;
+	const int lane = threadIdx.x;
+	if (fn == 4) {
+		const int fx = imode & 3, fy = (imode >> 2) & 3, bw = w >> 2, nb = bw * (h >> 2);
+		if (lane < nb) {
+			const int bx = lane % bw, by = lane / bw;
+			uint32_t win[9][3], o[4];
+#pragma unroll
+			for (int r = 0; r < 9; r++) {
+				uint32_t v[3] = {0, 0, 0};
+#pragma unroll
+				for (int k = 0; k < 9; k++) v[k >> 2] |= (uint32_t)in[(by * 4 + r) * 21 + bx * 4 + k] << (8 * (k & 3));      /* block origin (2,2): window from (0,0) */
+				win[r][0] = v[0]; win[r][1] = v[1]; win[r][2] = v[2];
+			}
+			mc_luma4x4(win, fx, fy, o);
+			for (int y = 0; y < 4; y++) for (int x = 0; x < 4; x++) out[(by * 4 + y) * w + bx * 4 + x] = (uint8_t)(o[y] >> (8 * x));
+		}
+		return;
+	}
+	const uint8_t *p = in + 80;
+	for (int i = lane; i < 384; i += 32) ws->res[i] = 0;
+	if (lane == 0) { memset(&rec, 0, sizeof(rec)); rec.kind = fn == 0 ? MBK_I4x4 : fn == 1 ? MBK_I8x8 : MBK_I16x16; for (int b = 0; b < 16; b++) rec.modes[b] = IMODE(2, 0); rec.modes[0] = (uint8_t)imode; rec.i16_mode = (uint8_t)imode; rec.chroma_mode = (uint8_t)imode; }
+	__syncwarp();
+	if (fn < 3) {
+		for (int x = lane - 1; x < 24; x += 32) YT(x, -1) = x < 16 ? p[x - 32] : p[15 - 32];
+		if (lane < 16) YT(-1, lane) = p[lane * 32 - 1];
+		__syncwarp();
+		intra_luma(ws, &rec, lane);
+		__syncwarp();
+		for (int i = lane; i < w * h; i += 32) out[i] = YT(i % w, i / w);
+	} else {   /* Cb = even rows, Cr = odd rows of the reference's interleaved chroma plane */
+		if (lane < 18) { const int pl = lane / 9, x = lane % 9 - 1; CT(pl, x, -1) = p[x + (pl ? -32 : -64)]; }
+		if (lane < 16) { const int pl = lane >> 3, y = lane & 7; CT(pl, -1, y) = p[(2 * y + pl) * 32 - 1]; }
+		__syncwarp();
+		intra_chroma(ws, &rec, lane);
+		__syncwarp();
+		for (int i = lane; i < 128; i += 32) { const int row = i >> 3, x = i & 7; out[i] = CT(row & 1, x, row >> 1); }
+	}
+}
+extern "C" int e264b_kat(int fn, int mode, const uint8_t *in, int in_bytes, uint8_t *out, int w, int h) {
+	uint8_t *d_in = NULL, *d_out = NULL;
+	CK(cudaMalloc(&d_in, in_bytes + 64)); CK(cudaMalloc(&d_out, 1024));
+	CK(cudaMemset(d_in, 0, in_bytes + 64)); CK(cudaMemcpy(d_in, in, in_bytes, cudaMemcpyHostToDevice)); CK(cudaMemset(d_out, 0, 1024));
+	e264_kat_kernel<<<1, 32>>>(fn, mode, d_in, d_out, w, h);
+	CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+	CK(cudaMemcpy(out, d_out, (size_t)w * h, cudaMemcpyDeviceToHost));
+	cudaFree(d_in); cudaFree(d_out);
+	return 0;
+}
+
 /* ---- backend vtable for decoder.c ---- */
 static int be_create(void **ctx) { return e264b_create((E264bDevice **)ctx); }
 static void be_destroy(void *ctx) { e264b_destroy((E264bDevice *)ctx); }

@@ -51,6 +51,8 @@ typedef struct E264bReplayStats {
 } E264bReplayStats;
 int      e264b_replay(E264bDevice **devs, int n, int reps, int threads, E264bReplayStats *stats);
 uint64_t e264b_slot_hash(E264bDevice *dev, int slot);
+/* known-answer support (tests): one block through the device's intra predictors (fn 0-3) or luma interpolation (fn 4) */
+int      e264b_kat(int fn, int mode, const uint8_t *in, int in_bytes, uint8_t *out, int w, int h);
 E264bDevice *e264b_of_decoder(struct Edge264Decoder *dec);
 
 #ifdef __cplusplus
