@@ -38,6 +38,10 @@ STREAMS = [
     # pictures where a neighbour may have been reconstructed by either kernel
     ("pb_intra_heavy",   20, 12, "-n 8 -s 77 --gop IPB --intra-pct 70 --deblock 0 --slices 3 --t8x8 50"),
     ("pb_intra_half",    13, 9,  "-n 9 -s 78 --gop IP --intra-pct 50 --deblock 0 --refs 2 --cavlc"),
+    # implicit bi-prediction weights at both ends of their range (w1 = -64 and w1 = 128: the reference's separate code path,
+    # edge264_inter.c:1152-1161) — reference B pictures + list modification put both references on one side of the picture;
+    # tests/test_weight_coverage.py proves the blocks are there
+    ("wp_implicit_extremes", 4, 4, "-n 40 -s 17 --gop IPB --bref --refs 3 --idr 23 --dpb --deblock 0 --wp 2"),
     # long-term references, list modification, memory-management operations (more of these, CPU side, in DPB_STREAMS)
     ("dpb_mmco_cabac",   4, 3, "-n 40 -s 101 --gop IP --refs 4 --idr 17 --dpb --deblock 0"),
     # B pictures used as references (verified on the B200 like the one above; its siblings run CPU side)
