@@ -86,139 +86,207 @@ __device__ __forceinline__ uint32_t add_res4(uint32_t p, const int16_t *res) {
 	                clip255((short)((int)((p >> 16) & 255) + r2)), clip255((short)((int)(p >> 24) + r3)));
 }
 
+/* ---- the kernel ----
+ * A block takes chunks of INTER_CHUNK consecutive macroblocks.  Per chunk:
+ *   1. records into shared memory; every (macroblock, list, 4x4 block) that is predicted becomes an ITEM and is queued by
+ *      interpolation class (mc_class: full, horizontal, vertical, diagonal, centre h-first, centre v-first) — warp
+ *      votes give the queue positions;
+ *   2. the warps take 32 items of ONE class at a time: the same instruction stream for all lanes, every lane busy —
+ *      window loads, interpolation, predictions (24 bytes) into shared memory;
+ *   3. a warp per macroblock: inverse transform of its coefficient run (cp.async.bulk one macroblock ahead), list-0 /
+ *      list-1 combination with the slice's weighting, residual, 128-bit row stores.
+ * A thread-per-block version without the binning ran every class present in a macroblock one after the other (about
+ * 2000 warp instructions per macroblock on random vectors, no faster than round 1's). */
+#define INTER_CHUNK 16
+#define INTER_WARPS 4
+struct __align__(16) InterSmem {
+	uint4 rec4[INTER_CHUNK][12];
+	uint32_t pred[INTER_CHUNK][2][16][8];          /* [macroblock][list][luma4x4BlkIdx]: four luma rows, 2x2 Cb, 2x2 Cr, (pad: 16-byte aligned entries) */
+	uint16_t queue[6][INTER_CHUNK * 32];           /* item = macroblock << 5 | list << 4 | luma4x4BlkIdx */
+	int qn[6];
+	WarpSmem ws[INTER_WARPS];
+	int16_t coef[INTER_WARPS][2][RES_COEF_MAX];
+	unsigned long long bars[INTER_WARPS][2];
+};
+
+template <int CLS>
+__device__ __forceinline__ void inter_item(const PicJob &J, InterSmem &sm, int item, int mb0, int W, int H) {
+	const int m = item >> 5, l = (item >> 4) & 1, z = item & 15, bx = blk_x(z), by = blk_y(z);
+	const E264MbRec *r = (const E264MbRec *)sm.rec4[m];
+	const int mb = mb0 + m, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
+	int slot = r->ref_pic[l][z >> 2];
+	if (slot < 0 || slot >= J.n_slots) slot = J.dst_slot;
+	const uint8_t *ref = J.frames + (size_t)slot * J.frame_bytes;
+	const int mvx = r->mv[l][z][0], mvy = r->mv[l][z][1];
+	const int fx = mvx & 3, fy = mvy & 3;
+	uint32_t win[9][3], py[4];
+	mc_load_luma(ref, J.stride_y, W, H, mbx * 16 + bx * 4 + (mvx >> 2) - 2, mby * 16 + by * 4 + (mvy >> 2) - 2, win);
+	uint32_t cb[3], cr[3];
+	const uint8_t *cplane = ref + J.plane_y;
+	const int cx = mbx * 8 + bx * 2 + (mvx >> 3), cy = mby * 8 + by * 2 + (mvy >> 3);
+	mc_load_chroma(cplane, J.stride_c, W >> 1, H >> 1, cx, cy, cb);
+	mc_load_chroma(cplane + (J.stride_c >> 1), J.stride_c, W >> 1, H >> 1, cx, cy, cr);
+	if (CLS == 0) {
+#pragma unroll
+		for (int y = 0; y < 4; y++) py[y] = mc_fsr(win[y + 2][0], win[y + 2][1], 16);
+	} else if (CLS == 1) mc_luma_h(win, fx, py);
+	else if (CLS == 2) mc_luma_v(win, fy, py);
+	else if (CLS == 3) mc_luma_diag(win, fx, fy, py);
+	else if (CLS == 4) mc_luma_center(win, fy, py);
+	else mc_luma_center_v(win, fx, py);
+	uint32_t *o = sm.pred[m][l][z];
+	*(uint4 *)o = make_uint4(py[0], py[1], py[2], py[3]);
+	*(uint2 *)(o + 4) = make_uint2(mc_chroma2x2(cb[0], cb[1], cb[2], mvx & 7, mvy & 7), mc_chroma2x2(cr[0], cr[1], cr[2], mvx & 7, mvy & 7));
+}
+
 template <int MINB>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MINB) e264_inter4_kernel(PicJob J) {
+__global__ void __launch_bounds__(INTER_WARPS * 32, MINB) e264_inter4_kernel(PicJob J) {
 	TraceScope trace_(J, 1);
-	__shared__ WarpSmem smem[WARPS_PER_BLOCK];
-	__shared__ InterStage stage[WARPS_PER_BLOCK][2];
-	__shared__ __align__(8) unsigned long long bars[WARPS_PER_BLOCK][2];
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	WarpSmem *ws = &smem[w];
+	__shared__ InterSmem sm;
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	WarpSmem *ws = &sm.ws[w];
 	const int nmb = J.w_mbs * J.h_mbs;
 	const int W = J.w_mbs * 16, H = J.h_mbs * 16;
 	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
 	if (lane == 0) {
-		mbar_init(&bars[w][0], 1); mbar_init(&bars[w][1], 1);
+		mbar_init(&sm.bars[w][0], 1); mbar_init(&sm.bars[w][1], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
-	__syncwarp();
-	/* stage s <- macroblock m: record through the read-only path; the coefficient run of a coded inter macroblock by the
-	 * TMA unit (bulk copy, completion counted in bytes on the warp's mbarrier).  Returns 1 inter, 2 inter with coefficients. */
-	auto issue = [&](int m, int s) -> int {
-		InterStage *st = &stage[w][s];
-		if (lane < 12) st->rec4[lane] = __ldg((const uint4 *)(J.recs + m) + lane);
-		__syncwarp();
-		const E264MbRec *r = (const E264MbRec *)st->rec4;
-		if (r->kind != MBK_INTER) return 0;
-		if (r->coded == 0) return 1;
-		if (lane == 0) tma_bulk_g2s(st->coef, J.coefs + r->coef_off, (unsigned)rec_coef_count(r) * 2u, &bars[w][s]);
-		return 2;
-	};
 	unsigned parity[2] = {0, 0};
-	/* macroblocks are dealt out by warp number: a shared ticket counter serialises in L2 (~10 cycles per atomic on one
-	 * address: 13 000 atomics per 1080p picture were most of the round-1 kernel's 77 us) and inter macroblocks cost about
-	 * the same, so a static deal balances well enough */
-	const unsigned step = gridDim.x * WARPS_PER_BLOCK;
-	unsigned t = blockIdx.x * WARPS_PER_BLOCK + w;
-	int s = 0, what = 0;
-	if (t < (unsigned)nmb) what = issue((int)t, 0);
-	while (t < (unsigned)nmb) {
-		const unsigned t2 = t + step;
-		int what2 = 0;
-		if (t2 < (unsigned)nmb) what2 = issue((int)t2, s ^ 1);
-		if (what) {
-			const int mb = (int)t, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
-			InterStage *st = &stage[w][s];
-			const E264MbRec *r = (const E264MbRec *)st->rec4;
-			const E264SliceRec *sr = J.slices + r->slice_idx;
-			/* ---- this thread's block: list l, luma4x4BlkIdx z ---- */
-			const int l = lane >> 4, z = lane & 15, bx = blk_x(z), by = blk_y(z), i8 = z >> 2;
-			const int ref_idx = r->ref_idx[l][i8];
-			uint32_t py[4] = {0, 0, 0, 0}, pcb = 0, pcr = 0;
-			if (ref_idx >= 0) {
-				int slot = r->ref_pic[l][i8];
-				if (slot < 0 || slot >= J.n_slots) slot = J.dst_slot;
-				const uint8_t *ref = J.frames + (size_t)slot * J.frame_bytes;
-				const int mvx = r->mv[l][z][0], mvy = r->mv[l][z][1];
-				uint32_t win[9][3];
-				mc_load_luma(ref, J.stride_y, W, H, mbx * 16 + bx * 4 + (mvx >> 2) - 2, mby * 16 + by * 4 + (mvy >> 2) - 2, win);
-				uint32_t cb[3], cr[3];
-				const uint8_t *cplane = ref + J.plane_y;
-				const int cx = mbx * 8 + bx * 2 + (mvx >> 3), cy = mby * 8 + by * 2 + (mvy >> 3);
-				mc_load_chroma(cplane, J.stride_c, W >> 1, H >> 1, cx, cy, cb);
-				mc_load_chroma(cplane + (J.stride_c >> 1), J.stride_c, W >> 1, H >> 1, cx, cy, cr);
-				mc_luma4x4(win, mvx & 3, mvy & 3, py);
-				pcb = mc_chroma2x2(cb[0], cb[1], cb[2], mvx & 7, mvy & 7);
-				pcr = mc_chroma2x2(cr[0], cr[1], cr[2], mvx & 7, mvy & 7);
+	const int nchunks = (nmb + INTER_CHUNK - 1) / INTER_CHUNK;
+	for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+		const int mb0 = chunk * INTER_CHUNK, cnt = min(INTER_CHUNK, nmb - mb0);
+		__syncthreads();                               /* the previous chunk's predictions and records are no longer read */
+		/* ---- 1. records, queues ---- */
+		for (int i = tid; i < cnt * 12; i += INTER_WARPS * 32) sm.rec4[i / 12][i % 12] = __ldg((const uint4 *)(J.recs + mb0) + i);
+		if (tid < 6) sm.qn[tid] = 0;
+		__syncthreads();
+		/* the macroblocks this warp finishes in step 3 are w, w + 4, ...: get the first coefficient run under way */
+		auto coef_issue = [&](int m, int b) -> int {     /* 0 not inter, 1 inter, 2 inter with coefficients (copy in flight) */
+			if (m >= cnt) return 0;
+			const E264MbRec *r = (const E264MbRec *)sm.rec4[m];
+			if (r->kind != MBK_INTER) return 0;
+			if (r->coded == 0) return 1;
+			if (lane == 0) tma_bulk_g2s(sm.coef[w][b], J.coefs + r->coef_off, (unsigned)rec_coef_count(r) * 2u, &sm.bars[w][b]);
+			return 2;
+		};
+		int what = coef_issue(w, 0);
+		for (int i0 = 0; i0 < cnt * 32; i0 += INTER_WARPS * 32) {
+			const int item = i0 + tid, m = item >> 5, l = (item >> 4) & 1, z = item & 15;
+			int cls = -1;
+			if (m < cnt) {
+				const E264MbRec *r = (const E264MbRec *)sm.rec4[m];
+				if (r->kind == MBK_INTER && r->ref_idx[l][z >> 2] >= 0) cls = mc_class(r->mv[l][z][0] & 3, r->mv[l][z][1] & 3);
 			}
-			/* ---- the inverse transform of this macroblock (all lanes), while the loads above drain ---- */
-			if (what == 2) {
-				if (!mbar_wait(&bars[w][s], parity[s])) { if (lane == 0) atomicExch(J.err, 4u); break; }
-				parity[s] ^= 1;
-				residual_stage(ws, r, sr, st->coef, lane);
+#pragma unroll
+			for (int c = 0; c < 6; c++) {
+				const unsigned mask = __ballot_sync(0xffffffffu, cls == c);
+				if (mask) {
+					int base = 0;
+					if (lane == 0) base = atomicAdd(&sm.qn[c], __popc(mask));
+					base = __shfl_sync(0xffffffffu, base, 0);
+					if (cls == c) sm.queue[c][base + __popc(mask & ((1u << lane) - 1))] = (uint16_t)item;
+				}
 			}
-			/* ---- list 1 -> list 0 thread, weighting, residual, tile ---- */
-			uint32_t qy[4], qcb, qcr;
+		}
+		__syncthreads();
+		/* ---- 2. one class at a time, 32 items per warp pass ---- */
+		{
+			int g = w;      /* this warp's next group among all groups of all classes */
 #pragma unroll
-			for (int k = 0; k < 4; k++) qy[k] = __shfl_xor_sync(0xffffffffu, py[k], 16);
-			qcb = __shfl_xor_sync(0xffffffffu, pcb, 16); qcr = __shfl_xor_sync(0xffffffffu, pcr, 16);
-			const int other = __shfl_xor_sync(0xffffffffu, ref_idx, 16);
-			if (lane < 16) {
-				const int r0 = ref_idx, r1 = other;
-				const int wpm = sr->wp_mode;
-				if (r0 >= 0 && r1 >= 0) {
-					if (wpm == WP_DEFAULT) {
-#pragma unroll
-						for (int k = 0; k < 4; k++) py[k] = mc_avg4(py[k], qy[k]);
-						pcb = mc_avg4(pcb, qcb); pcr = mc_avg4(pcr, qcr);
-					} else {
-						int w0[3], w1[3], o[3], lw[3];
-#pragma unroll
-						for (int c = 0; c < 3; c++) {
-							if (wpm == WP_EXPLICIT) { w0[c] = sr->wp_w[0][r0 & 15][c]; w1[c] = sr->wp_w[1][r1 & 15][c]; o[c] = (sr->wp_o[0][r0 & 15][c] + sr->wp_o[1][r1 & 15][c] + 1) >> 1; lw[c] = c ? sr->chroma_log2_wd : sr->luma_log2_wd; }
-							else { w1[c] = sr->implicit_w1[r0 & 15][r1 & 15]; w0[c] = 64 - w1[c]; o[c] = 0; lw[c] = 5; }
-						}
-#pragma unroll
-						for (int k = 0; k < 4; k++) py[k] = wp_word(py[k], qy[k], 3, w0[0], w1[0], o[0], lw[0]);
-						pcb = wp_word(pcb, qcb, 3, w0[1], w1[1], o[1], lw[1]); pcr = wp_word(pcr, qcr, 3, w0[2], w1[2], o[2], lw[2]);
-					}
-				} else {
-					if (r0 < 0) {
-#pragma unroll
-						for (int k = 0; k < 4; k++) py[k] = qy[k];
-						pcb = qcb; pcr = qcr;
-					}
-					if (wpm == WP_EXPLICIT && (r0 >= 0 || r1 >= 0)) {
-						const int ll = r0 >= 0 ? 0 : 1, ri = (ll ? r1 : r0) & 15;
-#pragma unroll
-						for (int k = 0; k < 4; k++) py[k] = wp_word(py[k], 0, 2, 0, sr->wp_w[ll][ri][0], sr->wp_o[ll][ri][0], sr->luma_log2_wd);
-						pcb = wp_word(pcb, 0, 2, 0, sr->wp_w[ll][ri][1], sr->wp_o[ll][ri][1], sr->chroma_log2_wd);
-						pcr = wp_word(pcr, 0, 2, 0, sr->wp_w[ll][ri][2], sr->wp_o[ll][ri][2], sr->chroma_log2_wd);
+			for (int c = 0; c < 6; c++) {
+				const int n = sm.qn[c], groups = (n + 31) >> 5;
+				for (; g < groups; g += INTER_WARPS) {
+					const int k = g * 32 + lane;
+					if (k < n) {
+						const int item = sm.queue[c][k];
+						if (c == 0) inter_item<0>(J, sm, item, mb0, W, H);
+						else if (c == 1) inter_item<1>(J, sm, item, mb0, W, H);
+						else if (c == 2) inter_item<2>(J, sm, item, mb0, W, H);
+						else if (c == 3) inter_item<3>(J, sm, item, mb0, W, H);
+						else if (c == 4) inter_item<4>(J, sm, item, mb0, W, H);
+						else inter_item<5>(J, sm, item, mb0, W, H);
 					}
 				}
+				g -= groups;
+			}
+		}
+		__syncthreads();
+		/* ---- 3. a warp per macroblock: inverse transform, weighting, residual, store ---- */
+		int b = 0;
+		bool failed = false;
+		for (int m = w; m < cnt; m += INTER_WARPS, b ^= 1) {
+			const int what2 = coef_issue(m + INTER_WARPS, b ^ 1);
+			if (what) {
+				const int mb = mb0 + m, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
+				const E264MbRec *r = (const E264MbRec *)sm.rec4[m];
+				const E264SliceRec *sr = J.slices + r->slice_idx;
 				if (what == 2) {
+					if (!mbar_wait(&sm.bars[w][b], parity[b])) { if (lane == 0) atomicExch(J.err, 4u); failed = true; }
+					parity[b] ^= 1;
+					if (!failed) residual_stage(ws, r, sr, sm.coef[w][b], lane);
+				}
+				if (lane < 16 && !failed) {
+					const int z = lane, bx = blk_x(z), by = blk_y(z), i8 = z >> 2;
+					const int r0 = r->ref_idx[0][i8], r1 = r->ref_idx[1][i8];
+					uint32_t py[4] = {0, 0, 0, 0}, pcb = 0, pcr = 0, qy[4] = {0, 0, 0, 0}, qcb = 0, qcr = 0;
+					if (r0 >= 0) { const uint4 a = *(const uint4 *)sm.pred[m][0][z]; const uint2 c2 = *(const uint2 *)(sm.pred[m][0][z] + 4); py[0] = a.x; py[1] = a.y; py[2] = a.z; py[3] = a.w; pcb = c2.x; pcr = c2.y; }
+					if (r1 >= 0) { const uint4 a = *(const uint4 *)sm.pred[m][1][z]; const uint2 c2 = *(const uint2 *)(sm.pred[m][1][z] + 4); qy[0] = a.x; qy[1] = a.y; qy[2] = a.z; qy[3] = a.w; qcb = c2.x; qcr = c2.y; }
+					const int wpm = sr->wp_mode;
+					if (r0 >= 0 && r1 >= 0) {
+						if (wpm == WP_DEFAULT) {
 #pragma unroll
-					for (int k = 0; k < 4; k++) py[k] = add_res4(py[k], ws->res + (by * 4 + k) * 16 + bx * 4);
-					{	/* chroma: two samples per row */
+							for (int k = 0; k < 4; k++) py[k] = mc_avg4(py[k], qy[k]);
+							pcb = mc_avg4(pcb, qcb); pcr = mc_avg4(pcr, qcr);
+						} else {
+							int w0[3], w1[3], o[3], lw[3];
+#pragma unroll
+							for (int c = 0; c < 3; c++) {
+								if (wpm == WP_EXPLICIT) { w0[c] = sr->wp_w[0][r0 & 15][c]; w1[c] = sr->wp_w[1][r1 & 15][c]; o[c] = (sr->wp_o[0][r0 & 15][c] + sr->wp_o[1][r1 & 15][c] + 1) >> 1; lw[c] = c ? sr->chroma_log2_wd : sr->luma_log2_wd; }
+								else { w1[c] = sr->implicit_w1[r0 & 15][r1 & 15]; w0[c] = 64 - w1[c]; o[c] = 0; lw[c] = 5; }
+							}
+#pragma unroll
+							for (int k = 0; k < 4; k++) py[k] = wp_word(py[k], qy[k], 3, w0[0], w1[0], o[0], lw[0]);
+							pcb = wp_word(pcb, qcb, 3, w0[1], w1[1], o[1], lw[1]); pcr = wp_word(pcr, qcr, 3, w0[2], w1[2], o[2], lw[2]);
+						}
+					} else {
+						if (r0 < 0) {
+#pragma unroll
+							for (int k = 0; k < 4; k++) py[k] = qy[k];
+							pcb = qcb; pcr = qcr;
+						}
+						if (wpm == WP_EXPLICIT && (r0 >= 0 || r1 >= 0)) {
+							const int ll = r0 >= 0 ? 0 : 1, ri = (ll ? r1 : r0) & 15;
+#pragma unroll
+							for (int k = 0; k < 4; k++) py[k] = wp_word(py[k], 0, 2, 0, sr->wp_w[ll][ri][0], sr->wp_o[ll][ri][0], sr->luma_log2_wd);
+							pcb = wp_word(pcb, 0, 2, 0, sr->wp_w[ll][ri][1], sr->wp_o[ll][ri][1], sr->chroma_log2_wd);
+							pcr = wp_word(pcr, 0, 2, 0, sr->wp_w[ll][ri][2], sr->wp_o[ll][ri][2], sr->chroma_log2_wd);
+						}
+					}
+					if (what == 2) {
+#pragma unroll
+						for (int k = 0; k < 4; k++) py[k] = add_res4(py[k], ws->res + (by * 4 + k) * 16 + bx * 4);
 						const int16_t *rc = ws->res + 256 + (by * 2) * 8 + bx * 2;
-						const uint32_t a = *(const uint32_t *)rc, b = *(const uint32_t *)(rc + 8), c2 = *(const uint32_t *)(rc + 64), d = *(const uint32_t *)(rc + 72);
+						const uint32_t a = *(const uint32_t *)rc, bb = *(const uint32_t *)(rc + 8), c2 = *(const uint32_t *)(rc + 64), d = *(const uint32_t *)(rc + 72);
 						pcb = mc_pack4(clip255((short)((int)(pcb & 255) + (short)(a & 0xffff))), clip255((short)((int)((pcb >> 8) & 255) + (short)(a >> 16))),
-						               clip255((short)((int)((pcb >> 16) & 255) + (short)(b & 0xffff))), clip255((short)((int)(pcb >> 24) + (short)(b >> 16))));
+						               clip255((short)((int)((pcb >> 16) & 255) + (short)(bb & 0xffff))), clip255((short)((int)(pcb >> 24) + (short)(bb >> 16))));
 						pcr = mc_pack4(clip255((short)((int)(pcr & 255) + (short)(c2 & 0xffff))), clip255((short)((int)((pcr >> 8) & 255) + (short)(c2 >> 16))),
 						               clip255((short)((int)((pcr >> 16) & 255) + (short)(d & 0xffff))), clip255((short)((int)(pcr >> 24) + (short)(d >> 16))));
 					}
-				}
 #pragma unroll
-				for (int k = 0; k < 4; k++) *(uint32_t *)&YT(bx * 4, by * 4 + k) = py[k];
-				*(uint16_t *)&CT(0, bx * 2, by * 2) = (uint16_t)pcb; *(uint16_t *)&CT(0, bx * 2, by * 2 + 1) = (uint16_t)(pcb >> 16);
-				*(uint16_t *)&CT(1, bx * 2, by * 2) = (uint16_t)pcr; *(uint16_t *)&CT(1, bx * 2, by * 2 + 1) = (uint16_t)(pcr >> 16);
+					for (int k = 0; k < 4; k++) *(uint32_t *)&YT(bx * 4, by * 4 + k) = py[k];
+					*(uint16_t *)&CT(0, bx * 2, by * 2) = (uint16_t)pcb; *(uint16_t *)&CT(0, bx * 2, by * 2 + 1) = (uint16_t)(pcb >> 16);
+					*(uint16_t *)&CT(1, bx * 2, by * 2) = (uint16_t)pcr; *(uint16_t *)&CT(1, bx * 2, by * 2 + 1) = (uint16_t)(pcr >> 16);
+				}
+				__syncwarp();
+				if (!failed) {
+					store_mb(ws, J, dst + (size_t)(mby * 16) * J.stride_y + mbx * 16, dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8, lane);
+					if (lane == 0) J.flags[mb] = J.epoch;     /* visible to the intra kernel through the kernel boundary */
+				}
+				__syncwarp();
 			}
-			__syncwarp();
-			store_mb(ws, J, dst + (size_t)(mby * 16) * J.stride_y + mbx * 16, dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8, lane);
-			if (lane == 0) J.flags[mb] = J.epoch;     /* visible to the intra kernel through the kernel boundary */
-			__syncwarp();
+			what = what2;
 		}
-		t = t2; what = what2; s ^= 1;
 	}
 }

@@ -66,20 +66,20 @@ MC_FN void mc_tr_window(const uint32_t w[9][3], uint32_t t[9][3]) {
 		}
 }
 
-/* "Horizontal family": fy == 0 (a, b, c), or fx == 2 with fy != 0 (f, j, q: centre computed horizontal pass first).
- * win rows 0..8 are y = -2..6.  Four output rows, four samples each. */
-MC_FN void mc_luma_hfamily(const uint32_t w[9][3], int fx, int fy, uint32_t out[4]) {
-	if (fy == 0) {
+/* a, b, c: horizontal half samples of rows y = 0..3 (window rows 2..5), averaged with the full sample left or right of them */
+MC_FN void mc_luma_h(const uint32_t w[9][3], int fx, uint32_t out[4]) {
 #pragma unroll
-		for (int y = 0; y < 4; y++) {
-			const uint32_t b = mc_half4(w[y + 2][0], w[y + 2][1], w[y + 2][2]);
-			/* full samples G at x = 0..3 are bytes 2..5 of the row, the right neighbours bytes 3..6 */
-			const uint32_t g = fx == 3 ? mc_fsr(w[y + 2][0], w[y + 2][1], 24) : mc_fsr(w[y + 2][0], w[y + 2][1], 16);
-			out[y] = fx == 2 ? b : mc_avg4(b, g);
-		}
-		return;
+	for (int y = 0; y < 4; y++) {
+		const uint32_t b = mc_half4(w[y + 2][0], w[y + 2][1], w[y + 2][2]);
+		/* full samples G at x = 0..3 are bytes 2..5 of the row, the right neighbours bytes 3..6 */
+		const uint32_t g = fx == 3 ? mc_fsr(w[y + 2][0], w[y + 2][1], 24) : mc_fsr(w[y + 2][0], w[y + 2][1], 16);
+		out[y] = fx == 2 ? b : mc_avg4(b, g);
 	}
-	/* centre: first pass horizontal on rows -2..6, unrounded; second pass vertical with the reference's int16 arithmetic */
+}
+/* f, j, q (xFrac 2): centre sample with the horizontal pass first — unrounded six-tap sums of rows -2..6, then the
+ * vertical pass in the reference's wrapping int16 arithmetic; f and q average it with the horizontal half sample of row
+ * y (yFrac 1) or y + 1 (yFrac 3), whose sums are already there */
+MC_FN void mc_luma_center(const uint32_t w[9][3], int fy, uint32_t out[4]) {
 	int t[9][4];
 #pragma unroll
 	for (int r = 0; r < 9; r++) mc_tap6x4(w[r][0], w[r][1], w[r][2], t[r]);
@@ -93,7 +93,7 @@ MC_FN void mc_luma_hfamily(const uint32_t w[9][3], int fx, int fy, uint32_t out[
 			v[x] = mc_clip255(((t16 >> 2) + cd + 32) >> 6);
 		}
 		uint32_t j = mc_pack4(v[0], v[1], v[2], v[3]);
-		if (fy != 2) {   /* f, q: average with the horizontal half sample of row y (b) or y+1 (s) — sums already there */
+		if (fy != 2) {
 			/* (selects, not a computed row index: the arrays must stay in registers) */
 			const int b0 = fy == 3 ? t[y + 3][0] : t[y + 2][0], b1 = fy == 3 ? t[y + 3][1] : t[y + 2][1], b2 = fy == 3 ? t[y + 3][2] : t[y + 2][2], b3 = fy == 3 ? t[y + 3][3] : t[y + 2][3];
 			const uint32_t b = mc_pack4(mc_clip255((b0 + 16) >> 5), mc_clip255((b1 + 16) >> 5), mc_clip255((b2 + 16) >> 5), mc_clip255((b3 + 16) >> 5));
@@ -102,23 +102,22 @@ MC_FN void mc_luma_hfamily(const uint32_t w[9][3], int fx, int fy, uint32_t out[
 		out[y] = j;
 	}
 }
-
-/* one 4x4 luma block at fraction (fx, fy) in quarter samples */
-MC_FN void mc_luma4x4(const uint32_t w[9][3], int fx, int fy, uint32_t out[4]) {
-	if (!(fx | fy)) {
-#pragma unroll
-		for (int y = 0; y < 4; y++) out[y] = mc_fsr(w[y + 2][0], w[y + 2][1], 16);
-		return;
-	}
-	if (fy == 0 || fx == 2) { mc_luma_hfamily(w, fx, fy, out); return; }
-	if (fx == 0 || fy == 2) {   /* vertical family = horizontal family of the transposed window */
-		uint32_t t[9][3], o[4];
-		mc_tr_window(w, t);
-		mc_luma_hfamily(t, fy, fx, o);
-		mc_tr4(o[0], o[1], o[2], o[3], out);
-		return;
-	}
-	/* e, g, p, r: average of a horizontal half sample (row y or y+1) and a vertical half sample (column x or x+1) */
+/* d, h, n (xFrac 0): the horizontal case of the transposed window */
+MC_FN void mc_luma_v(const uint32_t w[9][3], int fy, uint32_t out[4]) {
+	uint32_t t[9][3], o[4];
+	mc_tr_window(w, t);
+	mc_luma_h(t, fy, o);
+	mc_tr4(o[0], o[1], o[2], o[3], out);
+}
+/* i, k (yFrac 2, xFrac odd): centre sample with the vertical pass first = the centre case of the transposed window */
+MC_FN void mc_luma_center_v(const uint32_t w[9][3], int fx, uint32_t out[4]) {
+	uint32_t t[9][3], o[4];
+	mc_tr_window(w, t);
+	mc_luma_center(t, fx, o);
+	mc_tr4(o[0], o[1], o[2], o[3], out);
+}
+/* e, g, p, r: average of a horizontal half sample (row y or y+1) and a vertical half sample (column x or x+1) */
+MC_FN void mc_luma_diag(const uint32_t w[9][3], int fx, int fy, uint32_t out[4]) {
 	uint32_t t[9][3], vh[4], vt[4];
 	mc_tr_window(w, t);
 	/* window column 2 + x (+1 when xFrac is 3) holds the vertical half samples of output column x; selects, not computed indices */
@@ -127,6 +126,25 @@ MC_FN void mc_luma4x4(const uint32_t w[9][3], int fx, int fy, uint32_t out[4]) {
 	mc_tr4(vh[0], vh[1], vh[2], vh[3], vt);
 #pragma unroll
 	for (int y = 0; y < 4; y++) out[y] = mc_avg4(fy == 3 ? mc_half4(w[3 + y][0], w[3 + y][1], w[3 + y][2]) : mc_half4(w[2 + y][0], w[2 + y][1], w[2 + y][2]), vt[y]);
+}
+
+/* interpolation class of a fraction: 0 full sample, 1 horizontal (yFrac 0), 2 vertical (xFrac 0), 3 diagonal (both odd),
+ * 4 centre horizontal-first (xFrac 2), 5 centre vertical-first (yFrac 2, xFrac odd) */
+MC_FN int mc_class(int fx, int fy) { return !(fx | fy) ? 0 : fy == 0 ? 1 : fx == 0 ? 2 : fx == 2 ? 4 : fy == 2 ? 5 : 3; }
+
+/* one 4x4 luma block at fraction (fx, fy) in quarter samples */
+MC_FN void mc_luma4x4(const uint32_t w[9][3], int fx, int fy, uint32_t out[4]) {
+	switch (mc_class(fx, fy)) {
+	case 0:
+#pragma unroll
+		for (int y = 0; y < 4; y++) out[y] = mc_fsr(w[y + 2][0], w[y + 2][1], 16);
+		break;
+	case 1: mc_luma_h(w, fx, out); break;
+	case 2: mc_luma_v(w, fy, out); break;
+	case 3: mc_luma_diag(w, fx, fy, out); break;
+	case 4: mc_luma_center(w, fy, out); break;
+	default: mc_luma_center_v(w, fx, out); break;
+	}
 }
 
 /* 2x2 chroma samples of one plane: c[r] = bytes x = 0..3 of window row r (r = 0..2, x = 0..2 used), fractions in

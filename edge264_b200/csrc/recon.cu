@@ -303,12 +303,11 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 			else if (minb == 4) e264_inter_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
 			else e264_inter_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
 		} else {
-			/* one resident wave: every warp walks its share of the picture with the next macroblock's record and coefficients in flight */
-			static int waves = -1; if (waves < 0) { const char *e = getenv("E264B_INTER_WAVES"); waves = e ? atoi(e) : 1; }
-			int ib = (minb >= 6 ? 6 : 4) * c->sm_count * waves;
-			if (ib > blocks) ib = blocks;
-			if (minb >= 6) e264_inter4_kernel<6><<<ib, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
-			else e264_inter4_kernel<4><<<ib, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+			/* blocks take chunks of INTER_CHUNK macroblocks */
+			int ib = (nmb + INTER_CHUNK - 1) / INTER_CHUNK;
+			if (ib > c->sm_count * 8) ib = c->sm_count * 8;
+			if (minb >= 6) e264_inter4_kernel<6><<<ib, INTER_WARPS * 32, 0, c->stream>>>(J);
+			else e264_inter4_kernel<4><<<ib, INTER_WARPS * 32, 0, c->stream>>>(J);
 		}
 		c->launches++;
 	}
