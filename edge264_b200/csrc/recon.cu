@@ -62,6 +62,10 @@ struct E264bDevice {
 static std::mutex g_pool_mu;
 static std::vector<E264bDevice *> g_pool;
 
+static void free_mirror(void *p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) cudaFree(p); else { cudaGetLastError(); cudaFreeHost(p); }
+}
 static void free_geometry(E264bDevice *c) {
 	cudaStreamSynchronize(c->stream);
 	if (c->d_frames) cudaFree(c->d_frames);
@@ -130,7 +134,7 @@ extern "C" void e264b_destroy(E264bDevice *c) {
 		if (g_pool.size() < 256) { g_pool.push_back(c); return; }
 	}
 	free_geometry(c);
-	for (auto &h : c->host_free_list) cudaFreeHost(h.first);
+	for (auto &h : c->host_free_list) free_mirror(h.first);
 	c->host_free_list.clear();
 	for (int i = 0; i < E264_MAX_SLOTS; i++) cudaEventDestroy(c->rec_up[i]);
 	for (int i = 0; i < NSTAGE; i++) cudaEventDestroy(c->st[i].done);
@@ -192,7 +196,7 @@ extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots
 		return 0;
 	}
 	free_geometry(c);
-	for (auto &h : c->host_free_list) cudaFreeHost(h.first);
+	for (auto &h : c->host_free_list) free_mirror(h.first);
 	c->host_free_list.clear();
 	c->g = *g; c->n_slots = n_slots; c->nmb = (size_t)g->width_mbs * g->height_mbs;
 	c->n_stage = g->staging > 0 ? (g->staging < NSTAGE ? g->staging : NSTAGE) : 4;   /* 4 for a synchronous parser; more when pictures are parsed ahead */
@@ -230,7 +234,9 @@ extern "C" void *e264b_host_alloc(E264bDevice *c, size_t bytes) {
 		c->host_live.push_back(std::make_pair(p, bytes));
 		return p;
 	}
-	if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return NULL;
+	static int dev_out = -1;
+	if (dev_out < 0) { const char *e = getenv("E264B_OUTPUT"); dev_out = e && !strcmp(e, "device"); }
+	if ((dev_out ? cudaMalloc(&p, bytes) : cudaHostAlloc(&p, bytes, cudaHostAllocDefault)) != cudaSuccess) return NULL;
 	c->host_live.push_back(std::make_pair(p, bytes));
 	return p;
 }
@@ -241,7 +247,7 @@ extern "C" void e264b_host_free(E264bDevice *c, void *p) {
 		c->host_live.erase(c->host_live.begin() + i);
 		return;
 	}
-	cudaSetDevice(c->dev); cudaFreeHost(p);   /* not ours to pool */
+	cudaSetDevice(c->dev); free_mirror(p);   /* not ours to pool */
 }
 
 extern "C" int e264b_acquire_staging(E264bDevice *c, int slot, E264Staging *out) {
@@ -352,7 +358,10 @@ extern "C" int e264b_submit(E264bDevice *c, const E264PicDesc *pd, uint8_t *host
 			fprintf(stderr, "e264b:   -> %s, device error word %u\n", cudaGetErrorString(e), v);
 		}
 	}
-	if (host_out) { CK(cudaMemcpyAsync(host_out, c->d_frames + (size_t)pd->dst_slot * pd->frame_bytes, (size_t)pd->frame_bytes - 16, cudaMemcpyDeviceToHost, c->stream)); c->d2h_bytes += (size_t)pd->frame_bytes - 16; }
+	/* the output mirror: pinned host memory by default (D2H copy); memory the application's alloc_cb handed out may as well
+	 * be DEVICE memory — unified addressing picks the direction, the frame then reaches the application as device pointers
+	 * without ever crossing PCIe (zero-copy output); E264B_OUTPUT=device makes the decoder's own mirrors device memory */
+	if (host_out) { CK(cudaMemcpyAsync(host_out, c->d_frames + (size_t)pd->dst_slot * pd->frame_bytes, (size_t)pd->frame_bytes - 16, cudaMemcpyDefault, c->stream)); c->d2h_bytes += (size_t)pd->frame_bytes - 16; }
 	if (c->keep) {
 		KeptPic k; k.pd = *pd;
 		CK(cudaMalloc(&k.d_recs, rec_bytes)); CK(cudaMalloc(&k.d_coefs, coef_bytes + 64)); CK(cudaMalloc(&k.d_slices, sl_bytes + 64)); CK(cudaMalloc(&k.d_intra, in_bytes + 64));
