@@ -228,7 +228,7 @@ __device__ __forceinline__ void dbk_walk(const PicJob &J, DbkSmem *sm, int band,
 				bool bad = false;
 				if (act && mby > 0) {      /* lane 0 belongs to the upper row: act, mby, x are the upper row's */
 					if (wid > 0) {
-						while (*done_in < x + 1 && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
+						while (*done_in < x + 1 && !bad) { if (++spins > 8) __nanosleep(32); if ((spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 24); }
 						__threadfence_block();
 					} else if (avail < x + 1) {
 						const unsigned need = base + (unsigned)x + 1u;
@@ -243,7 +243,7 @@ __device__ __forceinline__ void dbk_walk(const PicJob &J, DbkSmem *sm, int band,
 					const bool l_out = lrow + 2 < 2 * DBK_PAIRS && mby + 2 < H;
 					if (l_out && xl >= 1 && xl <= W) {
 						volatile int *tk = sm->taken + lrow + 2;
-						while (*tk < xl - DBK_RING && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
+						while (*tk < xl - DBK_RING && !bad) { if (++spins > 8) __nanosleep(32); if ((spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 24); }
 					}
 				}
 				if (bad) atomicExch(J.err, 1u);

@@ -1,0 +1,180 @@
+/* intra_kernels.cuh — intra pictures (and any picture with more intra than inter macroblocks): the reconstruction
+ * wavefront as BANDS of rows.
+ *
+ * Intra prediction of macroblock (x, y) reads the unfiltered samples of its neighbours A (x-1, y), D, B, C (x-1..x+1, y-1)
+ * (reference: decode order edge264_slice.c:1651-1849 with the predictors of edge264_intra.c:291-765): rows can run in
+ * parallel two macroblocks apart.  Round 1 ran one warp per row with a global flag, a gpu-scope fence (which also
+ * invalidates L1) and reloads of the record, the residual and the row above from L2 inside every step: 8.7 us per
+ * macroblock step, 2.2 ms per 1080p I picture.  Here a block owns IR_ROWS consecutive rows (one warp each); the bottom
+ * sample row of every finished macroblock goes to the row below through a shared-memory ring with done/taken counters
+ * (block-scope fences); records arrive two macroblocks ahead and the residual one ahead, so a step is the prediction
+ * itself plus a shared-memory hand-shake.  Only the band's last row talks to the next block through global memory, with
+ * a progress counter published every IR_CHUNK macroblocks.  Inter macroblocks inside such a picture were reconstructed
+ * by the inter kernel before: their row warp only forwards their border samples. */
+#pragma once
+#include "recon_kernels.cuh"
+
+#define IR_ROWS 8
+#define IR_RING 16
+#define IR_CHUNK 8
+struct __align__(16) IntraRowsSmem {
+	WarpSmem ws[IR_ROWS];
+	uint4 recs[IR_ROWS][3][12];                 /* records of macroblocks x, x+1, x+2 of every row */
+	uint32_t ring[IR_ROWS][IR_RING][8];         /* bottom sample row of a finished macroblock: luma (4 words), Cb (2), Cr (2) */
+	int done[IR_ROWS];                          /* macroblocks a row has put into its ring */
+	int taken[IR_ROWS];                         /* the macroblock a row is working on: ring entries before it (minus one) are free */
+	int band;
+};
+
+__device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &sm, int band, int w, int lane) {
+	const int W = J.w_mbs, H = J.h_mbs, nmb = W * H;
+	const int lrow = w, mby = band * IR_ROWS + w;
+	if (mby >= H) return;
+	WarpSmem *ws = &sm.ws[w];
+	const bool from_global = lrow == 0 && mby > 0;
+	const bool from_ring = lrow > 0;
+	const bool to_ring = lrow + 1 < IR_ROWS && mby + 1 < H;
+	const bool to_global = lrow + 1 == IR_ROWS && mby + 1 < H;
+	volatile unsigned *prog = J.flags + nmb + 2 * H;          /* intra row progress (third counter array) */
+	const volatile unsigned *errp = J.err;
+	const unsigned base = J.epoch * 2048u;
+	volatile int *done_in = sm.done + (lrow > 0 ? lrow - 1 : 0), *done_out = sm.done + lrow;
+	volatile int *taken_me = sm.taken + lrow, *taken_next = sm.taken + (lrow + 1 < IR_ROWS ? lrow + 1 : lrow);
+	uint32_t (*ring_in)[8] = sm.ring[lrow > 0 ? lrow - 1 : 0];
+	uint32_t (*ring_out)[8] = sm.ring[lrow];
+	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
+	const int cpl = J.stride_c >> 1;
+	const E264MbRec *rowrecs = J.recs + (size_t)mby * W;
+	int avail = 0;                                            /* macroblocks of the row above the band known to be stored */
+
+	/* records two ahead, residual one ahead */
+	if (lane < 12) sm.recs[w][0][lane] = __ldg((const uint4 *)rowrecs + lane);
+	if (W > 1 && lane >= 12 && lane < 24) sm.recs[w][1][lane - 12] = __ldg((const uint4 *)(rowrecs + 1) + lane - 12);
+	__syncwarp();
+	uint4 nres0 = make_uint4(0, 0, 0, 0), nres1 = make_uint4(0, 0, 0, 0);
+	{
+		const E264MbRec *r0 = (const E264MbRec *)sm.recs[w][0];
+		if (r0->kind != MBK_INTER && r0->kind != MBK_IPCM && r0->coded != 0) {
+			const uint4 *src = (const uint4 *)(J.resid + (size_t)(mby * W) * 384);
+			nres0 = __ldg(src + lane); if (lane < 16) nres1 = __ldg(src + 32 + lane);
+		}
+	}
+#pragma unroll 1
+	for (int mbx = 0; mbx < W; mbx++) {
+		const int mb = mby * W + mbx;
+		const E264MbRec *r = (const E264MbRec *)sm.recs[w][mbx % 3];
+		const int kind = r->kind;
+		const bool has_res = kind != MBK_INTER && kind != MBK_IPCM && r->coded != 0;
+		uint8_t *Y = dst + (size_t)(mby * 16) * J.stride_y + mbx * 16;
+		uint8_t *C = dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8;
+		/* this macroblock's residual (requested one iteration ago) into the tile's residual area */
+		((uint4 *)ws->res)[lane] = has_res ? nres0 : make_uint4(0, 0, 0, 0);
+		if (lane < 16) ((uint4 *)ws->res)[32 + lane] = has_res ? nres1 : make_uint4(0, 0, 0, 0);
+		/* requests: record x+2, residual of x+1 */
+		if (mbx + 2 < W && lane < 12) sm.recs[w][(mbx + 2) % 3][lane] = __ldg((const uint4 *)(rowrecs + mbx + 2) + lane);
+		if (mbx + 1 < W) {
+			const E264MbRec *rn = (const E264MbRec *)sm.recs[w][(mbx + 1) % 3];
+			if (rn->kind != MBK_INTER && rn->kind != MBK_IPCM && rn->coded != 0) {
+				const uint4 *src = (const uint4 *)(J.resid + (size_t)(mb + 1) * 384);
+				nres0 = __ldg(src + lane); if (lane < 16) nres1 = __ldg(src + 32 + lane);
+			}
+		}
+		/* ---- wait for the row above: macroblocks up to x+1 (top-right neighbour) finished; and for room in our ring ---- */
+		if (lane == 0) {
+			unsigned spins = 0; bool bad = false;
+			const int need = min(mbx + 2, W);
+			if (from_ring) {
+				while (*done_in < need && !bad) { if (++spins > 8) __nanosleep(32); if ((spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 24); }
+				__threadfence_block();
+			} else if (from_global && avail < need) {
+				const unsigned target = base + (unsigned)need;
+				unsigned v = prog[mby - 1];
+				while ((int)(v - target) < 0 && !bad) { __nanosleep(40); if ((++spins & 255) == 0) bad = *errp != 0 || spins > (1u << 22); v = prog[mby - 1]; }
+				__threadfence();
+				avail = bad ? W : (int)(v - base);
+			}
+			if (to_ring) while (*taken_next <= mbx - IR_RING + 1 && !bad)     /* entry mbx - RING is still the corner sample of the row below's macroblock mbx - RING + 1 */ { if (++spins > 8) __nanosleep(32); if ((spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 24); }
+			if (bad) atomicExch(J.err, 1u);
+			*taken_me = mbx;
+		}
+		__syncwarp();
+		/* ---- the row above into the tile ---- */
+		if (from_ring) {
+			if (lane < 4) *(uint32_t *)&YT(4 * lane, -1) = ring_in[mbx % IR_RING][lane];
+			else if (lane < 6) { if (mbx + 1 < W) *(uint32_t *)&YT(16 + 4 * (lane - 4), -1) = ring_in[(mbx + 1) % IR_RING][lane - 4]; }
+			else if (lane == 6) { if (mbx > 0) YT(-1, -1) = (uint8_t)(ring_in[(mbx - 1) % IR_RING][3] >> 24); }
+			else if (lane >= 8 && lane < 12) *(uint32_t *)&CT((lane - 8) >> 1, 4 * (lane & 1), -1) = ring_in[mbx % IR_RING][lane - 4];
+			else if (lane == 12) { if (mbx > 0) CT(0, -1, -1) = (uint8_t)(ring_in[(mbx - 1) % IR_RING][5] >> 24); }
+			else if (lane == 13) { if (mbx > 0) CT(1, -1, -1) = (uint8_t)(ring_in[(mbx - 1) % IR_RING][7] >> 24); }
+		} else if (from_global) {
+			const int x = lane - 1;   /* -1..23 */
+			if (x < 24 && (x >= 0 || mbx > 0) && (x < 16 || mbx < W - 1)) YT(x, -1) = __ldcg(Y - J.stride_y + x);
+			if (lane < 18) { const int pl = lane / 9, cx = lane % 9 - 1; if (cx >= 0 || mbx > 0) CT(pl, cx, -1) = __ldcg(C + pl * cpl - J.stride_c + cx); }
+		}
+		__syncwarp();
+		/* ---- the macroblock ---- */
+		if (kind == MBK_INTER) {   /* reconstructed by the inter kernel: fetch its right column and bottom row for the neighbours to come */
+			if (lane < 16) YT(15, lane) = __ldcg(Y + (size_t)lane * J.stride_y + 15);
+			else { const int j = lane - 16; CT(j >> 3, 7, j & 7) = __ldcg(C + (j >> 3) * cpl + (size_t)(j & 7) * J.stride_c + 7); }
+			if (to_ring) {
+				if (lane < 4) ring_out[mbx % IR_RING][lane] = __ldcg((const uint32_t *)(Y + (size_t)15 * J.stride_y) + lane);
+				else if (lane < 8) ring_out[mbx % IR_RING][lane] = __ldcg((const uint32_t *)(C + ((lane - 4) >> 1) * cpl + (size_t)7 * J.stride_c) + (lane & 1));
+			}
+		} else {
+			if (kind == MBK_IPCM) {
+				const uint8_t *s = (const uint8_t *)(J.coefs + r->coef_off);
+				if (lane < 16) *(uint4 *)&YT(0, lane) = __ldg((const uint4 *)s + lane);
+				else { const int j = lane - 16; *(uint2 *)&CT(j >> 3, 0, j & 7) = __ldg((const uint2 *)(s + 256) + j); }
+				__syncwarp();
+			} else {
+				intra_luma(ws, r, lane);
+				intra_chroma(ws, r, lane);
+			}
+			store_mb(ws, J, Y, C, lane);
+			if (to_ring) {
+				if (lane < 4) ring_out[mbx % IR_RING][lane] = *(const uint32_t *)&YT(4 * lane, 15);
+				else if (lane < 8) ring_out[mbx % IR_RING][lane] = *(const uint32_t *)&CT((lane - 4) >> 1, 4 * (lane & 1), 7);
+			}
+		}
+		__syncwarp();
+		/* ---- publish: shared-memory counter for the row below in this band; global counter for the next band, one chunk late ---- */
+		if (lane == 0) {
+			if (to_ring) { __threadfence_block(); *done_out = mbx + 1; }
+			if (to_global && mbx > 0 && mbx % IR_CHUNK == 0) { __threadfence(); prog[mby] = base + (unsigned)mbx; }   /* covers macroblocks 0..mbx-1, stored in earlier iterations */
+		}
+		/* right-most column becomes the next macroblock's left neighbour */
+		{
+			uint8_t v = 0;
+			if (lane < 16) v = YT(15, lane);
+			else if (lane < 24) v = CT(0, 7, lane - 16);
+			const uint8_t v2 = lane < 8 ? CT(1, 7, lane) : 0;
+			__syncwarp();
+			if (lane < 16) YT(-1, lane) = v;
+			else if (lane < 24) CT(0, -1, lane - 16) = v;
+			if (lane < 8) CT(1, -1, lane) = v2;
+		}
+		avail = __shfl_sync(0xffffffffu, avail, 0);
+	}
+	__syncwarp();
+	if (lane == 0) {
+		*taken_me = W + IR_RING;       /* nothing of the ring above is needed any more */
+		if (to_global) { __threadfence(); prog[mby] = base + (unsigned)W; }
+	}
+}
+
+__global__ void __launch_bounds__(IR_ROWS * 32) e264_intra_rows_kernel(PicJob J) {
+	TraceScope trace_(J, 2);
+	__shared__ IntraRowsSmem sm;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int bands = (J.h_mbs + IR_ROWS - 1) / IR_ROWS;
+	/* bands in dispatch order: a band only waits for bands drawn before it */
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x < IR_ROWS) { sm.done[threadIdx.x] = 0; sm.taken[threadIdx.x] = 0; }
+		if (threadIdx.x == 0) sm.band = (int)atomicAdd(J.tickets + 2, 1u);
+		__syncthreads();
+		const int band = sm.band;
+		if (band >= bands) break;
+		intra_row_walk(J, sm, band, w, lane);
+	}
+}

@@ -20,6 +20,7 @@
 #include "recon_kernels.cuh"
 #include "deblock_kernels.cuh"
 #include "inter_kernels.cuh"
+#include "intra_kernels.cuh"
 extern "C" {
 #include "dec.h"
 }
@@ -318,9 +319,15 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 		c->launches++;
 	}
 	if (pd->n_intra > 0) {
-		int ib = J.rows_mode ? (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK : (pd->n_intra + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-		if (ib > cap) ib = cap;
-		e264_intra_kernel<<<ib, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++;
+		static int intra_old = -1; if (intra_old < 0) { const char *e = getenv("E264B_INTRA_OLD"); intra_old = e ? atoi(e) : 0; }
+		if (J.rows_mode && !intra_old) {   /* intra pictures: bands of rows, hand-over through shared memory */
+			e264_intra_rows_kernel<<<(J.h_mbs + IR_ROWS - 1) / IR_ROWS, IR_ROWS * 32, 0, c->stream>>>(J);
+		} else {
+			int ib = J.rows_mode ? (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK : (pd->n_intra + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+			if (ib > cap) ib = cap;
+			e264_intra_kernel<<<ib, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+		}
+		c->launches++;
 	}
 	if (with_deblock) {
 		if (dbk_old) {   /* round-1 kernel: one warp per macroblock row */
