@@ -92,7 +92,7 @@ class ReplayStats(ctypes.Structure):
                 ("kernel_ms", ctypes.c_double * 5), ("kernel_launches", ctypes.c_uint64 * 5)]
 
 
-KERNELS = ["e264_residual_kernel", "e264_inter_kernel", "e264_intra_kernel", "e264_deblock_kernel", "e264_prepass_kernel"]
+KERNELS = ["(unused)", "e264_inter4_kernel", "e264_intra_kernel / e264_intra_rows_kernel", "e264_deblock_kernel", "(unused)"]
 
 
 class ClockSampler(threading.Thread):
@@ -281,7 +281,7 @@ def main():
         core.e264b_kept_algorithmic_bytes(devs[i], ctypes.byref(r), ctypes.byref(d_), ctypes.byref(n)); rb += r.value; db += d_.value
     rb *= args.steps; db *= args.steps                      # bytes of the whole timed region on this GPU
     kms = [st.kernel_ms[k] for k in range(5)]; kn = [int(st.kernel_launches[k]) for k in range(5)]
-    groups = {"reconstruction": {"kinds": [0, 1, 2], "bytes": rb}, "deblocking": {"kinds": [4, 3], "bytes": db}}
+    groups = {"reconstruction": {"kinds": [1, 2], "bytes": rb}, "deblocking": {"kinds": [3], "bytes": db}}
     for g in groups.values():
         g["ms"] = sum(kms[k] for k in g["kinds"]); g["launches"] = max([kn[k] for k in g["kinds"]] + [1])
     dom = max(groups, key=lambda g: groups[g]["ms"])
@@ -298,7 +298,7 @@ def main():
             "traffic_note": "DRAM read+write bytes per picture of this kernel group from an ncu capture of the same streams (profiles/r2_ncu_traffic.json); algorithmic_bytes_per_launch is the figure `achieved` uses",
             "how": "achieved = algorithmic bytes of the group's launches / sum of their device spans (first block start to last block end, %globaltimer) measured inside the timed replay; launches of different streams overlap, so this is the per-launch (serialised) rate",
             "concurrent": {"achieved": (rb + db) / (st.ms_total / 1000) / 1e9, "frac": (rb + db) / (st.ms_total / 1000) / 1e9 / peak, "note": "all algorithmic bytes of the step / elapsed time of the step, every stream in flight"},
-            "per_kernel": {KERNELS[k]: {"launches": kn[k], "sum_ms": kms[k], "avg_us": 1000 * kms[k] / kn[k] if kn[k] else None} for k in range(5)},
+            "per_kernel": {KERNELS[k]: {"launches": kn[k], "sum_ms": kms[k], "avg_us": 1000 * kms[k] / kn[k] if kn[k] else None} for k in (1, 2, 3)},
             "per_group": {g: {"sum_ms": v["ms"], "algorithmic_gb": v["bytes"] / 1e9, "achieved_gbs": v["bytes"] / (v["ms"] / 1000) / 1e9 if v["ms"] > 0 else None} for g, v in groups.items()}}
 
     line = {"metric": cfg["metric"], "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

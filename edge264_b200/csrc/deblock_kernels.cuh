@@ -1,10 +1,9 @@
-/* deblock_kernels.cuh — the in-loop filter (8.7) in two kernels.
+/* deblock_kernels.cuh — the in-loop filter (8.7).
  *
- *   e264_prepass_kernel   no dependencies, one warp per macroblock: 32 boundary strengths (one lane per edge segment),
- *                         alpha / beta / tC0 of the 9 plane x edge-kind combinations -> one 64-byte E264DbkMb digest
- *                         per macroblock (reference: deblock_mb's bS derivation and table look-ups,
- *                         edge264_deblock.c:530-1123).  Block 0 also clears the picture's ticket words, so no memset
- *                         precedes a picture.
+ *   digest phase          every block first derives, for the rows of its band, a 64-byte E264DbkMb per macroblock: 32
+ *                         boundary strengths (one lane per edge segment), alpha / beta / tC0 of the 9 plane x edge-kind
+ *                         combinations (reference: deblock_mb's bS derivation and table look-ups,
+ *                         edge264_deblock.c:530-1123) — record-only work without dependencies, a warp per macroblock.
  *   e264_deblock_kernel   the sample filter as a wavefront over macroblock ROW PAIRS.  The standard fixes the order
  *                         (raster macroblocks, vertical edges left to right, then horizontal edges top to bottom;
  *                         reference order edge264_deblock.c:537-891): macroblock (x, y) needs (x-1, y) complete,
@@ -47,55 +46,46 @@ __device__ int dbk_bs_pair(const E264MbRec *p, int bp, const E264MbRec *q, int b
 #undef FAR
 }
 
-#define PRE_WARPS 4
-__global__ void __launch_bounds__(PRE_WARPS * 32) e264_prepass_kernel(PicJob J) {
-	TraceScope trace_(J, 4);
-	__shared__ uint4 recs[PRE_WARPS][3][12];
-	__shared__ __align__(16) E264DbkMb dgs[PRE_WARPS];
-	if (blockIdx.x == 0 && threadIdx.x < 8) J.tickets[threadIdx.x] = 0;    /* the kernels behind us on the stream draw from zero */
-	if (J.dbk == nullptr) return;     /* picture without deblocking: only the tickets */
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	const int nmb = J.w_mbs * J.h_mbs, W = J.w_mbs;
-	const E264MbRec *q = (const E264MbRec *)recs[w][0], *pL = (const E264MbRec *)recs[w][1], *pT = (const E264MbRec *)recs[w][2];
-	E264DbkMb *dg = &dgs[w];
-	for (int mb = blockIdx.x * PRE_WARPS + w; mb < nmb; mb += gridDim.x * PRE_WARPS) {
-		const int mbx = mb % W, mby = mb / W;
-		if (lane < 12) recs[w][0][lane] = __ldg((const uint4 *)(J.recs + mb) + lane);
-		else if (lane < 24) { if (mbx > 0) recs[w][1][lane - 12] = __ldg((const uint4 *)(J.recs + mb - 1) + lane - 12); }
-		if (lane < 12 && mby > 0) recs[w][2][lane] = __ldg((const uint4 *)(J.recs + mb - W) + lane);
-		__syncwarp();
-		const int qflags = q->flags;
-		const bool on_mb = qflags & MBF_DEBLOCK, fl = qflags & MBF_EDGE_L, ft = qflags & MBF_EDGE_T, t8 = qflags & MBF_T8x8;
-		int bs = 0;
-		{
-			const int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
-			const E264MbRec *p = q;
-			bool on = on_mb && !(t8 && (e & 1));
-			if (e == 0) { on = on && (dir ? ft : fl); p = dir ? pT : pL; }
-			if (on) {
-				const int qx = dir ? k : e, qy = dir ? e : k;
-				const int px_ = dir ? k : (e ? e - 1 : 3), py_ = dir ? (e ? e - 1 : 3) : k;
-				bs = dbk_bs_pair(p, blk_z(px_, py_), q, blk_z(qx, qy), e == 0);
-			}
+/* digest of one macroblock by one warp: 32 boundary strengths (one lane per edge segment), thresholds of the nine plane x
+ * edge-kind combinations.  recs: 3 x 12 uint4 of shared memory for the warp, dg: 64 bytes of shared memory. */
+__device__ __forceinline__ void dbk_digest_mb(const PicJob &J, uint4 (*recs)[12], E264DbkMb *dg, int mb, int lane) {
+	const int W = J.w_mbs, mbx = mb % W, mby = mb / W;
+	const E264MbRec *q = (const E264MbRec *)recs[0], *pL = (const E264MbRec *)recs[1], *pT = (const E264MbRec *)recs[2];
+	if (lane < 12) recs[0][lane] = __ldg((const uint4 *)(J.recs + mb) + lane);
+	else if (lane < 24) { if (mbx > 0) recs[1][lane - 12] = __ldg((const uint4 *)(J.recs + mb - 1) + lane - 12); }
+	if (lane < 12 && mby > 0) recs[2][lane] = __ldg((const uint4 *)(J.recs + mb - W) + lane);
+	__syncwarp();
+	const int qflags = q->flags;
+	const bool on_mb = qflags & MBF_DEBLOCK, fl = qflags & MBF_EDGE_L, ft = qflags & MBF_EDGE_T, t8 = qflags & MBF_T8x8;
+	int bs = 0;
+	{
+		const int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
+		const E264MbRec *p = q;
+		bool on = on_mb && !(t8 && (e & 1));
+		if (e == 0) { on = on && (dir ? ft : fl); p = dir ? pT : pL; }
+		if (on) {
+			const int qx = dir ? k : e, qy = dir ? e : k;
+			const int px_ = dir ? k : (e ? e - 1 : 3), py_ = dir ? (e ? e - 1 : 3) : k;
+			bs = dbk_bs_pair(p, blk_z(px_, py_), q, blk_z(qx, qy), e == 0);
 		}
-		unsigned v = (unsigned)bs << ((lane & 7) * 4);
-		v |= __shfl_xor_sync(0xffffffffu, v, 1); v |= __shfl_xor_sync(0xffffffffu, v, 2); v |= __shfl_xor_sync(0xffffffffu, v, 4);
-		if ((lane & 7) == 0) dg->bs[lane >> 3] = v;
-		if (lane < 9) {
-			const int pl = lane / 3, kind = lane % 3;
-			const E264MbRec *p = kind == 0 ? q : kind == 1 ? pL : pT;
-			if ((kind == 1 && !fl) || (kind == 2 && !ft) || !on_mb) p = q;
-			const E264SliceRec *sr = J.slices + q->slice_idx;
-			const int qpav = (p->qp[pl] + q->qp[pl] + 1) >> 1;
-			const int ia = min(max(qpav + sr->filter_offset_a, 0), 51), ib = min(max(qpav + sr->filter_offset_b, 0), 51);
-			dg->alpha[lane] = h264_alpha[ia]; dg->beta[lane] = h264_beta[ib];
-			dg->tc0[lane * 3] = h264_tc0[ia][0]; dg->tc0[lane * 3 + 1] = h264_tc0[ia][1]; dg->tc0[lane * 3 + 2] = h264_tc0[ia][2];
-		}
-		if (lane == 9) { dg->pad[0] = dg->pad[1] = dg->pad[2] = 0; }
-		__syncwarp();
-		if (lane < 4) ((uint4 *)(J.dbk + mb))[lane] = ((const uint4 *)dg)[lane];
-		__syncwarp();
 	}
+	unsigned v = (unsigned)bs << ((lane & 7) * 4);
+	v |= __shfl_xor_sync(0xffffffffu, v, 1); v |= __shfl_xor_sync(0xffffffffu, v, 2); v |= __shfl_xor_sync(0xffffffffu, v, 4);
+	if ((lane & 7) == 0) dg->bs[lane >> 3] = v;
+	if (lane < 9) {
+		const int pl = lane / 3, kind = lane % 3;
+		const E264MbRec *p = kind == 0 ? q : kind == 1 ? pL : pT;
+		if ((kind == 1 && !fl) || (kind == 2 && !ft) || !on_mb) p = q;
+		const E264SliceRec *sr = J.slices + q->slice_idx;
+		const int qpav = (p->qp[pl] + q->qp[pl] + 1) >> 1;
+		const int ia = min(max(qpav + sr->filter_offset_a, 0), 51), ib = min(max(qpav + sr->filter_offset_b, 0), 51);
+		dg->alpha[lane] = h264_alpha[ia]; dg->beta[lane] = h264_beta[ib];
+		dg->tc0[lane * 3] = h264_tc0[ia][0]; dg->tc0[lane * 3 + 1] = h264_tc0[ia][1]; dg->tc0[lane * 3 + 2] = h264_tc0[ia][2];
+	}
+	if (lane == 9) { dg->pad[0] = dg->pad[1] = dg->pad[2] = 0; }
+	__syncwarp();
+	if (lane < 4) ((uint4 *)(J.dbk + mb))[lane] = ((const uint4 *)dg)[lane];
+	__syncwarp();
 }
 
 /* ---- sample filters on one line across an edge, samples as ints ----
@@ -147,6 +137,7 @@ struct __align__(16) DbkSmem {
 	uint32_t top[DBK_PAIRS][2][4][4];                /* [half][row][word]: luma rows -4..-1; chroma [plane * 2 + row -2..-1][2 words] */
 	E264DbkMb dg[DBK_PAIRS][2];
 	uint32_t ring[2 * DBK_PAIRS][DBK_RING][4][4];    /* per row of the band: bottom sample rows of its finished macroblocks [x % RING], layout of top */
+	uint4 drecs[DBK_PAIRS][3][12];                   /* digest phase: records of the current, left and top macroblock per warp */
 	int done[2 * DBK_PAIRS];                         /* macroblocks a row has put into its ring */
 	int taken[2 * DBK_PAIRS];                        /* macroblocks a row has taken from the ring of the row above */
 	int band;
@@ -206,7 +197,7 @@ __device__ __forceinline__ void dbk_walk(const PicJob &J, DbkSmem *sm, int band,
 	if (half == 0 && row_ok && W > 0) {
 		if (CH) { uint2 v = *(const uint2 *)rowp; nxt[0] = v.x; nxt[1] = v.y; }
 		else { uint4 v = *(const uint4 *)rowp; nxt[0] = v.x; nxt[1] = v.y; nxt[2 % NW] = v.z; nxt[3 % NW] = v.w; }
-		if (hl < 4) ndg = __ldg((const uint4 *)dgp + hl);
+		if (hl < 4) ndg = *((const uint4 *)dgp + hl);
 	}
 
 #pragma unroll 1
@@ -228,7 +219,7 @@ __device__ __forceinline__ void dbk_walk(const PicJob &J, DbkSmem *sm, int band,
 				bool bad = false;
 				if (act && mby > 0) {      /* lane 0 belongs to the upper row: act, mby, x are the upper row's */
 					if (wid > 0) {
-						while (*done_in < x + 1 && !bad) { if (++spins > 8) __nanosleep(32); if ((spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 24); }
+						while (*done_in < x + 1 && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
 						__threadfence_block();
 					} else if (avail < x + 1) {
 						const unsigned need = base + (unsigned)x + 1u;
@@ -243,7 +234,7 @@ __device__ __forceinline__ void dbk_walk(const PicJob &J, DbkSmem *sm, int band,
 					const bool l_out = lrow + 2 < 2 * DBK_PAIRS && mby + 2 < H;
 					if (l_out && xl >= 1 && xl <= W) {
 						volatile int *tk = sm->taken + lrow + 2;
-						while (*tk < xl - DBK_RING && !bad) { if (++spins > 8) __nanosleep(32); if ((spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 24); }
+						while (*tk < xl - DBK_RING && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
 					}
 				}
 				if (bad) atomicExch(J.err, 1u);
@@ -270,7 +261,7 @@ __device__ __forceinline__ void dbk_walk(const PicJob &J, DbkSmem *sm, int band,
 			if (nact) {
 				if (CH) { uint2 v = *(const uint2 *)(rowp + xn * MBW); nxt[0] = v.x; nxt[1] = v.y; }
 				else { uint4 v = *(const uint4 *)(rowp + xn * MBW); nxt[0] = v.x; nxt[1] = v.y; nxt[2 % NW] = v.z; nxt[3 % NW] = v.w; }
-				if (hl < 4) ndg = __ldg((const uint4 *)(dgp + xn) + hl);
+				if (hl < 4) ndg = *((const uint4 *)(dgp + xn) + hl);
 			}
 			have_top = from_global && nact && avail >= xn + 1;     /* already known to be stored: no flag access */
 			if (have_top && top_lane) {
@@ -392,8 +383,13 @@ __device__ __forceinline__ void dbk_walk(const PicJob &J, DbkSmem *sm, int band,
 	if (to_global && hl == 0) { __threadfence(); prog[mby] = base + (unsigned)W; }
 }
 
-__global__ void __launch_bounds__(DBK_PAIRS * 32) e264_deblock_kernel(PicJob J) {
+/* MINB blocks per SM = the register budget: the kernel is a chain of dependent steps (a lone warp per scheduler issues
+ * about one instruction in five cycles) and holds its registers for the whole picture, so with many pictures in flight
+ * the registers of waiting deblocking warps are what the other kernels lack */
+template <int MINB>
+__global__ void __launch_bounds__(DBK_PAIRS * 32, MINB) e264_deblock_kernel(PicJob J) {
 	TraceScope trace_(J, 3);
+	reset_next_tickets(J);
 	__shared__ DbkSmem sm;
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const int bands = (J.h_mbs + 2 * DBK_PAIRS - 1) / (2 * DBK_PAIRS);
@@ -405,6 +401,12 @@ __global__ void __launch_bounds__(DBK_PAIRS * 32) e264_deblock_kernel(PicJob J) 
 		__syncthreads();
 		const int t = sm.band;
 		if (t >= 2 * bands) break;
+		{	/* the band's digests (record-only work, a warp per macroblock); the luma and the chroma block of a band both derive
+			 * them — identical values — rather than wait for each other */
+			const int first = (t >> 1) * 2 * DBK_PAIRS * J.w_mbs, last = min(first + 2 * DBK_PAIRS * J.w_mbs, J.w_mbs * J.h_mbs);
+			for (int mb = first + wid; mb < last; mb += DBK_PAIRS) dbk_digest_mb(J, sm.drecs[wid], &sm.dg[wid][0], mb, lane);
+		}
+		__syncthreads();
 		if (t & 1) dbk_walk<true>(J, &sm, t >> 1, wid, lane);
 		else dbk_walk<false>(J, &sm, t >> 1, wid, lane);
 	}

@@ -10,8 +10,8 @@
  * The macroblock's coefficient run (16..816 bytes) arrives by cp.async.bulk on an mbarrier one macroblock ahead and is
  * inverse-transformed in shared memory (residual_stage), so the residual never travels through global memory.
  * Round 1's kernel (rectangles regrouped on the device, windows by cp.async.bulk.tensor into shared memory, one output
- * sample per lane and loop iteration) needed ~3600 warp instructions per macroblock; it stays selectable with
- * E264B_INTER_OLD=1 for A/B runs. */
+ * sample per lane and loop iteration) needed ~3600 warp instructions per macroblock and 77 us per 1080p picture against
+ * 38 us here (profiles/README.md). */
 #pragma once
 #include "recon_kernels.cuh"
 #include "mc_math.cuh"
@@ -142,6 +142,7 @@ __device__ __forceinline__ void inter_item(const PicJob &J, InterSmem &sm, int i
 template <int MINB>
 __global__ void __launch_bounds__(INTER_WARPS * 32, MINB) e264_inter4_kernel(PicJob J) {
 	TraceScope trace_(J, 1);
+	reset_next_tickets(J);
 	__shared__ InterSmem sm;
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	WarpSmem *ws = &sm.ws[w];

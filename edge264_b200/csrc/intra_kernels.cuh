@@ -7,8 +7,9 @@
  * invalidates L1) and reloads of the record, the residual and the row above from L2 inside every step: 8.7 us per
  * macroblock step, 2.2 ms per 1080p I picture.  Here a block owns IR_ROWS consecutive rows (one warp each); the bottom
  * sample row of every finished macroblock goes to the row below through a shared-memory ring with done/taken counters
- * (block-scope fences); records arrive two macroblocks ahead and the residual one ahead, so a step is the prediction
- * itself plus a shared-memory hand-shake.  Only the band's last row talks to the next block through global memory, with
+ * (block-scope fences); records arrive two macroblocks ahead, coefficient runs one ahead (cp.async.bulk on an mbarrier) and
+ * are inverse-transformed BEFORE the row waits for its neighbours, so a step is the prediction itself plus a
+ * shared-memory hand-shake and the residual never travels through global memory.  Only the band's last row talks to the next block through global memory, with
  * a progress counter published every IR_CHUNK macroblocks.  Inter macroblocks inside such a picture were reconstructed
  * by the inter kernel before: their row warp only forwards their border samples. */
 #pragma once
@@ -21,12 +22,14 @@ struct __align__(16) IntraRowsSmem {
 	WarpSmem ws[IR_ROWS];
 	uint4 recs[IR_ROWS][3][12];                 /* records of macroblocks x, x+1, x+2 of every row */
 	uint32_t ring[IR_ROWS][IR_RING][8];         /* bottom sample row of a finished macroblock: luma (4 words), Cb (2), Cr (2) */
+	int16_t coef[IR_ROWS][2][RES_COEF_MAX];     /* coefficient runs of macroblocks x, x+1 of every row (cp.async.bulk) */
+	unsigned long long bars[IR_ROWS][2];
 	int done[IR_ROWS];                          /* macroblocks a row has put into its ring */
 	int taken[IR_ROWS];                         /* the macroblock a row is working on: ring entries before it (minus one) are free */
 	int band;
 };
 
-__device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &sm, int band, int w, int lane) {
+__device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &sm, int band, int w, int lane, unsigned (&parity)[2]) {
 	const int W = J.w_mbs, H = J.h_mbs, nmb = W * H;
 	const int lrow = w, mby = band * IR_ROWS + w;
 	if (mby >= H) return;
@@ -47,44 +50,43 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 	const E264MbRec *rowrecs = J.recs + (size_t)mby * W;
 	int avail = 0;                                            /* macroblocks of the row above the band known to be stored */
 
-	/* records two ahead, residual one ahead */
+	/* records two ahead, coefficient runs one ahead */
 	if (lane < 12) sm.recs[w][0][lane] = __ldg((const uint4 *)rowrecs + lane);
 	if (W > 1 && lane >= 12 && lane < 24) sm.recs[w][1][lane - 12] = __ldg((const uint4 *)(rowrecs + 1) + lane - 12);
 	__syncwarp();
-	uint4 nres0 = make_uint4(0, 0, 0, 0), nres1 = make_uint4(0, 0, 0, 0);
-	{
-		const E264MbRec *r0 = (const E264MbRec *)sm.recs[w][0];
-		if (r0->kind != MBK_INTER && r0->kind != MBK_IPCM && r0->coded != 0) {
-			const uint4 *src = (const uint4 *)(J.resid + (size_t)(mby * W) * 384);
-			nres0 = __ldg(src + lane); if (lane < 16) nres1 = __ldg(src + 32 + lane);
-		}
-	}
+	auto coef_issue = [&](int x) -> bool {       /* true: a copy is in flight into buffer x & 1 */
+		const E264MbRec *rr = (const E264MbRec *)sm.recs[w][x % 3];
+		if (rr->kind == MBK_INTER || rr->kind == MBK_IPCM || rr->coded == 0) return false;
+		if (lane == 0) tma_bulk_g2s(sm.coef[w][x & 1], J.coefs + rr->coef_off, (unsigned)rec_coef_count(rr) * 2u, &sm.bars[w][x & 1]);
+		return true;
+	};
+	bool pending = coef_issue(0);
 #pragma unroll 1
 	for (int mbx = 0; mbx < W; mbx++) {
-		const int mb = mby * W + mbx;
 		const E264MbRec *r = (const E264MbRec *)sm.recs[w][mbx % 3];
 		const int kind = r->kind;
-		const bool has_res = kind != MBK_INTER && kind != MBK_IPCM && r->coded != 0;
 		uint8_t *Y = dst + (size_t)(mby * 16) * J.stride_y + mbx * 16;
 		uint8_t *C = dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8;
-		/* this macroblock's residual (requested one iteration ago) into the tile's residual area */
-		((uint4 *)ws->res)[lane] = has_res ? nres0 : make_uint4(0, 0, 0, 0);
-		if (lane < 16) ((uint4 *)ws->res)[32 + lane] = has_res ? nres1 : make_uint4(0, 0, 0, 0);
-		/* requests: record x+2, residual of x+1 */
+		/* requests: record x+2, coefficient run of x+1 */
 		if (mbx + 2 < W && lane < 12) sm.recs[w][(mbx + 2) % 3][lane] = __ldg((const uint4 *)(rowrecs + mbx + 2) + lane);
-		if (mbx + 1 < W) {
-			const E264MbRec *rn = (const E264MbRec *)sm.recs[w][(mbx + 1) % 3];
-			if (rn->kind != MBK_INTER && rn->kind != MBK_IPCM && rn->coded != 0) {
-				const uint4 *src = (const uint4 *)(J.resid + (size_t)(mb + 1) * 384);
-				nres0 = __ldg(src + lane); if (lane < 16) nres1 = __ldg(src + 32 + lane);
-			}
+		const bool pending_next = mbx + 1 < W ? coef_issue(mbx + 1) : false;
+		/* this macroblock's residual — before the wait below: in the steady wavefront the row above is not ready yet anyway */
+		if (pending) {
+			if (!mbar_wait(&sm.bars[w][mbx & 1], parity[mbx & 1])) { if (lane == 0) atomicExch(J.err, 3u); }
+			parity[mbx & 1] ^= 1;
+			residual_stage(ws, r, J.slices + r->slice_idx, sm.coef[w][mbx & 1], lane);
+		} else if (kind != MBK_INTER && kind != MBK_IPCM) {
+			((uint4 *)ws->res)[lane] = make_uint4(0, 0, 0, 0);
+			if (lane < 16) ((uint4 *)ws->res)[32 + lane] = make_uint4(0, 0, 0, 0);
+			__syncwarp();
 		}
+		pending = pending_next;
 		/* ---- wait for the row above: macroblocks up to x+1 (top-right neighbour) finished; and for room in our ring ---- */
 		if (lane == 0) {
 			unsigned spins = 0; bool bad = false;
 			const int need = min(mbx + 2, W);
 			if (from_ring) {
-				while (*done_in < need && !bad) { if (++spins > 8) __nanosleep(32); if ((spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 24); }
+				while (*done_in < need && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
 				__threadfence_block();
 			} else if (from_global && avail < need) {
 				const unsigned target = base + (unsigned)need;
@@ -93,7 +95,7 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 				__threadfence();
 				avail = bad ? W : (int)(v - base);
 			}
-			if (to_ring) while (*taken_next <= mbx - IR_RING + 1 && !bad)     /* entry mbx - RING is still the corner sample of the row below's macroblock mbx - RING + 1 */ { if (++spins > 8) __nanosleep(32); if ((spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 24); }
+			if (to_ring) while (*taken_next <= mbx - IR_RING + 1 && !bad)     /* entry mbx - RING is still the corner sample of the row below's macroblock mbx - RING + 1 */ { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
 			if (bad) atomicExch(J.err, 1u);
 			*taken_me = mbx;
 		}
@@ -164,17 +166,112 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 
 __global__ void __launch_bounds__(IR_ROWS * 32) e264_intra_rows_kernel(PicJob J) {
 	TraceScope trace_(J, 2);
+	reset_next_tickets(J);
 	__shared__ IntraRowsSmem sm;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	const int bands = (J.h_mbs + IR_ROWS - 1) / IR_ROWS;
+	unsigned parity[2] = {0, 0};
+	if (lane == 0) {
+		mbar_init(&sm.bars[w][0], 1); mbar_init(&sm.bars[w][1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
 	/* bands in dispatch order: a band only waits for bands drawn before it */
 	for (;;) {
 		__syncthreads();
 		if (threadIdx.x < IR_ROWS) { sm.done[threadIdx.x] = 0; sm.taken[threadIdx.x] = 0; }
 		if (threadIdx.x == 0) sm.band = (int)atomicAdd(J.tickets + 2, 1u);
+
 		__syncthreads();
 		const int band = sm.band;
 		if (band >= bands) break;
-		intra_row_walk(J, sm, band, w, lane);
+		intra_row_walk(J, sm, band, w, lane, parity);
+	}
+}
+
+
+/* ---- intra macroblocks of P and B pictures ----
+ * The parser lists them in raster order (E264Staging.intra_list); warps draw list entries by ticket, so a macroblock
+ * only ever waits for entries drawn before its own.  Neighbours: A, D, B, C "reconstructed" flags — inter neighbours were
+ * flagged by e264_inter4_kernel (kernel boundary), intra ones are flagged here after a fence.  The coefficient run is
+ * fetched (cp.async.bulk) and inverse-transformed while the neighbours finish. */
+struct __align__(16) IntraTkSmem {
+	WarpSmem ws[WARPS_PER_BLOCK];
+	int16_t coef[WARPS_PER_BLOCK][RES_COEF_MAX];
+	unsigned long long bars[WARPS_PER_BLOCK];
+};
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_intra_kernel(PicJob J) {
+	TraceScope trace_(J, 2);
+	reset_next_tickets(J);
+	__shared__ IntraTkSmem sm;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	WarpSmem *ws = &sm.ws[w];
+	const int nmb = J.w_mbs * J.h_mbs, W = J.w_mbs, cpl = J.stride_c >> 1;
+	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
+	unsigned parity = 0;
+	if (lane == 0) {
+		mbar_init(&sm.bars[w], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	__syncwarp();
+	for (;;) {
+		unsigned t = 0;
+		if (lane == 0) t = atomicAdd(J.tickets + 2, 1u);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t >= (unsigned)J.n_intra) break;
+		const int mb = (int)__ldg(J.intra_list + t);
+		if (mb >= nmb) continue;
+		const int mbx = mb % W, mby = mb / W;
+		if (lane < 12) ws->rec4[lane] = __ldg((const uint4 *)(J.recs + mb) + lane);
+		__syncwarp();
+		const E264MbRec *r = (const E264MbRec *)ws->rec4;
+		const int kind = r->kind;
+		if (kind == MBK_INTER) continue;      /* (the list holds intra macroblocks only) */
+		uint8_t *Y = dst + (size_t)(mby * 16) * J.stride_y + mbx * 16;
+		uint8_t *C = dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8;
+		if (kind == MBK_IPCM) {
+			const uint8_t *s = (const uint8_t *)(J.coefs + r->coef_off);
+			if (lane < 16) *(uint4 *)&YT(0, lane) = __ldg((const uint4 *)s + lane);
+			else { const int j = lane - 16; *(uint2 *)&CT(j >> 3, 0, j & 7) = __ldg((const uint2 *)(s + 256) + j); }
+			__syncwarp();
+			store_mb(ws, J, Y, C, lane);
+		} else {
+			const bool coded = r->coded != 0;
+			if (coded && lane == 0) tma_bulk_g2s(sm.coef[w], J.coefs + r->coef_off, (unsigned)rec_coef_count(r) * 2u, &sm.bars[w]);
+			if (coded) {
+				if (!mbar_wait(&sm.bars[w], parity)) { if (lane == 0) atomicExch(J.err, 3u); }
+				parity ^= 1;
+				residual_stage(ws, r, J.slices + r->slice_idx, sm.coef[w], lane);
+			} else {
+				((uint4 *)ws->res)[lane] = make_uint4(0, 0, 0, 0);
+				if (lane < 16) ((uint4 *)ws->res)[32 + lane] = make_uint4(0, 0, 0, 0);
+			}
+			bool ok = true;
+			if (lane == 0) {
+				if (mbx > 0) ok = wait_flag(J.flags, mb - 1, J.epoch, J.err);
+				if (ok && mby > 0 && mbx > 0) ok = wait_flag(J.flags, mb - W - 1, J.epoch, J.err);
+				if (ok && mby > 0) ok = wait_flag(J.flags, mb - W, J.epoch, J.err);
+				if (ok && mby > 0) ok = wait_flag(J.flags, mbx < W - 1 ? mb - W + 1 : mb - W, J.epoch, J.err);
+				__threadfence();
+			}
+			__syncwarp();
+			if (mby > 0) {
+				const int x = lane - 1;   /* -1..23 */
+				if (x < 24 && (x >= 0 || mbx > 0) && (x < 16 || mbx < W - 1)) YT(x, -1) = __ldcg(Y - J.stride_y + x);
+				if (lane < 18) { const int pl = lane / 9, cx = lane % 9 - 1; if (cx >= 0 || mbx > 0) CT(pl, cx, -1) = __ldcg(C + pl * cpl - J.stride_c + cx); }
+			}
+			if (mbx > 0) {
+				if (lane < 16) YT(-1, lane) = __ldcg(Y + (size_t)lane * J.stride_y - 1);
+				else { const int j = lane - 16, pl = j >> 3, row = j & 7; CT(pl, -1, row) = __ldcg(C + pl * cpl + (size_t)row * J.stride_c - 1); }
+			}
+			__syncwarp();
+			intra_luma(ws, r, lane);
+			intra_chroma(ws, r, lane);
+			store_mb(ws, J, Y, C, lane);
+		}
+		__syncwarp();
+		if (lane == 0) { __threadfence(); *(volatile unsigned *)(J.flags + mb) = J.epoch; }
+		__syncwarp();
 	}
 }

@@ -9,7 +9,6 @@
  * There is NO CPU fallback: without a CUDA device e264b_create() fails and edge264_alloc() returns NULL.
  */
 #include <cuda_runtime.h>
-#include <cuda.h>            /* CUtensorMap types only: the encoder is resolved at run time, libcuda is not linked */
 #include <stdio.h>
 #include <time.h>
 #include <unistd.h>
@@ -32,7 +31,6 @@ extern "C" {
 
 struct Staging {
 	E264MbRec *d_recs; int16_t *d_coefs, *h_coefs; E264SliceRec *d_slices, *h_slices;
-	int16_t *d_resid;            /* residual of the picture in flight: nmb x 384 int16 */
 	E264DbkMb *d_dbk;            /* deblocking digests of the picture in flight */
 	uint32_t *d_intra, *h_intra; /* intra macroblock list */
 	cudaEvent_t done; bool busy;
@@ -43,7 +41,6 @@ struct E264bDevice {
 	int dev; cudaStream_t stream;
 	E264PicDesc g; int n_slots; size_t nmb; uint32_t coef_cap;
 	uint8_t *d_frames;
-	void *d_tmaps;               /* CUtensorMap[n_slots][6] over the frame pool, or NULL when the geometry does not fit TMA's rules */
 	E264MbRec *h_recs[E264_MAX_SLOTS]; cudaEvent_t rec_up[E264_MAX_SLOTS]; bool rec_busy[E264_MAX_SLOTS];
 	Staging st[NSTAGE]; int stage, n_stage;
 	unsigned *d_sync;            /* [0..7] tickets (0 inter, 1 deblock, 2 intra), [8] err, [16..) flags[nmb] + row progress[3 * h_mbs] */
@@ -71,12 +68,10 @@ static void free_geometry(E264bDevice *c) {
 	cudaStreamSynchronize(c->stream);
 	if (c->d_frames) cudaFree(c->d_frames);
 	c->d_frames = NULL;
-	if (c->d_tmaps) cudaFree(c->d_tmaps);
-	c->d_tmaps = NULL;
 	for (int i = 0; i < E264_MAX_SLOTS; i++) { if (c->h_recs[i]) cudaFreeHost(c->h_recs[i]); c->h_recs[i] = NULL; c->rec_busy[i] = false; }
 	for (int i = 0; i < NSTAGE; i++) {
 		Staging *s = &c->st[i];
-		if (s->d_recs) cudaFree(s->d_recs); if (s->d_coefs) cudaFree(s->d_coefs); if (s->d_slices) cudaFree(s->d_slices); if (s->d_resid) cudaFree(s->d_resid); s->d_resid = NULL;
+		if (s->d_recs) cudaFree(s->d_recs); if (s->d_coefs) cudaFree(s->d_coefs); if (s->d_slices) cudaFree(s->d_slices);
 		if (s->d_dbk) cudaFree(s->d_dbk); if (s->d_intra) cudaFree(s->d_intra); if (s->h_intra) cudaFreeHost(s->h_intra); s->d_dbk = NULL; s->d_intra = NULL; s->h_intra = NULL;
 		if (s->h_coefs) cudaFreeHost(s->h_coefs); if (s->h_slices) cudaFreeHost(s->h_slices);
 		s->d_recs = NULL; s->d_coefs = NULL; s->d_slices = NULL; s->h_coefs = NULL; s->h_slices = NULL; s->busy = false;
@@ -107,7 +102,7 @@ extern "C" int e264b_create(E264bDevice **out) {
 		}
 	}
 	E264bDevice *c = new E264bDevice();
-	c->dev = 0; c->stream = 0; memset(&c->g, 0, sizeof(c->g)); c->n_slots = 0; c->nmb = 0; c->coef_cap = 0; c->d_frames = NULL; c->d_tmaps = NULL;
+	c->dev = 0; c->stream = 0; memset(&c->g, 0, sizeof(c->g)); c->n_slots = 0; c->nmb = 0; c->coef_cap = 0; c->d_frames = NULL;
 	memset(c->h_recs, 0, sizeof(c->h_recs)); memset(c->rec_busy, 0, sizeof(c->rec_busy)); memset(c->st, 0, sizeof(c->st)); c->stage = 0; c->d_sync = NULL; c->epoch = 0; c->tick_seq = 0;
 	c->launches = c->h2d_bytes = c->d2h_bytes = 0;
 	c->dev = dev;
@@ -146,45 +141,6 @@ extern "C" void e264b_destroy(E264bDevice *c) {
 }
 
 
-/* Tensor maps for the motion-compensation windows: per frame slot, luma boxes 48 x {21,13,9} over the W x H luma
- * plane and chroma boxes 32 x {9,5,3} over the Cb|Cr rows (one 2-D tensor: Cr starts stride_c/2 bytes into a row).
- * Returns 0 and leaves d_tmaps NULL when TMA cannot describe the geometry (tiny pictures, odd strides, old driver):
- * the kernel then gathers every window with clamped loads. */
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int build_tensor_maps(E264bDevice *c) {
-	const E264PicDesc *g = &c->g;
-	const int W = g->width_mbs * 16, H = g->height_mbs * 16;
-	if (W < 48 || H < 32 || (g->stride_y & 15) || (g->stride_c & 15) || (g->plane_y & 15) || (g->frame_bytes & 15)) return 0;
-	/* resolved once per process; decoders are created from many threads at once (one per stream), so the lookup is
-	 * serialised — a thread must never see "tried" without the pointer and silently lose the TMA path */
-	static EncodeTiledFn enc = NULL; static std::once_flag enc_once;
-	std::call_once(enc_once, [] {
-		void *fn = NULL; cudaDriverEntryPointQueryResult q;
-		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) enc = (EncodeTiledFn)fn;
-		else { cudaGetLastError(); fprintf(stderr, "edge264_b200: cuTensorMapEncodeTiled unavailable, windows fall back to gathered loads\n"); }
-	});
-	if (!enc) return 0;
-	static const cuuint32_t lrows[3] = {21, 13, 9}, crows[3] = {9, 5, 3};
-	/* six rank-3 maps (x, y, frame slot) serve every reference of every picture: few enough to stay in the TMA
-	 * unit's descriptor cache (with six maps per slot the issue of the three loads took 25% of the warps' time) */
-	std::vector<CUtensorMap> maps(6);
-	for (int k = 0; k < 6; k++) {
-		const bool chroma = k >= 3;
-		uint8_t *base = c->d_frames + (chroma ? g->plane_y : 0);
-		cuuint64_t dims[3] = {(cuuint64_t)(chroma ? (g->stride_c >> 1) + (W >> 1) : W), (cuuint64_t)(chroma ? H >> 1 : H), (cuuint64_t)c->n_slots};
-		cuuint64_t strides[2] = {(cuuint64_t)(chroma ? g->stride_c : g->stride_y), (cuuint64_t)g->frame_bytes};
-		cuuint32_t box[3] = {chroma ? 32u : 48u, chroma ? crows[k - 3] : lrows[k], 1};
-		cuuint32_t estr[3] = {1, 1, 1};
-		CUresult r = enc(&maps[k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
-		                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-		if (r != CUDA_SUCCESS) { fprintf(stderr, "edge264_b200: cuTensorMapEncodeTiled failed (%d) for %dx%d, windows fall back to gathered loads\n", (int)r, W, H); return 0; }
-	}
-	CK(cudaMalloc(&c->d_tmaps, maps.size() * sizeof(CUtensorMap)));
-	CK(cudaMemcpy(c->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-	return 0;
-}
-
 extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots) {
 	CK(cudaSetDevice(c->dev));
 	if (c->d_frames && c->n_slots == n_slots && !memcmp(&c->g, g, sizeof(*g))) {   /* pooled context of the same geometry */
@@ -205,14 +161,12 @@ extern "C" int e264b_configure(E264bDevice *c, const E264PicDesc *g, int n_slots
 	size_t pool = (size_t)g->frame_bytes * n_slots;
 	CK(cudaMalloc(&c->d_frames, pool + 256));
 	CK(cudaMemsetAsync(c->d_frames, 128, pool + 256, c->stream));
-	if (build_tensor_maps(c)) return -1;
 	for (int i = 0; i < n_slots; i++) CK(cudaHostAlloc(&c->h_recs[i], c->nmb * sizeof(E264MbRec), cudaHostAllocDefault));
 	for (int i = 0; i < c->n_stage; i++) {
 		Staging *s = &c->st[i];
 		CK(cudaMalloc(&s->d_recs, c->nmb * sizeof(E264MbRec)));
 		CK(cudaMalloc(&s->d_coefs, (size_t)c->coef_cap * 2 + 64));
 		CK(cudaMalloc(&s->d_slices, E264_MAX_SLICES * sizeof(E264SliceRec)));
-		CK(cudaMalloc(&s->d_resid, c->nmb * 384 * sizeof(int16_t)));
 		CK(cudaHostAlloc(&s->h_coefs, (size_t)c->coef_cap * 2 + 64, cudaHostAllocDefault));
 		CK(cudaHostAlloc(&s->h_slices, E264_MAX_SLICES * sizeof(E264SliceRec), cudaHostAllocDefault));
 		CK(cudaMalloc(&s->d_dbk, c->nmb * sizeof(E264DbkMb)));
@@ -266,77 +220,51 @@ static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, int stage, const E
 	J.recs = recs; J.coefs = coefs; J.slices = slices; J.frames = c->d_frames;
 	J.frame_bytes = pd->frame_bytes; J.w_mbs = pd->width_mbs; J.h_mbs = pd->height_mbs;
 	J.stride_y = pd->stride_y; J.stride_c = pd->stride_c; J.plane_y = pd->plane_y; J.dst_slot = pd->dst_slot; J.n_slots = c->n_slots;
-	J.tickets = c->d_sync; J.err = c->d_sync + 8; J.flags = c->d_sync + 16;
-	J.resid = c->st[stage].d_resid;
+	J.err = c->d_sync + 8; J.flags = c->d_sync + 16;
 	J.dbk = pd->any_deblock ? c->st[stage].d_dbk : NULL;
 	J.intra_list = intra; J.n_intra = pd->n_intra;
 	J.rows_mode = pd->n_intra * 2 > pd->width_mbs * pd->height_mbs;   /* intra pictures: wavefront of row warps */
-	J.trace = NULL; J.trace_base = 0; J.phase_slot = 0;
-	{ static int old = -1; if (old < 0) { const char *e = getenv("E264B_INTER_OLD"); old = e ? atoi(e) : 0; } J.resid_inter = old; }
-	{ static int tma = -1; if (tma < 0) { const char *e = getenv("E264B_TMA"); tma = e ? atoi(e) : 1; } J.tmaps = tma ? c->d_tmaps : NULL; }
-	{ static int force = -2; if (force == -2) { const char *e = getenv("E264B_ROWS"); force = e ? atoi(e) : -1; } if (force >= 0) J.rows_mode = force; }
+	J.trace = NULL; J.trace_base = 0;
 	if (c->epoch >= (1u << 20)) {   /* row progress counters encode epoch * 2048 + count: restart before it wraps */
 		cudaStreamSynchronize(c->stream);
 		cudaMemsetAsync(c->d_sync, 0, c->sync_words * sizeof(unsigned), c->stream);
 		c->epoch = 0;
 	}
 	J.epoch = ++c->epoch;
+	J.tickets = c->d_sync + (J.epoch & 1) * 4; J.tickets_next = c->d_sync + ((J.epoch + 1) & 1) * 4;    /* two sets, pictures alternate; every kernel clears the next picture's */
 	return J;
 }
 static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd, int with_deblock) {
-	int nmb = J.w_mbs * J.h_mbs;
-	int blocks = (nmb + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-	int cap = c->sm_count * 8;
-	if (blocks > cap) blocks = cap;
-	static int minb = -1, dbk_old = -1;
+	const int nmb = J.w_mbs * J.h_mbs;
+	const int cap = c->sm_count * 8;
+	static int minb = -1, dm = -1;
 	if (minb < 0) { const char *e = getenv("E264B_MINB"); minb = e ? atoi(e) : 4; }
-	if (dbk_old < 0) { const char *e = getenv("E264B_DBK_OLD"); dbk_old = e ? atoi(e) : 0; }
-	/* first on the stream: clears the ticket words (no memset per picture) and, for deblocked pictures, derives every
-	 * macroblock's boundary strengths and filter thresholds — record-only work without dependencies */
-	{
-		PicJob P = J;
-		if (!with_deblock || dbk_old) P.dbk = NULL;
-		int pb = P.dbk ? (nmb + PRE_WARPS - 1) / PRE_WARPS : 1;
-		if (pb > c->sm_count * 4) pb = c->sm_count * 4;
-		e264_prepass_kernel<<<pb, PRE_WARPS * 32, 0, c->stream>>>(P); c->launches++;
-	}
-	/* inter macroblocks transform their own coefficients; the residual kernel serves the intra kernel (and the round-1 inter kernel) */
-	if (pd->n_coefs > 0 && (J.resid_inter || pd->n_intra > 0)) { e264_residual_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J); c->launches++; }
+	if (dm < 0) { const char *e = getenv("E264B_DBK_MINB"); dm = e ? atoi(e) : 2; }
+	/* up to three launches per picture, nothing in between: inter macroblocks (inverse transform + prediction), intra
+	 * macroblocks (flags order them behind their neighbours), deblocking (its blocks derive the boundary strengths first) */
 	if (pd->n_intra < nmb) {
-		if (J.resid_inter) {
-			if (minb >= 8) e264_inter_kernel<8><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
-			else if (minb >= 6) e264_inter_kernel<6><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
-			else if (minb >= 5) e264_inter_kernel<5><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
-			else if (minb == 4) e264_inter_kernel<4><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
-			else e264_inter_kernel<3><<<blocks, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
-		} else {
-			/* blocks take chunks of INTER_CHUNK macroblocks */
-			int ib = (nmb + INTER_CHUNK - 1) / INTER_CHUNK;
-			if (ib > c->sm_count * 8) ib = c->sm_count * 8;
-			if (minb >= 6) e264_inter4_kernel<6><<<ib, INTER_WARPS * 32, 0, c->stream>>>(J);
-			else e264_inter4_kernel<4><<<ib, INTER_WARPS * 32, 0, c->stream>>>(J);
-		}
+		int ib = (nmb + INTER_CHUNK - 1) / INTER_CHUNK;
+		if (ib > cap) ib = cap;
+		if (minb >= 8) e264_inter4_kernel<8><<<ib, INTER_WARPS * 32, 0, c->stream>>>(J);
+		else if (minb >= 6) e264_inter4_kernel<6><<<ib, INTER_WARPS * 32, 0, c->stream>>>(J);
+		else e264_inter4_kernel<4><<<ib, INTER_WARPS * 32, 0, c->stream>>>(J);
 		c->launches++;
 	}
 	if (pd->n_intra > 0) {
-		static int intra_old = -1; if (intra_old < 0) { const char *e = getenv("E264B_INTRA_OLD"); intra_old = e ? atoi(e) : 0; }
-		if (J.rows_mode && !intra_old) {   /* intra pictures: bands of rows, hand-over through shared memory */
+		if (J.rows_mode) {   /* intra pictures: bands of rows, hand-over through shared memory */
 			e264_intra_rows_kernel<<<(J.h_mbs + IR_ROWS - 1) / IR_ROWS, IR_ROWS * 32, 0, c->stream>>>(J);
 		} else {
-			int ib = J.rows_mode ? (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK : (pd->n_intra + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+			int ib = (pd->n_intra + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
 			if (ib > cap) ib = cap;
 			e264_intra_kernel<<<ib, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
 		}
 		c->launches++;
 	}
-	if (with_deblock) {
-		if (dbk_old) {   /* round-1 kernel: one warp per macroblock row */
-			int rb = (J.h_mbs + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-			e264_deblock_rows_kernel<<<rb, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
-		} else {         /* one block per band of 16 rows and kind of plane */
-			int bands = (J.h_mbs + 2 * DBK_PAIRS - 1) / (2 * DBK_PAIRS);
-			e264_deblock_kernel<<<2 * bands, DBK_PAIRS * 32, 0, c->stream>>>(J);
-		}
+	if (with_deblock) {      /* one block per band of 16 rows and kind of plane */
+		const int bands = (J.h_mbs + 2 * DBK_PAIRS - 1) / (2 * DBK_PAIRS);
+		if (dm >= 5) e264_deblock_kernel<5><<<2 * bands, DBK_PAIRS * 32, 0, c->stream>>>(J);
+		else if (dm == 4) e264_deblock_kernel<4><<<2 * bands, DBK_PAIRS * 32, 0, c->stream>>>(J);
+		else e264_deblock_kernel<2><<<2 * bands, DBK_PAIRS * 32, 0, c->stream>>>(J);
 		c->launches++;
 	}
 	CK(cudaGetLastError());
@@ -441,7 +369,7 @@ extern "C" double e264b_kept_algorithmic_bytes(E264bDevice *c, double *recon_byt
  * (each owns a share of the streams): one thread alone tops out near 40-50 thousand launches per second and would
  * make the result a CPU number.  Every kernel stamps its first block's start and last block's end (%globaltimer)
  * into a trace array during the timed pass; stats->kernel_ms[k] is the sum over launches of that span per kernel
- * kind (0 residual, 1 inter, 2 intra, 3 deblock, 4 prepass) — spans of concurrent launches overlap, so their sum may
+ * kind (1 inter, 2 intra, 3 deblock; 0 and 4 unused since the inverse transform and the boundary-strength pass were folded into them) — spans of concurrent launches overlap, so their sum may
  * exceed the elapsed time.  E264B_TRACE=<file> also dumps the spans. */
 #include <thread>
 extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264bReplayStats *stats) {
@@ -474,7 +402,7 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264
 				for (int i = t; i < n; i += threads) {
 					KeptPic &kp = cs[i]->kept[k];
 					PicJob J = make_job(cs[i], &kp.pd, kp.pd.staging, kp.d_recs, kp.d_coefs, kp.d_slices, kp.d_intra);
-					J.trace = d_trace; J.trace_base = (int)((((size_t)r * npic + k) * n + i) * NK); J.phase_slot = (int)(n_trace * 2);
+					J.trace = d_trace; J.trace_base = (int)((((size_t)r * npic + k) * n + i) * NK);
 					if (launch_picture(cs[i], J, &kp.pd, kp.pd.any_deblock)) { rc[t] = -1; return; }
 				}
 	};
@@ -490,7 +418,6 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264
 	std::vector<unsigned long long> h(n_trace * 2 + 16);
 	CK(cudaMemcpy(h.data(), d_trace, n_trace * 16 + 128, cudaMemcpyDeviceToHost)); cudaFree(d_trace);
 	for (size_t j = 0; j < n_trace; j++) if (h[2 * j + 1] && h[2 * j] != ~0ull) { stats->kernel_ms[j % NK] += 1e-6 * (double)(h[2 * j + 1] - h[2 * j]); stats->kernel_launches[j % NK]++; }
-	{ unsigned long long tot = 0; for (int i = 0; i < 10; i++) tot += h[n_trace * 2 + i]; if (tot) { fprintf(stderr, "inter kernel phase clocks (%% of warp time):"); for (int i = 0; i < 10; i++) fprintf(stderr, " p%d=%.1f", i, 100.0 * h[n_trace * 2 + i] / tot); fprintf(stderr, "  total warp-cycles %llu\n", tot); } }
 	const char *trace_path = getenv("E264B_TRACE");
 	if (trace_path) {
 		FILE *f = fopen(trace_path, "w");

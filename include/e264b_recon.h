@@ -46,7 +46,7 @@ typedef struct E264bReplayStats {
 	float    ms_total;             /* device time from the common start to the last stream's end */
 	int      threads;              /* host threads that issued the launches */
 	uint64_t launches;
-	double   kernel_ms[5];         /* per kernel kind (0 residual, 1 inter, 2 intra, 3 deblock, 4 prepass): sum over launches of last-block-end minus first-block-start */
+	double   kernel_ms[5];         /* per kernel kind (1 inter, 2 intra, 3 deblock; 0 and 4 unused): sum over launches of last-block-end minus first-block-start */
 	uint64_t kernel_launches[5];
 } E264bReplayStats;
 int      e264b_replay(E264bDevice **devs, int n, int reps, int threads, E264bReplayStats *stats);

@@ -10,7 +10,7 @@ try:
     d = json.loads(open("gpurun_out/bench_${c}_$TAG.json").read().strip().splitlines()[-1])
     r = d["roofline"]
     print("$c value %.0f fps  e2e %.0f fps (dec_threads %s)  cpu_baseline %s  roofline %s frac %.4f concurrent %.4f" % (d["value"], d["e2e"]["value"], d["e2e"]["decoder_n_threads"], d.get("cpu_baseline", {}).get("value"), r["kernel"].split(" ")[0], r["frac"], r["concurrent"]["frac"]))
-    print("   per kernel avg us:", {k.split("_")[1]: (round(v["avg_us"]) if v["avg_us"] else None) for k, v in r["per_kernel"].items()})
+    print("   per kernel avg us:", {k.split("_")[1]: (round(v["avg_us"]) if v["avg_us"] else None) for k, v in r["per_kernel"].items()}, "launches", d["gpu_launches"])
 except Exception as e:
     print("$c: no line", e)
 PY
