@@ -1,9 +1,11 @@
 /* deblock_kernels.cuh — the in-loop filter (8.7).
  *
- *   digest phase          every block first derives, for the rows of its band, a 64-byte E264DbkMb per macroblock: 32
- *                         boundary strengths (one lane per edge segment), alpha / beta / tC0 of the 9 plane x edge-kind
- *                         combinations (reference: deblock_mb's bS derivation and table look-ups,
- *                         edge264_deblock.c:530-1123) — record-only work without dependencies, a warp per macroblock.
+ *   dbk_digest_mb         a 64-byte E264DbkMb per macroblock: 32 boundary strengths (one lane per edge segment), alpha /
+ *                         beta / tC0 of the 9 plane x edge-kind combinations (reference: deblock_mb's bS derivation
+ *                         and table look-ups, edge264_deblock.c:530-1123) — record-only work without dependencies, a
+ *                         warp per macroblock.  It runs inside the reconstruction kernels (the inter kernel derives
+ *                         the digests of its chunk, the intra-picture kernel those of its rows): hundreds of warps
+ *                         share it and no separate launch is needed.
  *   e264_deblock_kernel   the sample filter as a wavefront over macroblock ROW PAIRS.  The standard fixes the order
  *                         (raster macroblocks, vertical edges left to right, then horizontal edges top to bottom;
  *                         reference order edge264_deblock.c:537-891): macroblock (x, y) needs (x-1, y) complete,
@@ -137,7 +139,6 @@ struct __align__(16) DbkSmem {
 	uint32_t top[DBK_PAIRS][2][4][4];                /* [half][row][word]: luma rows -4..-1; chroma [plane * 2 + row -2..-1][2 words] */
 	E264DbkMb dg[DBK_PAIRS][2];
 	uint32_t ring[2 * DBK_PAIRS][DBK_RING][4][4];    /* per row of the band: bottom sample rows of its finished macroblocks [x % RING], layout of top */
-	uint4 drecs[DBK_PAIRS][3][12];                   /* digest phase: records of the current, left and top macroblock per warp */
 	int done[2 * DBK_PAIRS];                         /* macroblocks a row has put into its ring */
 	int taken[2 * DBK_PAIRS];                        /* macroblocks a row has taken from the ring of the row above */
 	int band;
@@ -401,12 +402,6 @@ __global__ void __launch_bounds__(DBK_PAIRS * 32, MINB) e264_deblock_kernel(PicJ
 		__syncthreads();
 		const int t = sm.band;
 		if (t >= 2 * bands) break;
-		{	/* the band's digests (record-only work, a warp per macroblock); the luma and the chroma block of a band both derive
-			 * them — identical values — rather than wait for each other */
-			const int first = (t >> 1) * 2 * DBK_PAIRS * J.w_mbs, last = min(first + 2 * DBK_PAIRS * J.w_mbs, J.w_mbs * J.h_mbs);
-			for (int mb = first + wid; mb < last; mb += DBK_PAIRS) dbk_digest_mb(J, sm.drecs[wid], &sm.dg[wid][0], mb, lane);
-		}
-		__syncthreads();
 		if (t & 1) dbk_walk<true>(J, &sm, t >> 1, wid, lane);
 		else dbk_walk<false>(J, &sm, t >> 1, wid, lane);
 	}

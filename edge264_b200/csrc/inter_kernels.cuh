@@ -14,6 +14,7 @@
  * 38 us here (profiles/README.md). */
 #pragma once
 #include "recon_kernels.cuh"
+#include "deblock_kernels.cuh"
 #include "mc_math.cuh"
 
 struct __align__(16) InterStage {
@@ -105,6 +106,8 @@ struct __align__(16) InterSmem {
 	uint16_t queue[6][INTER_CHUNK * 32];           /* item = macroblock << 5 | list << 4 | luma4x4BlkIdx */
 	int qn[6];
 	WarpSmem ws[INTER_WARPS];
+	uint4 drecs[INTER_WARPS][3][12];               /* deblocking digests: records of the current, left and top macroblock per warp */
+	E264DbkMb ddg[INTER_WARPS];
 	int16_t coef[INTER_WARPS][2][RES_COEF_MAX];
 	unsigned long long bars[INTER_WARPS][2];
 };
@@ -191,6 +194,8 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, MINB) e264_inter4_kernel(Pic
 				}
 			}
 		}
+		/* the chunk's deblocking digests (every macroblock, intra ones too): record-only work, a warp per macroblock */
+		if (J.dbk != nullptr) for (int m = w; m < cnt; m += INTER_WARPS) dbk_digest_mb(J, sm.drecs[w], &sm.ddg[w], mb0 + m, lane);
 		__syncthreads();
 		/* ---- 2. one class at a time, 32 items per warp pass ---- */
 		{

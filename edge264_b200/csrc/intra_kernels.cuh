@@ -14,6 +14,7 @@
  * by the inter kernel before: their row warp only forwards their border samples. */
 #pragma once
 #include "recon_kernels.cuh"
+#include "deblock_kernels.cuh"
 
 #define IR_ROWS 8
 #define IR_RING 16
@@ -50,6 +51,8 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 	const E264MbRec *rowrecs = J.recs + (size_t)mby * W;
 	int avail = 0;                                            /* macroblocks of the row above the band known to be stored */
 
+	/* a picture without inter macroblocks has no inter kernel to derive the deblocking digests: every row does its own first */
+	if (J.dbk != nullptr && J.n_intra == nmb) for (int x = 0; x < W; x++) dbk_digest_mb(J, sm.recs[w], (E264DbkMb *)sm.coef[w][0], mby * W + x, lane);   /* buffers the walk has not started to use */
 	/* records two ahead, coefficient runs one ahead */
 	if (lane < 12) sm.recs[w][0][lane] = __ldg((const uint4 *)rowrecs + lane);
 	if (W > 1 && lane >= 12 && lane < 24) sm.recs[w][1][lane - 12] = __ldg((const uint4 *)(rowrecs + 1) + lane - 12);

@@ -224,7 +224,7 @@ static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, int stage, const E
 	J.dbk = pd->any_deblock ? c->st[stage].d_dbk : NULL;
 	J.intra_list = intra; J.n_intra = pd->n_intra;
 	J.rows_mode = pd->n_intra * 2 > pd->width_mbs * pd->height_mbs;   /* intra pictures: wavefront of row warps */
-	J.trace = NULL; J.trace_base = 0;
+	J.trace = NULL; J.trace_base = 0; J.trace_rep = NULL; J.trace_rep_stride = 0;
 	if (c->epoch >= (1u << 20)) {   /* row progress counters encode epoch * 2048 + count: restart before it wraps */
 		cudaStreamSynchronize(c->stream);
 		cudaMemsetAsync(c->d_sync, 0, c->sync_words * sizeof(unsigned), c->stream);
@@ -372,6 +372,7 @@ extern "C" double e264b_kept_algorithmic_bytes(E264bDevice *c, double *recon_byt
  * kind (1 inter, 2 intra, 3 deblock; 0 and 4 unused since the inverse transform and the boundary-strength pass were folded into them) — spans of concurrent launches overlap, so their sum may
  * exceed the elapsed time.  E264B_TRACE=<file> also dumps the spans. */
 #include <thread>
+__global__ void e264_replay_rep_kernel(unsigned *rep) { if (threadIdx.x == 0) *rep += 1; }
 extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264bReplayStats *stats) {
 	if (n <= 0 || !stats) return -1;
 	memset(stats, 0, sizeof(*stats));
@@ -392,9 +393,51 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264
 	}
 	if (threads < 1) threads = 1;
 	if (threads > n) threads = n;
+	/* Default: every stream's pictures of one repetition are captured into ONE CUDA graph (its kernels stay the same
+	 * launches, in the same order, on the same stream) and a repetition is one graph launch per stream — the issue rate
+	 * of individual launches (tens of thousands per second for the whole process, less with several threads contending
+	 * for the driver) would otherwise bound the result.  The synchronisation words restart at every repetition
+	 * (two memset nodes) because the captured epochs repeat.  E264B_REPLAY_GRAPH=0 issues plain launches instead. */
+	const char *ge = getenv("E264B_REPLAY_GRAPH");
+	const bool use_graph = !(ge && atoi(ge) == 0);
+	std::vector<cudaGraphExec_t> execs(n, nullptr);
+	unsigned *d_rep = NULL;
+	uint64_t per_rep_launches = 0;
+	if (use_graph) {
+		CK(cudaMalloc(&d_rep, n * sizeof(unsigned))); CK(cudaMemset(d_rep, 0, n * sizeof(unsigned)));
+		for (int i = 0; i < n; i++) {
+			E264bDevice *c = cs[i];
+			c->epoch = 0;
+			const uint64_t lbefore = c->launches;
+			cudaGraph_t g = nullptr;
+			CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+			CK(cudaMemsetAsync(c->d_sync, 0, 8 * sizeof(unsigned), c->stream));
+			CK(cudaMemsetAsync(c->d_sync + 16, 0, (c->sync_words - 16) * sizeof(unsigned), c->stream));
+			int bad = 0;
+			for (size_t k = 0; k < npic && !bad; k++) {
+				KeptPic &kp = c->kept[k];
+				PicJob J = make_job(c, &kp.pd, kp.pd.staging, kp.d_recs, kp.d_coefs, kp.d_slices, kp.d_intra);
+				J.trace = d_trace; J.trace_base = (int)((k * n + i) * NK); J.trace_rep = d_rep + i; J.trace_rep_stride = (int)(npic * n * NK);
+				bad = launch_picture(c, J, &kp.pd, kp.pd.any_deblock);
+			}
+			e264_replay_rep_kernel<<<1, 32, 0, c->stream>>>(d_rep + i);
+			cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+			if (bad || ce != cudaSuccess) { fprintf(stderr, "edge264_b200: replay graph capture failed: %s\n", cudaGetErrorString(ce)); return -1; }
+			CK(cudaGraphInstantiate(&execs[i], g, 0));
+			CK(cudaGraphDestroy(g));
+			CK(cudaGraphUpload(execs[i], c->stream));
+			per_rep_launches += c->launches - lbefore;
+			c->launches += (c->launches - lbefore) * (uint64_t)(reps - 1);
+		}
+		for (int i = 0; i < n; i++) CK(cudaStreamSynchronize(cs[i]->stream));
+	}
 	CK(cudaEventRecord(start, cs[0]->stream));
 	for (int i = 1; i < n; i++) CK(cudaStreamWaitEvent(cs[i]->stream, start, 0));
 	std::vector<int> rc(threads, 0);
+	if (use_graph) {
+		for (int r = 0; r < reps; r++) for (int i = 0; i < n; i++) CK(cudaGraphLaunch(execs[i], cs[i]->stream));
+		threads = 0;
+	}
 	auto issue = [&](int t) {
 		cudaSetDevice(cs[0]->dev);
 		for (int r = 0; r < reps; r++)
@@ -406,7 +449,8 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264
 					if (launch_picture(cs[i], J, &kp.pd, kp.pd.any_deblock)) { rc[t] = -1; return; }
 				}
 	};
-	if (threads == 1) issue(0);
+	if (threads == 0) {}
+	else if (threads == 1) issue(0);
 	else { std::vector<std::thread> th; for (int t = 0; t < threads; t++) th.emplace_back(issue, t); for (auto &x : th) x.join(); }
 	for (int t = 0; t < threads; t++) if (rc[t]) return -1;
 	for (int i = 1; i < n; i++) { CK(cudaEventRecord(ends[i], cs[i]->stream)); CK(cudaStreamWaitEvent(cs[0]->stream, ends[i], 0)); }
@@ -414,7 +458,10 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264
 	CK(cudaEventSynchronize(stop));
 	CK(cudaEventElapsedTime(&stats->ms_total, start, stop));
 	{ uint64_t l1 = 0; for (int i = 0; i < n; i++) l1 += cs[i]->launches; stats->launches = l1 - l0; }
-	stats->threads = threads;
+	stats->threads = threads;      /* 0: graph replay */
+	for (int i = 0; i < n; i++) if (execs[i]) cudaGraphExecDestroy(execs[i]);
+	if (d_rep) cudaFree(d_rep);
+	if (use_graph) for (int i = 0; i < n; i++) { cs[i]->epoch = (unsigned)npic; }     /* the words hold the last repetition's epochs */
 	std::vector<unsigned long long> h(n_trace * 2 + 16);
 	CK(cudaMemcpy(h.data(), d_trace, n_trace * 16 + 128, cudaMemcpyDeviceToHost)); cudaFree(d_trace);
 	for (size_t j = 0; j < n_trace; j++) if (h[2 * j + 1] && h[2 * j] != ~0ull) { stats->kernel_ms[j % NK] += 1e-6 * (double)(h[2 * j + 1] - h[2 * j]); stats->kernel_launches[j % NK]++; }

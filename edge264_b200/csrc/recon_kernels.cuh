@@ -28,6 +28,8 @@ struct PicJob {
 	int n_intra;
 	unsigned long long *trace;   /* measurement only (e264b_replay): [trace_base + kind] = {first block start, last block end} in globaltimer ns; kinds: 1 inter, 2 intra, 3 deblock */
 	int trace_base;
+	const unsigned *trace_rep;   /* graph replay: device counter of the repetition under way; its slots start trace_rep_stride further on */
+	int trace_rep_stride;
 };
 
 #define WARPS_PER_BLOCK 4
@@ -69,7 +71,7 @@ struct TraceScope {
 	unsigned long long *t;
 	__device__ __forceinline__ static unsigned long long now() { unsigned long long v; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)); return v; }
 	/* one thread per block: two atomics per block keep the timed replay undisturbed (a block's first warp starts it, its exit is within one macroblock of the block's end) */
-	__device__ __forceinline__ TraceScope(const PicJob &J, int kind) { t = J.trace ? J.trace + 2 * (J.trace_base + kind) : nullptr; if (t && threadIdx.x == 0) atomicMin(t, now()); }
+	__device__ __forceinline__ TraceScope(const PicJob &J, int kind) { t = J.trace ? J.trace + 2 * ((size_t)J.trace_base + kind + (J.trace_rep ? (size_t)*J.trace_rep * J.trace_rep_stride : 0)) : nullptr; if (t && threadIdx.x == 0) atomicMin(t, now()); }
 	__device__ __forceinline__ ~TraceScope() { if (t && threadIdx.x == 0) atomicMax(t + 1, now()); }
 };
 
@@ -285,152 +287,112 @@ __device__ __noinline__ void residual_stage(WarpSmem *ws, const E264MbRec *r, co
 #define YT(x, y) ws->ytile[((y) + 1) * YT_STRIDE + 16 + (x)]     /* x in -1..23, y in -1..15 */
 #define CT(pl, x, y) ws->ctile[pl][((y) + 1) * CT_STRIDE + 8 + (x)]
 
-/* predicted sample (x,y) of a 4x4 block whose top-left tile coordinate is (X0,Y0) */
-__device__ __noinline__ int pred4x4(const WarpSmem *ws, int X0, int Y0, int imode, int x, int y) {
-	int mode = imode & 15, un = imode >> 4;
-	bool hasA = !(un & 1), hasB = !(un & 2), hasC = !(un & 4);
-#define T(i) ((i) < 0 ? (int)YT(X0 - 1, Y0 - 1) : (int)YT(X0 + (((i) > 3 && !hasC) ? 3 : (i)), Y0 - 1))
-#define L(i) ((i) < 0 ? (int)YT(X0 - 1, Y0 - 1) : (int)YT(X0 - 1, Y0 + (i)))
+/* ---- Intra 4x4 / 8x8 prediction: one edge vector in registers, a table of taps, three shuffles ----
+ * Every directional predictor of 8.3.1.2 / 8.3.2.2 is a copy, a 2-tap or a 3-tap average of ADJACENT entries of one
+ * vector  E = [L(N-1) L(N-1) .. L0  TL  T0 .. T(2N-1)  T(2N-1)]  (the duplicated ends absorb the "3*last" cases), so a
+ * lane holds one entry of E, a 64-bit constant per sample holds (index, kind) for the 9 modes, and a block costs one
+ * shared-memory load, three shuffles and a handful of integer instructions instead of a per-sample walk over the tile.
+ * (reference formulation: the shuffle-table predictors of edge264_intra.c:13-420; same arithmetic, other machinery). */
+struct IntraTap { int idx, kind; };   /* kind 0: E[idx]; 1: (E[idx] + E[idx+1] + 1) >> 1; 2: (E[idx] + 2 E[idx+1] + E[idx+2] + 2) >> 2 */
+constexpr IntraTap intra_tap(int N, int mode, int x, int y) {
+	const int bT = N + 2, bL = N;        /* T(i) = E[bT + i], L(i) = E[bL - i], TL = E[N + 1] */
 	switch (mode) {
-	case 0: return T(x);
-	case 1: return L(y);
-	case 2:
-		if (hasA && hasB) return (T(0) + T(1) + T(2) + T(3) + L(0) + L(1) + L(2) + L(3) + 4) >> 3;
-		if (hasA) return (L(0) + L(1) + L(2) + L(3) + 2) >> 2;
-		if (hasB) return (T(0) + T(1) + T(2) + T(3) + 2) >> 2;
-		return 128;
-	case 3: return (x == 3 && y == 3) ? (T(6) + 3 * T(7) + 2) >> 2 : (T(x + y) + 2 * T(x + y + 1) + T(x + y + 2) + 2) >> 2;
-	case 4:
-		if (x > y) return (T(x - y - 2) + 2 * T(x - y - 1) + T(x - y) + 2) >> 2;
-		if (x < y) return (L(y - x - 2) + 2 * L(y - x - 1) + L(y - x) + 2) >> 2;
-		return (T(0) + 2 * T(-1) + L(0) + 2) >> 2;
-	case 5: {
-		int z = 2 * x - y;
-		if (z >= 0 && !(z & 1)) return (T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 1) >> 1;
-		if (z > 0) return (T(x - (y >> 1) - 2) + 2 * T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 2) >> 2;
-		if (z == -1) return (L(0) + 2 * L(-1) + T(0) + 2) >> 2;
-		return (L(y - 1) + 2 * L(y - 2) + L(y - 3) + 2) >> 2; }
-	case 6: {
-		int z = 2 * y - x;
-		if (z >= 0 && !(z & 1)) return (L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 1) >> 1;
-		if (z > 0) return (L(y - (x >> 1) - 2) + 2 * L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 2) >> 2;
-		if (z == -1) return (L(0) + 2 * L(-1) + T(0) + 2) >> 2;
-		return (T(x - 1) + 2 * T(x - 2) + T(x - 3) + 2) >> 2; }
-	case 7:
-		if (!(y & 1)) return (T(x + (y >> 1)) + T(x + (y >> 1) + 1) + 1) >> 1;
-		return (T(x + (y >> 1)) + 2 * T(x + (y >> 1) + 1) + T(x + (y >> 1) + 2) + 2) >> 2;
-	default: {
-		int z = x + 2 * y;
-		if (z > 5) return L(3);
-		if (z == 5) return (L(2) + 3 * L(3) + 2) >> 2;
-		if (!(z & 1)) return (L(y + (x >> 1)) + L(y + (x >> 1) + 1) + 1) >> 1;
-		return (L(y + (x >> 1)) + 2 * L(y + (x >> 1) + 1) + L(y + (x >> 1) + 2) + 2) >> 2; }
+	case 0: return {bT + x, 0};
+	case 1: return {bL - y, 0};
+	case 3: return {bT + x + y, 2};
+	case 4: return {x > y ? bT + x - y - 2 : x < y ? bL - (y - x) : bL, 2};
+	case 5: { const int z = 2 * x - y;
+		if (z >= 0 && !(z & 1)) return {bT + x - (y >> 1) - 1, 1};
+		if (z > 0) return {bT + x - (y >> 1) - 2, 2};
+		if (z == -1) return {bL, 2};
+		return {bL - (y - 2 * x - 1), 2}; }
+	case 6: { const int z = 2 * y - x;
+		if (z >= 0 && !(z & 1)) return {bL - (y - (x >> 1)), 1};
+		if (z > 0) return {bL - (y - (x >> 1)), 2};
+		if (z == -1) return {bL, 2};
+		return {bT + x - 2 * y - 3, 2}; }
+	case 7: return {bT + x + (y >> 1), (y & 1) ? 2 : 1};
+	case 8: { const int z = x + 2 * y, k = y + (x >> 1);
+		if (z > 2 * N - 3) return {1, 0};
+		if (z == 2 * N - 3) return {0, 2};
+		if (!(z & 1)) return {bL - (k + 1), 1};
+		return {bL - (k + 2), 2}; }
+	default: return {0, 0};
 	}
-#undef T
-#undef L
+}
+struct I4Taps { uint64_t v[16];
+	constexpr I4Taps() : v{} { for (int p = 0; p < 16; p++) { uint64_t w = 0; for (int m = 0; m < 9; m++) { const IntraTap t = intra_tap(4, m, p & 3, p >> 2); w |= (uint64_t)(t.idx | t.kind << 4) << (6 * m); } v[p] = w; } } };
+struct I8Taps { uint64_t v[64];
+	constexpr I8Taps() : v{} { for (int p = 0; p < 64; p++) { uint64_t w = 0; for (int m = 0; m < 9; m++) { const IntraTap t = intra_tap(8, m, p & 7, p >> 3); w |= (uint64_t)(t.idx | t.kind << 5) << (7 * m); } v[p] = w; } } };
+__device__ const I4Taps e264_i4taps = I4Taps();
+__device__ const I8Taps e264_i8taps = I8Taps();
+
+__device__ __forceinline__ int intra_tap_apply(int E, int idx, int kind) {
+	const int a = __shfl_sync(0xffffffffu, E, idx), b = __shfl_sync(0xffffffffu, E, idx + 1), c = __shfl_sync(0xffffffffu, E, idx + 2);
+	return kind == 2 ? (a + 2 * b + c + 2) >> 2 : kind == 1 ? (a + b + 1) >> 1 : a;
 }
 
-/* Intra 8x8: filtered reference samples in ws->u.edge[0][1+x] (top, x=-1..15) and edge[1][1+y] (left, y=-1..7) */
-__device__ __noinline__ void intra8x8_edges(WarpSmem *ws, int X0, int Y0, int un, int lane) {
-	bool hasA = !(un & 1), hasB = !(un & 2), hasC = !(un & 4), hasD = !(un & 8);
-#define RT(i) ((i) < 0 ? (int)YT(X0 - 1, Y0 - 1) : (int)YT(X0 + (((i) > 7 && !hasC) ? 7 : (i)), Y0 - 1))
-#define RL(i) ((i) < 0 ? (int)YT(X0 - 1, Y0 - 1) : (int)YT(X0 - 1, Y0 + (i)))
-	if (lane < 16) {   /* top x = lane */
-		int x = lane, v = 128;
-		if (hasB) {
-			if (x == 0) v = hasD ? (RT(-1) + 2 * RT(0) + RT(1) + 2) >> 2 : (3 * RT(0) + RT(1) + 2) >> 2;
-			else if (x == 15) v = (RT(14) + 3 * RT(15) + 2) >> 2;
-			else v = (RT(x - 1) + 2 * RT(x) + RT(x + 1) + 2) >> 2;
-		}
-		ws->u.edge[0][1 + x] = v;
-	} else if (lane < 24) {   /* left y = lane - 16 */
-		int y = lane - 16, v = 128;
-		if (hasA) {
-			if (y == 0) v = hasD ? (RL(-1) + 2 * RL(0) + RL(1) + 2) >> 2 : (3 * RL(0) + RL(1) + 2) >> 2;
-			else if (y == 7) v = (RL(6) + 3 * RL(7) + 2) >> 2;
-			else v = (RL(y - 1) + 2 * RL(y) + RL(y + 1) + 2) >> 2;
-		}
-		ws->u.edge[1][1 + y] = v;
-	} else if (lane == 24) {
-		int v = hasD ? RT(-1) : 128;
-		if (hasD) {
-			if (hasA && hasB) v = (RT(0) + 2 * RT(-1) + RL(0) + 2) >> 2;
-			else if (hasB) v = (3 * RT(-1) + RT(0) + 2) >> 2;
-			else if (hasA) v = (3 * RT(-1) + RL(0) + 2) >> 2;
-		}
-		ws->u.edge[0][0] = v; ws->u.edge[1][0] = v;
+/* one 4x4 block at tile coordinate (X0, Y0): lanes 0..15 return their predicted sample (x = lane & 3, y = lane >> 2) */
+__device__ __forceinline__ int pred4x4_warp(const WarpSmem *ws, int X0, int Y0, int imode, uint64_t taps, int lane) {
+	const int mode = imode & 15, un = imode >> 4;
+	const bool hasA = !(un & 1), hasB = !(un & 2);
+	const int e = min(lane, 14);
+	int i = min(e - 6, 7); if ((un & 4) && i > 3) i = 3;          /* top-right unavailable: T4..T7 = T3 */
+	const int E = YT(X0 + (e <= 5 ? -1 : i), Y0 + (e <= 4 ? min(4 - e, 3) : -1));
+	if (mode == 2) {
+		int s = (lane < 15 && ((e >= 6 && e <= 9 && hasB) || (e >= 1 && e <= 4 && hasA))) ? E : 0;
+		s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4); s += __shfl_xor_sync(0xffffffffu, s, 8);
+		return (hasA && hasB) ? (s + 4) >> 3 : (hasA || hasB) ? (s + 2) >> 2 : 128;
 	}
-#undef RT
-#undef RL
-	__syncwarp();
+	const int ent = (int)(taps >> (6 * mode)) & 63;
+	return intra_tap_apply(E, ent & 15, ent >> 4);
 }
-__device__ __noinline__ int pred8x8(const WarpSmem *ws, int imode, int x, int y) {
-	int mode = imode & 15, un = imode >> 4;
-	bool hasA = !(un & 1), hasB = !(un & 2);
-#define T(i) ws->u.edge[0][1 + (i)]
-#define L(i) ws->u.edge[1][1 + (i)]
-	switch (mode) {
-	case 0: return T(x);
-	case 1: return L(y);
-	case 2: {
-		int st = 0, sl = 0;
-#pragma unroll
-		for (int k = 0; k < 8; k++) { st += T(k); sl += L(k); }
-		return (hasA && hasB) ? (st + sl + 8) >> 4 : hasA ? (sl + 4) >> 3 : hasB ? (st + 4) >> 3 : 128; }
-	case 3: return (x == 7 && y == 7) ? (T(14) + 3 * T(15) + 2) >> 2 : (T(x + y) + 2 * T(x + y + 1) + T(x + y + 2) + 2) >> 2;
-	case 4:
-		if (x > y) return (T(x - y - 2) + 2 * T(x - y - 1) + T(x - y) + 2) >> 2;
-		if (x < y) return (L(y - x - 2) + 2 * L(y - x - 1) + L(y - x) + 2) >> 2;
-		return (T(0) + 2 * T(-1) + L(0) + 2) >> 2;
-	case 5: {
-		int z = 2 * x - y;
-		if (z >= 0 && !(z & 1)) return (T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 1) >> 1;
-		if (z > 0) return (T(x - (y >> 1) - 2) + 2 * T(x - (y >> 1) - 1) + T(x - (y >> 1)) + 2) >> 2;
-		if (z == -1) return (L(0) + 2 * L(-1) + T(0) + 2) >> 2;
-		return (L(y - 2 * x - 1) + 2 * L(y - 2 * x - 2) + L(y - 2 * x - 3) + 2) >> 2; }
-	case 6: {
-		int z = 2 * y - x;
-		if (z >= 0 && !(z & 1)) return (L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 1) >> 1;
-		if (z > 0) return (L(y - (x >> 1) - 2) + 2 * L(y - (x >> 1) - 1) + L(y - (x >> 1)) + 2) >> 2;
-		if (z == -1) return (L(0) + 2 * L(-1) + T(0) + 2) >> 2;
-		return (T(x - 2 * y - 1) + 2 * T(x - 2 * y - 2) + T(x - 2 * y - 3) + 2) >> 2; }
-	case 7:
-		if (!(y & 1)) return (T(x + (y >> 1)) + T(x + (y >> 1) + 1) + 1) >> 1;
-		return (T(x + (y >> 1)) + 2 * T(x + (y >> 1) + 1) + T(x + (y >> 1) + 2) + 2) >> 2;
-	default: {
-		int z = x + 2 * y;
-		if (z > 13) return L(7);
-		if (z == 13) return (L(6) + 3 * L(7) + 2) >> 2;
-		if (!(z & 1)) return (L(y + (x >> 1)) + L(y + (x >> 1) + 1) + 1) >> 1;
-		return (L(y + (x >> 1)) + 2 * L(y + (x >> 1) + 1) + L(y + (x >> 1) + 2) + 2) >> 2; }
+
+/* one 8x8 block: reference samples filtered in registers (8.3.2.2.1), then two samples per lane (rows y and y + 4) */
+__device__ __forceinline__ void pred8x8_warp(const WarpSmem *ws, int X0, int Y0, int imode, uint64_t taps0, uint64_t taps1, int lane, int &v0, int &v1) {
+	const int mode = imode & 15, un = imode >> 4;
+	const bool hasA = !(un & 1), hasB = !(un & 2), hasD = !(un & 8);
+	const int e = min(lane, 26);
+	int i = min(e - 10, 15); if ((un & 4) && i > 7) i = 7;
+	const int raw = YT(X0 + (e <= 9 ? -1 : i), Y0 + (e <= 8 ? min(8 - e, 7) : -1));
+	int lo = __shfl_up_sync(0xffffffffu, raw, 1), hi = __shfl_down_sync(0xffffffffu, raw, 1);
+	if ((e == 9 && !hasA) || (e == 10 && !hasD)) lo = raw;
+	if ((e == 9 && !hasB) || (e == 8 && !hasD)) hi = raw;
+	int E = (lo + 2 * raw + hi + 2) >> 2;
+	if ((e >= 10 && !hasB) || (e <= 8 && !hasA) || (e == 9 && !hasD)) E = 128;
+	E = __shfl_sync(0xffffffffu, E, min(max(e, 1), 25));     /* the duplicated ends */
+	if (mode == 2) {
+		int s = ((e >= 10 && e <= 17 && hasB) || (e >= 1 && e <= 8 && hasA)) ? E : 0;
+		s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+		s += __shfl_xor_sync(0xffffffffu, s, 8); s += __shfl_xor_sync(0xffffffffu, s, 16);
+		v0 = v1 = (hasA && hasB) ? (s + 8) >> 4 : (hasA || hasB) ? (s + 4) >> 3 : 128;
+		return;
 	}
-#undef T
-#undef L
+	const int e0 = (int)(taps0 >> (7 * mode)) & 127, e1 = (int)(taps1 >> (7 * mode)) & 127;
+	v0 = intra_tap_apply(E, e0 & 31, e0 >> 5);
+	v1 = intra_tap_apply(E, e1 & 31, e1 >> 5);
 }
 
 __device__ __noinline__ void intra_luma(WarpSmem *ws, const E264MbRec *r, int lane) {
 	if (r->kind == MBK_I4x4) {
+		const uint64_t taps = __ldg(&e264_i4taps.v[lane & 15]);
 #pragma unroll 1
 		for (int b = 0; b < 16; b++) {
-			int X0 = blk_x(b) * 4, Y0 = blk_y(b) * 4;
-			if (lane < 16) {
-				int x = lane & 3, y = lane >> 2;
-				int v = pred4x4(ws, X0, Y0, r->modes[b], x, y);
-				v = clip255((short)(v + ws->res[(Y0 + y) * 16 + X0 + x]));
-				YT(X0 + x, Y0 + y) = (uint8_t)v;   /* reads above touch only samples outside the block */
-			}
+			const int X0 = blk_x(b) * 4, Y0 = blk_y(b) * 4, x = lane & 3, y = (lane >> 2) & 3;
+			int v = pred4x4_warp(ws, X0, Y0, r->modes[b], taps, lane);
+			v = clip255((short)(v + ws->res[(Y0 + y) * 16 + X0 + x]));
+			if (lane < 16) YT(X0 + x, Y0 + y) = (uint8_t)v;   /* the reads above touch only samples outside the block */
 			__syncwarp();
 		}
 	} else if (r->kind == MBK_I8x8) {
+		const uint64_t taps0 = __ldg(&e264_i8taps.v[lane]), taps1 = __ldg(&e264_i8taps.v[lane + 32]);
 #pragma unroll 1
 		for (int i = 0; i < 4; i++) {
-			int X0 = (i & 1) * 8, Y0 = (i >> 1) * 8, im = r->modes[i];
-			intra8x8_edges(ws, X0, Y0, im >> 4, lane);
-			int x = lane & 7, y = lane >> 3;
-			int v0 = pred8x8(ws, im, x, y), v1 = pred8x8(ws, im, x, y + 4);
+			const int X0 = (i & 1) * 8, Y0 = (i >> 1) * 8, x = lane & 7, y = lane >> 3;
+			int v0, v1;
+			pred8x8_warp(ws, X0, Y0, r->modes[i], taps0, taps1, lane, v0, v1);
 			v0 = clip255((short)(v0 + ws->res[(Y0 + y) * 16 + X0 + x]));
 			v1 = clip255((short)(v1 + ws->res[(Y0 + y + 4) * 16 + X0 + x]));
-			__syncwarp();
 			YT(X0 + x, Y0 + y) = (uint8_t)v0; YT(X0 + x, Y0 + y + 4) = (uint8_t)v1;
 			__syncwarp();
 		}

@@ -17,4 +17,4 @@ core.e264b_replay(devs, S, 1, T, ctypes.byref(st))
 core.e264b_replay(devs, S, steps, T, ctypes.byref(st))
 n = sum(frames) * steps
 per = " ".join(f"{n}={1000 * st.kernel_ms[k] / max(1, st.kernel_launches[k]):.0f}us" for k, n in ((1, "inter"), (2, "intra"), (3, "deblock")))
-print(f"{os.environ.get('TAG','')}: total {st.ms_total/steps:.1f} ms/step with {st.threads} launch threads -> {n/st.ms_total*1000:.0f} fps; mean span per launch: {per} (e2e decode of warm-up: {sum(frames)/secs:.0f} fps)")
+print(f"{os.environ.get('TAG','')}: total {st.ms_total/steps:.1f} ms/step ({"graph" if st.threads == 0 else str(st.threads) + " launch threads"}) -> {n/st.ms_total*1000:.0f} fps; mean span per launch: {per} (e2e decode of warm-up: {sum(frames)/secs:.0f} fps)")
