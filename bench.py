@@ -91,7 +91,7 @@ class BenchLib:
 
 class ReplayStats(ctypes.Structure):
     _fields_ = [("ms_total", ctypes.c_float), ("threads", ctypes.c_int), ("launches", ctypes.c_uint64),
-                ("kernel_ms", ctypes.c_double * 5), ("kernel_launches", ctypes.c_uint64 * 5)]
+                ("kernel_ms", ctypes.c_double * 5), ("kernel_launches", ctypes.c_uint64 * 5), ("inflight", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 KERNELS = ["(unused)", "e264_inter4_kernel", "e264_intra_kernel / e264_intra_rows_kernel", "e264_deblock_kernel", "(unused)"]
@@ -307,7 +307,7 @@ def main():
     line = {"metric": cfg["metric"], "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "macroblocks_per_s": fps * mbpf, "config": config_dict(cfg, args, world),
-            "clocks": sampler.summary(), "gpu_launches": int(st.launches), "replay": "cuda-graph per stream and step" if st.threads == 0 else f"{int(st.threads)} host launch threads",
+            "clocks": sampler.summary(), "gpu_launches": int(st.launches), "replay": f"cuda-graph per stream and step, {int(st.inflight)} streams in flight" if st.threads == 0 else f"{int(st.threads)} host launch threads",
             "e2e": {"value": e2e_fps, "unit": "frames/s", "macroblocks_per_s": e2e_fps * mbpf, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                     "app_threads": S, "decoder_n_threads": dec_threads, "usable_cpus": usable_cpus(), "cpus_per_rank": cpus, "bytes_per_unit": len(bufs[0]),
                     "saturated": "host CPUs (bitstream parsing)" if S * max(1, dec_threads) >= cpus else "streams in flight",

@@ -5,7 +5,8 @@
  * (reference: decode order edge264_slice.c:1651-1849 with the predictors of edge264_intra.c:291-765): rows can run in
  * parallel two macroblocks apart.  Round 1 ran one warp per row with a global flag, a gpu-scope fence (which also
  * invalidates L1) and reloads of the record, the residual and the row above from L2 inside every step: 8.7 us per
- * macroblock step, 2.2 ms per 1080p I picture.  Here a block owns IR_ROWS consecutive rows (one warp each); the bottom
+ * macroblock step, 2.2 ms per 1080p I picture.  Here a block owns IR_ROWS consecutive rows (two warps each: one
+ * inverse-transforms up to two macroblocks ahead, one predicts); the bottom
  * sample row of every finished macroblock goes to the row below through a shared-memory ring with done/taken counters
  * (block-scope fences); records arrive two macroblocks ahead, coefficient runs one ahead (cp.async.bulk on an mbarrier) and
  * are inverse-transformed BEFORE the row waits for its neighbours, so a step is the prediction itself plus a
@@ -20,21 +21,77 @@
 #define IR_RING 16
 #define IR_CHUNK 8
 struct __align__(16) IntraRowsSmem {
-	WarpSmem ws[IR_ROWS];
-	uint4 recs[IR_ROWS][3][12];                 /* records of macroblocks x, x+1, x+2 of every row */
+	WarpSmem ws[IR_ROWS][2];                    /* macroblocks x and x+1 of every row: residual from the row's transform warp, tile of its prediction warp */
+	uint4 recs[IR_ROWS][4][12];                 /* records of macroblocks x-1 .. x+2 of every row */
 	uint32_t ring[IR_ROWS][IR_RING][8];         /* bottom sample row of a finished macroblock: luma (4 words), Cb (2), Cr (2) */
 	int16_t coef[IR_ROWS][2][RES_COEF_MAX];     /* coefficient runs of macroblocks x, x+1 of every row (cp.async.bulk) */
 	unsigned long long bars[IR_ROWS][2];
+	uint4 drecs[IR_ROWS][3][12];                /* deblocking digests of intra-only pictures: current, left and top record */
+	E264DbkMb ddg[IR_ROWS];
 	int done[IR_ROWS];                          /* macroblocks a row has put into its ring */
 	int taken[IR_ROWS];                         /* the macroblock a row is working on: ring entries before it (minus one) are free */
+	int ready[IR_ROWS];                         /* macroblocks whose residual (and record) the transform warp has delivered */
+	int used[IR_ROWS];                          /* macroblocks the prediction warp is through with */
 	int band;
 };
 
-__device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &sm, int band, int w, int lane, unsigned (&parity)[2]) {
+/* The row's TRANSFORM warp: records two ahead, coefficient runs one ahead (cp.async.bulk), dequantisation and inverse
+ * transforms into the residual of slot x & 1, at most two macroblocks ahead of the prediction warp.  In a picture without
+ * inter macroblocks it also derives the row's deblocking digests (no inter kernel runs that would). */
+__device__ __forceinline__ void intra_row_transform(const PicJob &J, IntraRowsSmem &sm, int band, int w, int lane, unsigned (&parity)[2]) {
+	const int W = J.w_mbs, H = J.h_mbs, nmb = W * H;
+	const int mby = band * IR_ROWS + w;
+	if (mby >= H) return;
+	const E264MbRec *rowrecs = J.recs + (size_t)mby * W;
+	const volatile unsigned *errp = J.err;
+	volatile int *used = sm.used + w, *ready = sm.ready + w;
+	const bool digests = J.dbk != nullptr && J.n_intra == nmb;
+	if (lane < 12) sm.recs[w][0][lane] = __ldg((const uint4 *)rowrecs + lane);
+	if (W > 1 && lane >= 12 && lane < 24) sm.recs[w][1][lane - 12] = __ldg((const uint4 *)(rowrecs + 1) + lane - 12);
+	__syncwarp();
+	auto coef_issue = [&](int x) -> bool {       /* true: a copy is in flight into buffer x & 1 */
+		const E264MbRec *rr = (const E264MbRec *)sm.recs[w][x & 3];
+		if (rr->kind == MBK_INTER || rr->kind == MBK_IPCM || rr->coded == 0) return false;
+		if (lane == 0) tma_bulk_g2s(sm.coef[w][x & 1], J.coefs + rr->coef_off, (unsigned)rec_coef_count(rr) * 2u, &sm.bars[w][x & 1]);
+		return true;
+	};
+	bool pending = coef_issue(0);
+#pragma unroll 1
+	for (int mbx = 0; mbx < W; mbx++) {
+		/* slot mbx & 1 and record slot (mbx + 2) & 3 are free once the prediction warp is through with macroblock mbx - 2 */
+		if (lane == 0) {
+			unsigned spins = 0; bool bad = false;
+			while (*used < mbx - 1 && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
+			if (bad) atomicExch(J.err, 1u);
+			__threadfence_block();
+		}
+		__syncwarp();
+		const E264MbRec *r = (const E264MbRec *)sm.recs[w][mbx & 3];
+		WarpSmem *ws = &sm.ws[w][mbx & 1];
+		if (mbx + 2 < W && lane < 12) sm.recs[w][(mbx + 2) & 3][lane] = __ldg((const uint4 *)(rowrecs + mbx + 2) + lane);
+		const bool pending_next = mbx + 1 < W ? coef_issue(mbx + 1) : false;
+		const int kind = r->kind;
+		if (pending) {
+			if (!mbar_wait(&sm.bars[w][mbx & 1], parity[mbx & 1])) { if (lane == 0) atomicExch(J.err, 3u); }
+			parity[mbx & 1] ^= 1;
+			residual_stage(ws, r, J.slices + r->slice_idx, sm.coef[w][mbx & 1], lane);
+		} else if (kind != MBK_INTER && kind != MBK_IPCM) {
+			((uint4 *)ws->res)[lane] = make_uint4(0, 0, 0, 0);
+			if (lane < 16) ((uint4 *)ws->res)[32 + lane] = make_uint4(0, 0, 0, 0);
+		}
+		pending = pending_next;
+		__syncwarp();
+		if (lane == 0) { __threadfence_block(); *ready = mbx + 1; }
+		if (digests) dbk_digest_mb(J, sm.drecs[w], &sm.ddg[w], mby * W + mbx, lane);
+	}
+}
+
+/* The row's PREDICTION warp: waits for the residual, for the row above (top-right neighbour finished) and for room in
+ * its ring, predicts into the tile of slot x & 1, stores, hands the bottom sample row down. */
+__device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &sm, int band, int w, int lane) {
 	const int W = J.w_mbs, H = J.h_mbs, nmb = W * H;
 	const int lrow = w, mby = band * IR_ROWS + w;
 	if (mby >= H) return;
-	WarpSmem *ws = &sm.ws[w];
 	const bool from_global = lrow == 0 && mby > 0;
 	const bool from_ring = lrow > 0;
 	const bool to_ring = lrow + 1 < IR_ROWS && mby + 1 < H;
@@ -44,53 +101,23 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 	const unsigned base = J.epoch * 2048u;
 	volatile int *done_in = sm.done + (lrow > 0 ? lrow - 1 : 0), *done_out = sm.done + lrow;
 	volatile int *taken_me = sm.taken + lrow, *taken_next = sm.taken + (lrow + 1 < IR_ROWS ? lrow + 1 : lrow);
+	volatile int *ready = sm.ready + w, *used = sm.used + w;
 	uint32_t (*ring_in)[8] = sm.ring[lrow > 0 ? lrow - 1 : 0];
 	uint32_t (*ring_out)[8] = sm.ring[lrow];
 	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
 	const int cpl = J.stride_c >> 1;
-	const E264MbRec *rowrecs = J.recs + (size_t)mby * W;
 	int avail = 0;                                            /* macroblocks of the row above the band known to be stored */
-
-	/* a picture without inter macroblocks has no inter kernel to derive the deblocking digests: every row does its own first */
-	if (J.dbk != nullptr && J.n_intra == nmb) for (int x = 0; x < W; x++) dbk_digest_mb(J, sm.recs[w], (E264DbkMb *)sm.coef[w][0], mby * W + x, lane);   /* buffers the walk has not started to use */
-	/* records two ahead, coefficient runs one ahead */
-	if (lane < 12) sm.recs[w][0][lane] = __ldg((const uint4 *)rowrecs + lane);
-	if (W > 1 && lane >= 12 && lane < 24) sm.recs[w][1][lane - 12] = __ldg((const uint4 *)(rowrecs + 1) + lane - 12);
-	__syncwarp();
-	auto coef_issue = [&](int x) -> bool {       /* true: a copy is in flight into buffer x & 1 */
-		const E264MbRec *rr = (const E264MbRec *)sm.recs[w][x % 3];
-		if (rr->kind == MBK_INTER || rr->kind == MBK_IPCM || rr->coded == 0) return false;
-		if (lane == 0) tma_bulk_g2s(sm.coef[w][x & 1], J.coefs + rr->coef_off, (unsigned)rec_coef_count(rr) * 2u, &sm.bars[w][x & 1]);
-		return true;
-	};
-	bool pending = coef_issue(0);
 #pragma unroll 1
 	for (int mbx = 0; mbx < W; mbx++) {
-		const E264MbRec *r = (const E264MbRec *)sm.recs[w][mbx % 3];
-		const int kind = r->kind;
 		uint8_t *Y = dst + (size_t)(mby * 16) * J.stride_y + mbx * 16;
 		uint8_t *C = dst + J.plane_y + (size_t)(mby * 8) * J.stride_c + mbx * 8;
-		/* requests: record x+2, coefficient run of x+1 */
-		if (mbx + 2 < W && lane < 12) sm.recs[w][(mbx + 2) % 3][lane] = __ldg((const uint4 *)(rowrecs + mbx + 2) + lane);
-		const bool pending_next = mbx + 1 < W ? coef_issue(mbx + 1) : false;
-		/* this macroblock's residual — before the wait below: in the steady wavefront the row above is not ready yet anyway */
-		if (pending) {
-			if (!mbar_wait(&sm.bars[w][mbx & 1], parity[mbx & 1])) { if (lane == 0) atomicExch(J.err, 3u); }
-			parity[mbx & 1] ^= 1;
-			residual_stage(ws, r, J.slices + r->slice_idx, sm.coef[w][mbx & 1], lane);
-		} else if (kind != MBK_INTER && kind != MBK_IPCM) {
-			((uint4 *)ws->res)[lane] = make_uint4(0, 0, 0, 0);
-			if (lane < 16) ((uint4 *)ws->res)[32 + lane] = make_uint4(0, 0, 0, 0);
-			__syncwarp();
-		}
-		pending = pending_next;
-		/* ---- wait for the row above: macroblocks up to x+1 (top-right neighbour) finished; and for room in our ring ---- */
+		/* ---- wait: residual delivered; row above through with macroblocks up to x+1 (top-right neighbour); room in our ring ---- */
 		if (lane == 0) {
 			unsigned spins = 0; bool bad = false;
+			while (*ready <= mbx && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
 			const int need = min(mbx + 2, W);
 			if (from_ring) {
 				while (*done_in < need && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
-				__threadfence_block();
 			} else if (from_global && avail < need) {
 				const unsigned target = base + (unsigned)need;
 				unsigned v = prog[mby - 1];
@@ -100,9 +127,13 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 			}
 			if (to_ring) while (*taken_next <= mbx - IR_RING + 1 && !bad)     /* entry mbx - RING is still the corner sample of the row below's macroblock mbx - RING + 1 */ { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
 			if (bad) atomicExch(J.err, 1u);
+			__threadfence_block();
 			*taken_me = mbx;
 		}
 		__syncwarp();
+		const E264MbRec *r = (const E264MbRec *)sm.recs[w][mbx & 3];
+		const int kind = r->kind;
+		WarpSmem *ws = &sm.ws[w][mbx & 1];
 		/* ---- the row above into the tile ---- */
 		if (from_ring) {
 			if (lane < 4) *(uint32_t *)&YT(4 * lane, -1) = ring_in[mbx % IR_RING][lane];
@@ -147,17 +178,15 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 			if (to_ring) { __threadfence_block(); *done_out = mbx + 1; }
 			if (to_global && mbx > 0 && mbx % IR_CHUNK == 0) { __threadfence(); prog[mby] = base + (unsigned)mbx; }   /* covers macroblocks 0..mbx-1, stored in earlier iterations */
 		}
-		/* right-most column becomes the next macroblock's left neighbour */
+		/* right-most column becomes the next macroblock's left neighbour (the other slot's tile) */
 		{
-			uint8_t v = 0;
-			if (lane < 16) v = YT(15, lane);
-			else if (lane < 24) v = CT(0, 7, lane - 16);
-			const uint8_t v2 = lane < 8 ? CT(1, 7, lane) : 0;
-			__syncwarp();
-			if (lane < 16) YT(-1, lane) = v;
-			else if (lane < 24) CT(0, -1, lane - 16) = v;
-			if (lane < 8) CT(1, -1, lane) = v2;
+			WarpSmem *wn = &sm.ws[w][(mbx + 1) & 1];
+			if (lane < 16) wn->ytile[(lane + 1) * YT_STRIDE + 15] = YT(15, lane);
+			else if (lane < 24) wn->ctile[0][(lane - 16 + 1) * CT_STRIDE + 7] = CT(0, 7, lane - 16);
+			if (lane < 8) wn->ctile[1][(lane + 1) * CT_STRIDE + 7] = CT(1, 7, lane);
 		}
+		__syncwarp();
+		if (lane == 0) { __threadfence_block(); *used = mbx + 1; }
 		avail = __shfl_sync(0xffffffffu, avail, 0);
 	}
 	__syncwarp();
@@ -167,14 +196,16 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 	}
 }
 
-__global__ void __launch_bounds__(IR_ROWS * 32) e264_intra_rows_kernel(PicJob J) {
+__global__ void __launch_bounds__(IR_ROWS * 64) e264_intra_rows_kernel(PicJob J) {
 	TraceScope trace_(J, 2);
 	reset_next_tickets(J);
-	__shared__ IntraRowsSmem sm;
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	extern __shared__ __align__(16) unsigned char ir_smem_raw[];
+	IntraRowsSmem &sm = *(IntraRowsSmem *)ir_smem_raw;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, w = wid & (IR_ROWS - 1);
+	const bool transform = wid >= IR_ROWS;
 	const int bands = (J.h_mbs + IR_ROWS - 1) / IR_ROWS;
 	unsigned parity[2] = {0, 0};
-	if (lane == 0) {
+	if (transform && lane == 0) {
 		mbar_init(&sm.bars[w][0], 1); mbar_init(&sm.bars[w][1], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -182,13 +213,13 @@ __global__ void __launch_bounds__(IR_ROWS * 32) e264_intra_rows_kernel(PicJob J)
 	/* bands in dispatch order: a band only waits for bands drawn before it */
 	for (;;) {
 		__syncthreads();
-		if (threadIdx.x < IR_ROWS) { sm.done[threadIdx.x] = 0; sm.taken[threadIdx.x] = 0; }
+		if (threadIdx.x < IR_ROWS) { sm.done[threadIdx.x] = 0; sm.taken[threadIdx.x] = 0; sm.ready[threadIdx.x] = 0; sm.used[threadIdx.x] = 0; }
 		if (threadIdx.x == 0) sm.band = (int)atomicAdd(J.tickets + 2, 1u);
-
 		__syncthreads();
 		const int band = sm.band;
 		if (band >= bands) break;
-		intra_row_walk(J, sm, band, w, lane, parity);
+		if (transform) intra_row_transform(J, sm, band, w, lane, parity);
+		else intra_row_walk(J, sm, band, w, lane);
 	}
 }
 

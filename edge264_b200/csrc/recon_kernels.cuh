@@ -373,6 +373,14 @@ __device__ __forceinline__ void pred8x8_warp(const WarpSmem *ws, int X0, int Y0,
 	v1 = intra_tap_apply(E, e1 & 31, e1 >> 5);
 }
 
+/* four predicted samples (bytes of p) plus four int16 residuals (r01 = first two, r23 = last two), clipped to 8 bits;
+ * the sum wraps in 16 bits first like the reference's saturating 16-bit adds never see it: v + res fits unless res is garbage */
+__device__ __forceinline__ uint32_t intra_add_res4(uint32_t p, uint32_t r01, uint32_t r23) {
+	const int v0 = clip255((short)((int)(p & 255u) + (short)(r01 & 0xffffu))), v1 = clip255((short)((int)((p >> 8) & 255u) + (short)(r01 >> 16)));
+	const int v2 = clip255((short)((int)((p >> 16) & 255u) + (short)(r23 & 0xffffu))), v3 = clip255((short)((int)(p >> 24) + (short)(r23 >> 16)));
+	return (uint32_t)v0 | (uint32_t)v1 << 8 | (uint32_t)v2 << 16 | (uint32_t)v3 << 24;
+}
+
 __device__ __noinline__ void intra_luma(WarpSmem *ws, const E264MbRec *r, int lane) {
 	if (r->kind == MBK_I4x4) {
 		const uint64_t taps = __ldg(&e264_i4taps.v[lane & 15]);
@@ -396,62 +404,70 @@ __device__ __noinline__ void intra_luma(WarpSmem *ws, const E264MbRec *r, int la
 			YT(X0 + x, Y0 + y) = (uint8_t)v0; YT(X0 + x, Y0 + y + 4) = (uint8_t)v1;
 			__syncwarp();
 		}
-	} else {   /* Intra16x16 */
-		int mode = r->i16_mode & 15, un = r->i16_mode >> 4;
-		bool hasA = !(un & 1), hasB = !(un & 2);
-		int a = 0, b = 0, c = 0, dc = 128;
-		if (mode == 3) {
-			int H = 0, V = 0;
+	} else {   /* Intra16x16: lanes 0-15 hold the row above, 16-31 the column to the left; a lane predicts 8 samples of one row */
+		const int mode = r->i16_mode & 15, un = r->i16_mode >> 4;
+		const bool hasA = !(un & 1), hasB = !(un & 2);
+		const int ei = lane & 15, y = lane >> 1, x0 = (lane & 1) * 8;
+		const int ev = lane < 16 ? YT(ei, -1) : YT(-1, ei);
+		uint32_t p0, p1;
+		if (mode == 0) { const uint2 t = hasB ? *(const uint2 *)&YT(x0, -1) : make_uint2(0x80808080u, 0x80808080u); p0 = t.x; p1 = t.y; }
+		else if (mode == 1) { const int v = __shfl_sync(0xffffffffu, ev, 16 + y); p0 = p1 = (hasA ? (uint32_t)v : 128u) * 0x01010101u; }
+		else if (mode == 2) {
+			int sdc = ev;
+			sdc += __shfl_xor_sync(0xffffffffu, sdc, 1); sdc += __shfl_xor_sync(0xffffffffu, sdc, 2); sdc += __shfl_xor_sync(0xffffffffu, sdc, 4); sdc += __shfl_xor_sync(0xffffffffu, sdc, 8);
+			const int st = __shfl_sync(0xffffffffu, sdc, 0), sl = __shfl_sync(0xffffffffu, sdc, 16);
+			const int dc = (hasA && hasB) ? (st + sl + 16) >> 5 : hasA ? (sl + 8) >> 4 : hasB ? (st + 8) >> 4 : 128;
+			p0 = p1 = (uint32_t)dc * 0x01010101u;
+		} else {   /* plane: H = sum (i - 7) T(i) - 8 TL over i = 0..15, likewise V */
+			int t = (ei - 7) * ev;
+			t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4); t += __shfl_xor_sync(0xffffffffu, t, 8);
+			const int corner = YT(-1, -1);
+			const int Hs = __shfl_sync(0xffffffffu, t, 0) - 8 * corner, Vs = __shfl_sync(0xffffffffu, t, 16) - 8 * corner;
+			const int a = 16 * (__shfl_sync(0xffffffffu, ev, 31) + __shfl_sync(0xffffffffu, ev, 15)), b = (5 * Hs + 32) >> 6, c = (5 * Vs + 32) >> 6;
+			const int base = a + c * (y - 7) + 16 + b * (x0 - 7);
+			p0 = p1 = 0;
 #pragma unroll
-			for (int k = 0; k < 8; k++) { H += (k + 1) * ((int)YT(8 + k, -1) - (int)YT(6 - k, -1)); V += (k + 1) * ((int)YT(-1, 8 + k) - (int)YT(-1, 6 - k)); }
-			a = 16 * ((int)YT(-1, 15) + (int)YT(15, -1)); b = (5 * H + 32) >> 6; c = (5 * V + 32) >> 6;
-		} else if (mode == 2) {
-			int st = 0, sl = 0;
-#pragma unroll
-			for (int k = 0; k < 16; k++) { st += YT(k, -1); sl += YT(-1, k); }
-			dc = (hasA && hasB) ? (st + sl + 16) >> 5 : hasA ? (sl + 8) >> 4 : hasB ? (st + 8) >> 4 : 128;
+			for (int k = 0; k < 4; k++) { p0 |= (uint32_t)clip255((base + b * k) >> 5) << (8 * k); p1 |= (uint32_t)clip255((base + b * (k + 4)) >> 5) << (8 * k); }
 		}
-#pragma unroll 1
-		for (int k = 0; k < 8; k++) {   /* reads touch only samples outside the macroblock: no hazard with the writes */
-			int p = lane + 32 * k, x = p & 15, y = p >> 4;
-			int v = mode == 0 ? (hasB ? (int)YT(x, -1) : 128) : mode == 1 ? (hasA ? (int)YT(-1, y) : 128) : mode == 2 ? dc : clip255((a + b * (x - 7) + c * (y - 7) + 16) >> 5);
-			YT(x, y) = (uint8_t)clip255((short)(v + ws->res[p]));
-		}
+		const uint4 rs = *(const uint4 *)&ws->res[y * 16 + x0];
+		*(uint2 *)&YT(x0, y) = make_uint2(intra_add_res4(p0, rs.x, rs.y), intra_add_res4(p1, rs.z, rs.w));   /* the reads above touch only samples outside the macroblock */
 		__syncwarp();
 	}
 }
 
+/* both chroma planes: lanes 0-15 hold the rows above (plane, x), 16-31 the columns to the left (plane, y); a lane predicts 4
+ * samples of one row (plane = lane >> 4, y = (lane >> 1) & 7, x0 = 4 (lane & 1)), i.e. one quadrant's DC for all four */
 __device__ __noinline__ void intra_chroma(WarpSmem *ws, const E264MbRec *r, int lane) {
-	int mode = r->chroma_mode & 15, un = r->chroma_mode >> 4;
-	bool hasA = !(un & 1), hasB = !(un & 2);
-#pragma unroll 1
-	for (int k = 0; k < 4; k++) {   /* reads touch only the row above / column left of the block */
-		int p = lane + 32 * k, pl = p >> 6, x = p & 7, y = (p >> 3) & 7, v;
-#define TC(i) (hasB ? (int)CT(pl, i, -1) : 128)
-#define LC(i) (hasA ? (int)CT(pl, -1, i) : 128)
-		if (mode == 0) {
-			int bx = x >> 2, by = y >> 2, st = 0, sl = 0;
+	const int mode = r->chroma_mode & 15, un = r->chroma_mode >> 4;
+	const bool hasA = !(un & 1), hasB = !(un & 2);
+	const int ep = (lane >> 3) & 1, ei = lane & 7;
+	const int pl = lane >> 4, y = (lane >> 1) & 7, x0 = (lane & 1) * 4;
+	const int ev = lane < 16 ? CT(ep, ei, -1) : CT(ep, -1, ei);
+	uint32_t p;
+	if (mode == 0) {
+		int s4 = ev + __shfl_xor_sync(0xffffffffu, ev, 1); s4 += __shfl_xor_sync(0xffffffffu, s4, 2);
+		const int bx = x0 >> 2, by = y >> 2;
+		const int st = __shfl_sync(0xffffffffu, s4, pl * 8 + bx * 4), sl = __shfl_sync(0xffffffffu, s4, 16 + pl * 8 + by * 4);
+		int v;
+		if (bx == by) v = (hasA && hasB) ? (st + sl + 4) >> 3 : hasA ? (sl + 2) >> 2 : hasB ? (st + 2) >> 2 : 128;
+		else if (bx == 1) v = hasB ? (st + 2) >> 2 : hasA ? (sl + 2) >> 2 : 128;
+		else v = hasA ? (sl + 2) >> 2 : hasB ? (st + 2) >> 2 : 128;
+		p = (uint32_t)v * 0x01010101u;
+	} else if (mode == 1) { const int v = __shfl_sync(0xffffffffu, ev, 16 + pl * 8 + y); p = (hasA ? (uint32_t)v : 128u) * 0x01010101u; }
+	else if (mode == 2) p = hasB ? *(const uint32_t *)&CT(pl, x0, -1) : 0x80808080u;
+	else {   /* plane: H = sum (i - 3) T(i) - 4 TL over i = 0..7, likewise V */
+		int t = (ei - 3) * ev;
+		t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4);
+		const int corner = CT(pl, -1, -1);
+		const int Hs = __shfl_sync(0xffffffffu, t, pl * 8) - 4 * corner, Vs = __shfl_sync(0xffffffffu, t, 16 + pl * 8) - 4 * corner;
+		const int a = 16 * (__shfl_sync(0xffffffffu, ev, 16 + pl * 8 + 7) + __shfl_sync(0xffffffffu, ev, pl * 8 + 7)), b = (34 * Hs + 32) >> 6, c = (34 * Vs + 32) >> 6;
+		const int base = a + c * (y - 3) + 16 + b * (x0 - 3);
+		p = 0;
 #pragma unroll
-			for (int q = 0; q < 4; q++) { st += TC(bx * 4 + q); sl += LC(by * 4 + q); }
-			if (bx == by) v = (hasA && hasB) ? (st + sl + 4) >> 3 : hasA ? (sl + 2) >> 2 : hasB ? (st + 2) >> 2 : 128;
-			else if (bx == 1) v = hasB ? (st + 2) >> 2 : hasA ? (sl + 2) >> 2 : 128;
-			else v = hasA ? (sl + 2) >> 2 : hasB ? (st + 2) >> 2 : 128;
-		} else if (mode == 1) v = LC(y);
-		else if (mode == 2) v = TC(x);
-		else {
-			int H = 0, V = 0, corner = CT(pl, -1, -1);
-#pragma unroll
-			for (int q = 0; q < 4; q++) {
-				H += (q + 1) * ((int)CT(pl, 4 + q, -1) - (q == 3 ? corner : (int)CT(pl, 2 - q, -1)));
-				V += (q + 1) * ((int)CT(pl, -1, 4 + q) - (q == 3 ? corner : (int)CT(pl, -1, 2 - q)));
-			}
-			int a = 16 * ((int)CT(pl, -1, 7) + (int)CT(pl, 7, -1)), b = (34 * H + 32) >> 6, c = (34 * V + 32) >> 6;
-			v = clip255((a + b * (x - 3) + c * (y - 3) + 16) >> 5);
-		}
-#undef TC
-#undef LC
-		CT(pl, x, y) = (uint8_t)clip255((short)(v + ws->res[256 + pl * 64 + y * 8 + x]));
+		for (int k = 0; k < 4; k++) p |= (uint32_t)clip255((base + b * k) >> 5) << (8 * k);
 	}
+	const uint2 rs = *(const uint2 *)&ws->res[256 + pl * 64 + y * 8 + x0];
+	*(uint32_t *)&CT(pl, x0, y) = intra_add_res4(p, rs.x, rs.y);   /* the reads above touch only the row above / column left of the block */
 	__syncwarp();
 }
 

@@ -44,10 +44,12 @@ int      e264b_kept_count(E264bDevice *dev);
 double   e264b_kept_algorithmic_bytes(E264bDevice *dev, double *recon_bytes, double *deblock_bytes, uint64_t *macroblocks);
 typedef struct E264bReplayStats {
 	float    ms_total;             /* device time from the common start to the last stream's end */
-	int      threads;              /* host threads that issued the launches */
-	uint64_t launches;
+	int      threads;              /* host threads that issued the launches; 0: one CUDA graph per stream and repetition */
+	uint64_t launches;             /* kernels executed in the timed region */
 	double   kernel_ms[5];         /* per kernel kind (1 inter, 2 intra, 3 deblock; 0 and 4 unused): sum over launches of last-block-end minus first-block-start */
 	uint64_t kernel_launches[5];
+	int      inflight;             /* graph replay: streams with pictures on the GPU at a time */
+	int      reserved;
 } E264bReplayStats;
 int      e264b_replay(E264bDevice **devs, int n, int reps, int threads, E264bReplayStats *stats);
 uint64_t e264b_slot_hash(E264bDevice *dev, int slot);
