@@ -31,6 +31,10 @@ typedef struct CabacDec {
 static uint8_t cabac_next_mps[128], cabac_next_lps[128];
 static uint8_t cabac_trans[256];      /* [0..127] state after an MPS, [128..255] after an LPS */
 static uint8_t cabac_lps4[4 * 128];   /* rangeTabLPS indexed by qCodIRangeIdx * 128 + packed state */
+/* per packed state: four 16-bit entries (one per qCodIRangeIdx) = rangeLPS | renormalisation shift of rangeLPS << 8.
+ * Indexed by the STATE only, so the load does not wait for the previous bin's range; the range picks its entry
+ * with one variable shift. */
+static uint64_t cabac_lpsw[128];
 static int cabac_tables_ready;
 static void cabac_build_tables(void) {
 	if (cabac_tables_ready) return;
@@ -40,6 +44,9 @@ static void cabac_build_tables(void) {
 		cabac_trans[s * 2 + m] = cabac_next_mps[s * 2 + m];
 		cabac_trans[128 + s * 2 + m] = cabac_next_lps[s * 2 + m];
 		for (int q = 0; q < 4; q++) cabac_lps4[q * 128 + s * 2 + m] = h264_range_lps[s][q];
+		uint64_t w = 0;
+		for (int q = 0; q < 4; q++) w |= (uint64_t)(h264_range_lps[s][q] | ((__builtin_clz((unsigned)h264_range_lps[s][q]) - 23) << 8)) << (16 * q);
+		cabac_lpsw[s * 2 + m] = w;
 	}
 	cabac_tables_ready = 1;
 }
@@ -67,19 +74,39 @@ static inline void cabac_r_refill(CabacRegs *r) {
 		r->avail += 32;
 	}
 }
+/* One context-coded bin.  The serial dependency between bins runs through `range` (and `val`); it is kept short:
+ * the table word depends on the state only, the renormalised LPS range comes from the table (no count-leading-zeros
+ * in the chain), the MPS range needs a shift of 0 or 1, and the two outcomes are selected with conditional moves. */
 static inline int cabac_r_bin(CabacRegs *r, CabacState *state, int ctx) {
 	cabac_r_refill(r);
-	uint32_t s = state[ctx];
-	uint32_t lps = cabac_lps4[((r->range & 0xC0) << 1) + s];
-	uint32_t rmps = r->range - lps;
-	uint64_t scaled = (uint64_t)rmps << CABAC_POS;
-	uint64_t m = (uint64_t)0 - (uint64_t)(r->val >= scaled);     /* all ones on the LPS path */
-	r->val -= scaled & m;
-	uint32_t range = rmps + ((lps - rmps) & (uint32_t)m);
-	state[ctx] = cabac_trans[s + ((uint32_t)m & 128)];
-	int n = __builtin_clz(range) - 23;
-	r->range = range << n; r->val <<= n; r->avail -= n;
-	return (int)((s ^ (uint32_t)m) & 1);
+	const uint32_t s = state[ctx];
+	const uint64_t w = cabac_lpsw[s];
+	const uint32_t range = r->range;
+	const uint32_t e = (uint32_t)(w >> ((range >> 2) & 0x30));
+	const uint32_t lps = e & 0xff, nl = (e >> 8) & 7;
+	const uint32_t rmps = range - lps;
+	const uint64_t scaled = (uint64_t)rmps << CABAC_POS;
+	const uint32_t nm = (rmps >> 8) ^ 1;                 /* rmps is in [128, 510]: shift by one iff below 256 */
+	const uint32_t rm = rmps << nm, rl = lps << nl;
+	uint64_t val = r->val; const uint64_t vl = val - scaled;
+	uint32_t n = nm, range2 = rm, is_lps;
+#if defined(__x86_64__)
+	/* compilers turn the three selections into ONE branch, and bins at this bit rate are close to unpredictable
+	 * (about 0.75 bit of information each): conditional moves keep the cost flat */
+	uint8_t f;
+	__asm__("cmp %[sc], %[v]\n\tcmovae %[rl], %[rg]\n\tcmovae %[nl], %[n]\n\tcmovae %[vl], %[v]\n\tsetae %[f]"
+		: [rg] "+r"(range2), [n] "+r"(n), [v] "+r"(val), [f] "=q"(f)
+		: [sc] "r"(scaled), [rl] "r"(rl), [nl] "r"(nl), [vl] "r"(vl) : "cc");
+	is_lps = f;
+#else
+	const uint64_t m = (uint64_t)0 - (uint64_t)(val >= scaled);
+	is_lps = (uint32_t)m & 1; n ^= (n ^ nl) & (uint32_t)m; range2 ^= (range2 ^ rl) & (uint32_t)m; val -= scaled & m;
+#endif
+	r->range = range2;
+	r->val = val << n;
+	r->avail -= n;
+	state[ctx] = cabac_trans[s + (is_lps << 7)];
+	return (int)((s & 1) ^ is_lps);
 }
 static inline int cabac_r_bypass(CabacRegs *r) {
 	cabac_r_refill(r);
