@@ -16,8 +16,8 @@ One "step" = one pass over the batch of one GPU.
           Each launch also stamps its first/last block (%globaltimer): the roofline object is computed from THIS pass.
   e2e     the same batch decoded through the edge264 C API (edge264_decode_NAL / get_frame) from HOST buffers: CPU
           parsing, H2D of the records, kernels, D2H of every frame and a host read of every output frame are inside the
-          timed region.  One application thread per stream; with CPUs to spare each decoder also parses ahead on worker
-          threads (edge264_alloc n_threads).
+          timed region.  A pool of application threads (one per usable CPU, at most one per stream) takes the streams one
+          after the other; with CPUs to spare each decoder also parses ahead on worker threads (edge264_alloc n_threads).
   --impl reference   the reference decoder compiled from its own sources (oracle/_ref), one single-threaded decoder per
           stream on all usable host cores, same streams, same application loop.
 """
@@ -220,6 +220,10 @@ def main():
     cpus = max(1, usable_cpus() // world)
     dec_threads = args.dec_threads if args.dec_threads >= 0 else max(0, min(4, cpus // S))
     os.environ["E264_BENCH_DEC_THREADS"] = str(dec_threads)
+    # application threads: a pool that takes the units one after the other, like the reference arm's; no more threads than
+    # CPUs (measured on the 16-CPU box, profiles/r2_e2e_threads.txt: 32 units on 16 threads 1292 frames/s, on 32 threads 1220 —
+    # the waits for the GPU are short, surplus threads only cost context switches and cache)
+    app_threads = max(1, min(S, cpus))
 
     lib = BenchLib(os.path.join(ROOT, "tools", "libe264bench.so"))
     core = ctypes.CDLL(os.path.join(ROOT, "edge264_b200", "libedge264_b200.so"))
@@ -238,13 +242,13 @@ def main():
     # ---- e2e: decode through the C API from host buffers ----
     os.environ["E264B_KEEP"] = "0"
     for _ in range(max(args.warmup, 1)):          # also creates and pools the per-decoder device contexts
-        _, frames, sums, d = lib.run(bufs, S); lib.free(d)
+        _, frames, sums, d = lib.run(bufs, app_threads); lib.free(d)
     frames_per_step = sum(frames)
     sampler = ClockSampler(local); sampler.start()
     barrier()
     e2e_secs = 0.0; h2d = d2h = 0
     for _ in range(args.steps):
-        s, fr, sm, d = lib.run(bufs, S, keep=True)
+        s, fr, sm, d = lib.run(bufs, app_threads, keep=True)
         for i in range(S):
             a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
             core.e264b_stats(core.e264b_of_decoder(d[i]), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)); h2d += b.value; d2h += c.value
@@ -257,7 +261,7 @@ def main():
 
     # the same batch once more with E264B_KEEP=1: the decoders stay alive and retain their device-side records
     os.environ["E264B_KEEP"] = "1"
-    _, frames, sums_k, decs = lib.run(bufs, S, keep=True)
+    _, frames, sums_k, decs = lib.run(bufs, app_threads, keep=True)
     assert sums_k == sums
     os.environ["E264B_KEEP"] = "0"
     devs = (ctypes.c_void_p * S)(*[core.e264b_of_decoder(decs[i]) for i in range(S)])
@@ -309,8 +313,8 @@ def main():
             "macroblocks_per_s": fps * mbpf, "config": config_dict(cfg, args, world),
             "clocks": sampler.summary(), "gpu_launches": int(st.launches), "replay": f"cuda-graph per stream and step, {int(st.inflight)} streams in flight" if st.threads == 0 else f"{int(st.threads)} host launch threads",
             "e2e": {"value": e2e_fps, "unit": "frames/s", "macroblocks_per_s": e2e_fps * mbpf, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-                    "app_threads": S, "decoder_n_threads": dec_threads, "usable_cpus": usable_cpus(), "cpus_per_rank": cpus, "bytes_per_unit": len(bufs[0]),
-                    "saturated": "host CPUs (bitstream parsing)" if S * max(1, dec_threads) >= cpus else "streams in flight",
+                    "app_threads": app_threads, "decoder_n_threads": dec_threads, "usable_cpus": usable_cpus(), "cpus_per_rank": cpus, "bytes_per_unit": len(bufs[0]),
+                    "saturated": "host CPUs (bitstream parsing)" if app_threads * max(1, dec_threads + 1) >= cpus else "streams in flight",
                     "note": "edge264_decode_NAL/get_frame from host buffers; application threads sleep while get_frame waits for the GPU"},
             "roofline": roof}
     lib.free(decs)

@@ -202,60 +202,30 @@ __device__ __forceinline__ void dbk_walk(const PicJob &J, DbkSmem *sm, int band,
 	}
 
 #pragma unroll 1
-	for (int i = 0; i <= W + 2; i++) {
-		const int x = i - 2 * half;
+	for (int i = 0; i <= W + 1; i++) {
+		const int x = i - half;
 		const bool act = row_ok && x >= 0 && x < W;       /* a macroblock to filter */
 		const bool fin = row_ok && x >= 1 && x <= W;      /* macroblock x-1 receives its last change (our left edge) and is stored */
 		uint32_t cur[NW];
 #pragma unroll
 		for (int k = 0; k < NW; k++) cur[k] = nxt[k];
-		/* ---- digest and the rows above into shared memory ---- */
+		/* ---- digest into shared memory; room in the lower row's ring ---- */
 		if (act && hl < 4) ((uint4 *)&dgs[half])[hl] = ndg;
-		{
-			/* lane 0 waits for both rows of the warp (one lane, single-exit loops: the warp must reconverge behind
-			 * this, or the two halves would run the whole iteration one after the other): the upper row's input — ring
-			 * of the warp above, or the previous band through global memory — and room in the lower row's ring */
-			if (lane == 0) {
-				unsigned spins = 0;
-				bool bad = false;
-				if (act && mby > 0) {      /* lane 0 belongs to the upper row: act, mby, x are the upper row's */
-					if (wid > 0) {
-						while (*done_in < x + 1 && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
-						__threadfence_block();
-					} else if (avail < x + 1) {
-						const unsigned need = base + (unsigned)x + 1u;
-						unsigned v = prog[mby - 1];
-						while ((int)(v - need) < 0 && !bad) { __nanosleep(40); if ((++spins & 255) == 0) bad = *errp != 0 || spins > (1u << 22); v = prog[mby - 1]; }
-						__threadfence();
-						avail = bad ? W : (int)(v - base);
-					}
-				}
-				{	/* the lower row (local row lrow + 1) stores macroblock i - 3 in this iteration */
-					const int xl = i - 2;
-					const bool l_out = lrow + 2 < 2 * DBK_PAIRS && mby + 2 < H;
-					if (l_out && xl >= 1 && xl <= W) {
-						volatile int *tk = sm->taken + lrow + 2;
-						while (*tk < xl - DBK_RING && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
-					}
-				}
+		if (lane == 0) {	/* the lower row (local row lrow + 1) stores macroblock i - 2 into its ring in this iteration */
+			const int xl = i - 1;
+			const bool l_out = lrow + 2 < 2 * DBK_PAIRS && mby + 2 < H;
+			if (l_out && xl >= 1 && xl <= W) {
+				unsigned spins = 0; bool bad = false;
+				volatile int *tk = sm->taken + lrow + 2;
+				while (*tk < xl - DBK_RING && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
 				if (bad) atomicExch(J.err, 1u);
-			}
-			__syncwarp();
-			avail = __shfl_sync(0xffffffffu, avail, 0);
-			__syncwarp();
-			if (act && top_lane) {
-				uint32_t tw[NW];
-#pragma unroll
-				for (int k = 0; k < NW; k++) tw[k] = from_global ? ntop[k] : ring_in[x % DBK_RING][hl][k];
-				if (from_global && !have_top) {       /* rare: the row above was not known to be ready one iteration ago */
-					if (CH) { uint2 v = __ldcg((const uint2 *)(topp + x * MBW)); tw[0] = v.x; tw[1] = v.y; }
-					else { uint4 v = __ldcg((const uint4 *)(topp + x * MBW)); tw[0] = v.x; tw[1] = v.y; tw[2 % NW] = v.z; tw[3 % NW] = v.w; }
-				}
-#pragma unroll
-				for (int k = 0; k < NW; k++) top[half][hl][k] = tw[k];
 			}
 		}
 		/* ---- requests for the next iteration ---- */
+		const bool had_top = have_top;        /* ntop holds the rows above macroblock x */
+		uint32_t ctop[NW];
+#pragma unroll
+		for (int k = 0; k < NW; k++) ctop[k] = ntop[k];
 		{
 			const int xn = x + 1;
 			const bool nact = row_ok && xn >= 0 && xn < W;
@@ -271,7 +241,6 @@ __device__ __forceinline__ void dbk_walk(const PicJob &J, DbkSmem *sm, int band,
 			}
 		}
 		__syncwarp();
-		if (cross_in && act && hl == 0) *taken_me = x + 1;      /* the ring slot has been copied */
 		/* ---- vertical edges: this lane's sample row, left to right, in registers ---- */
 		uint32_t carry = prev[NW - 1];
 		/* the bS 4 vote is taken by the whole warp, outside the predicated region (a vote inside diverged code can hang) */
@@ -326,6 +295,39 @@ __device__ __forceinline__ void dbk_walk(const PicJob &J, DbkSmem *sm, int band,
 		}
 		__syncwarp();
 		if (cross_out && fin && hl == 0) { __threadfence_block(); *done_out = x; }     /* macroblocks 0..x-1 are in the ring */
+		/* ---- the rows above: needed by the horizontal pass only, so the row above has to be just ONE macroblock ahead
+		 * (its vertical pass of x + 1 finalises x).  Lower row of the warp: the upper row wrote the ring slot before the
+		 * barrier above.  Upper row: lane 0 waits (single-exit loops, the warp reconverges behind them) for the warp above
+		 * (shared-memory counter) or the previous band (global progress counter). */
+		if (lane == 0 && act && mby > 0) {      /* lane 0 belongs to the upper row: act, mby, x are the upper row's */
+			unsigned spins = 0; bool bad = false;
+			if (wid > 0) {
+				while (*done_in < x + 1 && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
+				__threadfence_block();
+			} else if (avail < x + 1) {
+				const unsigned need = base + (unsigned)x + 1u;
+				unsigned v = prog[mby - 1];
+				while ((int)(v - need) < 0 && !bad) { __nanosleep(40); if ((++spins & 255) == 0) bad = *errp != 0 || spins > (1u << 22); v = prog[mby - 1]; }
+				__threadfence();
+				avail = bad ? W : (int)(v - base);
+			}
+			if (bad) atomicExch(J.err, 1u);
+		}
+		__syncwarp();
+		avail = __shfl_sync(0xffffffffu, avail, 0);
+		if (act && top_lane) {
+			uint32_t tw[NW];
+#pragma unroll
+			for (int k = 0; k < NW; k++) tw[k] = from_global ? ctop[k] : ring_in[x % DBK_RING][hl][k];
+			if (from_global && !had_top) {       /* rare: the row above was not known to be ready one iteration ago */
+				if (CH) { uint2 v = __ldcg((const uint2 *)(topp + x * MBW)); tw[0] = v.x; tw[1] = v.y; }
+				else { uint4 v = __ldcg((const uint4 *)(topp + x * MBW)); tw[0] = v.x; tw[1] = v.y; tw[2 % NW] = v.z; tw[3 % NW] = v.w; }
+			}
+#pragma unroll
+			for (int k = 0; k < NW; k++) top[half][hl][k] = tw[k];
+		}
+		__syncwarp();
+		if (cross_in && act && hl == 0) *taken_me = x + 1;      /* the ring slot has been copied */
 		/* ---- horizontal edges: this lane's sample column, top to bottom ---- */
 		const int c = CH ? hl & 7 : hl;
 		const int hseg4 = (CH ? c >> 1 : c >> 2) * 4;

@@ -281,13 +281,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_intra_kernel(PicJob
 				((uint4 *)ws->res)[lane] = make_uint4(0, 0, 0, 0);
 				if (lane < 16) ((uint4 *)ws->res)[32 + lane] = make_uint4(0, 0, 0, 0);
 			}
-			bool ok = true;
-			if (lane == 0) {
-				if (mbx > 0) ok = wait_flag(J.flags, mb - 1, J.epoch, J.err);
-				if (ok && mby > 0 && mbx > 0) ok = wait_flag(J.flags, mb - W - 1, J.epoch, J.err);
-				if (ok && mby > 0) ok = wait_flag(J.flags, mb - W, J.epoch, J.err);
-				if (ok && mby > 0) ok = wait_flag(J.flags, mbx < W - 1 ? mb - W + 1 : mb - W, J.epoch, J.err);
-				__threadfence();
+			{	/* A, D, B, C: one lane each, the four round trips overlap */
+				int idx = -1;
+				if (lane == 0 && mbx > 0) idx = mb - 1;
+				else if (lane == 1 && mby > 0 && mbx > 0) idx = mb - W - 1;
+				else if (lane == 2 && mby > 0) idx = mb - W;
+				else if (lane == 3 && mby > 0) idx = mbx < W - 1 ? mb - W + 1 : mb - W;
+				if (idx >= 0) wait_flag_acquire(J.flags, idx, J.epoch, J.err);
 			}
 			__syncwarp();
 			if (mby > 0) {

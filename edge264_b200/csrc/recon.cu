@@ -225,7 +225,7 @@ static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, int stage, const E
 	J.dbk = pd->any_deblock ? c->st[stage].d_dbk : NULL;
 	J.intra_list = intra; J.n_intra = pd->n_intra;
 	J.rows_mode = pd->n_intra * 2 > pd->width_mbs * pd->height_mbs;   /* intra pictures: wavefront of row warps */
-	J.trace = NULL; J.trace_base = 0; J.trace_rep = NULL; J.trace_rep_stride = 0;
+	J.trace = NULL; J.trace_base = 0; J.trace_rep = NULL; J.trace_rep_stride = 0; J.diag = 0;
 	if (c->epoch >= (1u << 20)) {   /* row progress counters encode epoch * 2048 + count: restart before it wraps */
 		cudaStreamSynchronize(c->stream);
 		cudaMemsetAsync(c->d_sync, 0, c->sync_words * sizeof(unsigned), c->stream);
@@ -241,9 +241,18 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 	static int minb = -1, dm = -1;
 	if (minb < 0) { const char *e = getenv("E264B_MINB"); minb = e ? atoi(e) : 4; }
 	if (dm < 0) { const char *e = getenv("E264B_DBK_MINB"); dm = e ? atoi(e) : 2; }
+	/* experiments (replay only): E264B_REPLAY_ONLY = mask of kernel kinds to launch (1 inter, 2 intra, 4 deblocking; J.trace
+	 * marks a replay), E264B_DBK_SMEM = extra dynamic shared memory of the deblocking blocks (limits blocks per SM) */
+	static int only = -1, dbk_smem = -1;
+	if (only < 0) { const char *e = getenv("E264B_REPLAY_ONLY"); only = e && atoi(e) > 0 ? atoi(e) : 7; }
+	if (dbk_smem < 0) {
+		const char *e = getenv("E264B_DBK_SMEM"); dbk_smem = e ? atoi(e) : 0;
+		if (dbk_smem > 0) { cudaFuncSetAttribute(e264_deblock_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dbk_smem); cudaFuncSetAttribute(e264_deblock_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dbk_smem); cudaFuncSetAttribute(e264_deblock_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, dbk_smem); }
+	}
+	const int mask = J.trace ? only : 7;
 	/* up to three launches per picture, nothing in between: inter macroblocks (inverse transform + prediction), intra
 	 * macroblocks (flags order them behind their neighbours), deblocking (its blocks derive the boundary strengths first) */
-	if (pd->n_intra < nmb) {
+	if (pd->n_intra < nmb && (mask & 1)) {
 		int ib = (nmb + INTER_CHUNK - 1) / INTER_CHUNK;
 		if (ib > cap) ib = cap;
 		if (minb >= 8) e264_inter4_kernel<8><<<ib, INTER_WARPS * 32, 0, c->stream>>>(J);
@@ -251,21 +260,25 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 		else e264_inter4_kernel<4><<<ib, INTER_WARPS * 32, 0, c->stream>>>(J);
 		c->launches++;
 	}
-	if (pd->n_intra > 0) {
+	if (pd->n_intra > 0 && (mask & 2)) {
 		if (J.rows_mode) {   /* intra pictures: bands of rows, hand-over through shared memory */
 			e264_intra_rows_kernel<<<(J.h_mbs + IR_ROWS - 1) / IR_ROWS, IR_ROWS * 64, sizeof(IntraRowsSmem), c->stream>>>(J);
 		} else {
-			int ib = (pd->n_intra + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+			/* the kernel's span is the longest chain of dependent intra macroblocks, not its amount of work: a warp takes
+			 * several list entries (E264B_INTRA_DIV, default 1) and a picture holds that many fewer blocks resident */
+			static int idiv = -1;
+			if (idiv < 0) { const char *e = getenv("E264B_INTRA_DIV"); idiv = e && atoi(e) > 0 ? atoi(e) : 1; }
+			int ib = (pd->n_intra + WARPS_PER_BLOCK * idiv - 1) / (WARPS_PER_BLOCK * idiv);
 			if (ib > cap) ib = cap;
 			e264_intra_kernel<<<ib, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
 		}
 		c->launches++;
 	}
-	if (with_deblock) {      /* one block per band of 16 rows and kind of plane */
+	if (with_deblock && (mask & 4)) {      /* one block per band of 16 rows and kind of plane */
 		const int bands = (J.h_mbs + 2 * DBK_PAIRS - 1) / (2 * DBK_PAIRS);
-		if (dm >= 5) e264_deblock_kernel<5><<<2 * bands, DBK_PAIRS * 32, 0, c->stream>>>(J);
-		else if (dm == 4) e264_deblock_kernel<4><<<2 * bands, DBK_PAIRS * 32, 0, c->stream>>>(J);
-		else e264_deblock_kernel<2><<<2 * bands, DBK_PAIRS * 32, 0, c->stream>>>(J);
+		if (dm >= 5) e264_deblock_kernel<5><<<2 * bands, DBK_PAIRS * 32, dbk_smem, c->stream>>>(J);
+		else if (dm == 4) e264_deblock_kernel<4><<<2 * bands, DBK_PAIRS * 32, dbk_smem, c->stream>>>(J);
+		else e264_deblock_kernel<2><<<2 * bands, DBK_PAIRS * 32, dbk_smem, c->stream>>>(J);
 		c->launches++;
 	}
 	CK(cudaGetLastError());
@@ -399,6 +412,8 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264
 	 * of individual launches (tens of thousands per second for the whole process, less with several threads contending
 	 * for the driver) would otherwise bound the result.  The synchronisation words restart at every repetition
 	 * (two memset nodes) because the captured epochs repeat.  E264B_REPLAY_GRAPH=0 issues plain launches instead. */
+	const int diag = getenv("E264B_DIAG") && atoi(getenv("E264B_DIAG")) ? 1 : 0;
+	if (diag) { static unsigned z[3][4][160]; cudaMemcpyToSymbol(g_diag_cnt, z[0], sizeof z[0]); cudaMemcpyToSymbol(g_diag_cur, z[1], sizeof z[1]); cudaMemcpyToSymbol(g_diag_max, z[2], sizeof z[2]); }
 	const char *ge = getenv("E264B_REPLAY_GRAPH");
 	const bool use_graph = !(ge && atoi(ge) == 0);
 	std::vector<cudaGraphExec_t> execs(n, nullptr);
@@ -418,7 +433,7 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264
 			for (size_t k = 0; k < npic && !bad; k++) {
 				KeptPic &kp = c->kept[k];
 				PicJob J = make_job(c, &kp.pd, kp.pd.staging, kp.d_recs, kp.d_coefs, kp.d_slices, kp.d_intra);
-				J.trace = d_trace; J.trace_base = (int)((k * n + i) * NK); J.trace_rep = d_rep + i; J.trace_rep_stride = (int)(npic * n * NK);
+				J.trace = d_trace; J.trace_base = (int)((k * n + i) * NK); J.trace_rep = d_rep + i; J.trace_rep_stride = (int)(npic * n * NK); J.diag = diag;
 				bad = launch_picture(c, J, &kp.pd, kp.pd.any_deblock);
 			}
 			e264_replay_rep_kernel<<<1, 32, 0, c->stream>>>(d_rep + i);
@@ -479,6 +494,17 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264
 	std::vector<unsigned long long> h(n_trace * 2 + 16);
 	CK(cudaMemcpy(h.data(), d_trace, n_trace * 16 + 128, cudaMemcpyDeviceToHost)); cudaFree(d_trace);
 	for (size_t j = 0; j < n_trace; j++) if (h[2 * j + 1] && h[2 * j] != ~0ull) { stats->kernel_ms[j % NK] += 1e-6 * (double)(h[2 * j + 1] - h[2 * j]); stats->kernel_launches[j % NK]++; }
+	if (diag) {     /* block placement: per kernel kind, how many SMs saw blocks, the spread of blocks per SM, the most blocks resident at once */
+		static unsigned cnt[4][160], mx[4][160];
+		cudaMemcpyFromSymbol(cnt, g_diag_cnt, sizeof cnt); cudaMemcpyFromSymbol(mx, g_diag_max, sizeof mx);
+		for (int k = 1; k < 4; k++) {
+			unsigned used = 0, lo = ~0u, hi = 0, m = 0; unsigned long long tot = 0; unsigned hist[9] = {0};
+			for (int s_ = 0; s_ < 160; s_++) if (cnt[k][s_]) { used++; tot += cnt[k][s_]; lo = cnt[k][s_] < lo ? cnt[k][s_] : lo; hi = cnt[k][s_] > hi ? cnt[k][s_] : hi; m = mx[k][s_] > m ? mx[k][s_] : m; hist[mx[k][s_] > 8 ? 8 : mx[k][s_]]++; }
+			fprintf(stderr, "diag kind %d: %llu blocks on %u SMs (per SM min %u max %u), max resident on one SM %u; SMs by max resident 1..8+:", k, tot, used, used ? lo : 0, hi, m);
+			for (int j = 1; j < 9; j++) fprintf(stderr, " %u", hist[j]);
+			fprintf(stderr, "\n");
+		}
+	}
 	const char *trace_path = getenv("E264B_TRACE");
 	if (trace_path) {
 		FILE *f = fopen(trace_path, "w");

@@ -30,6 +30,7 @@ struct PicJob {
 	int trace_base;
 	const unsigned *trace_rep;   /* graph replay: device counter of the repetition under way; its slots start trace_rep_stride further on */
 	int trace_rep_stride;
+	int diag;                    /* measurement only: count block placement per SM (g_diag_*) */
 };
 
 #define WARPS_PER_BLOCK 4
@@ -66,13 +67,18 @@ __device__ __forceinline__ int norm8(int m, int i, int j) {
 
 __device__ __forceinline__ void reset_next_tickets(const PicJob &J) { if (blockIdx.x == 0 && threadIdx.x < 4) J.tickets_next[threadIdx.x] = 0; }
 
+/* measurement only (replay with E264B_DIAG=1): how the blocks of each kernel kind land on the SMs —
+ * [kind][sm]: blocks started, blocks of this kind resident right now, the maximum of that */
+__device__ unsigned g_diag_cnt[4][160], g_diag_cur[4][160], g_diag_max[4][160];
 /* measurement only: first-start / last-end timestamps of a launch, see e264b_replay */
 struct TraceScope {
-	unsigned long long *t;
+	unsigned long long *t; int dk; unsigned sm;
 	__device__ __forceinline__ static unsigned long long now() { unsigned long long v; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)); return v; }
 	/* one thread per block: two atomics per block keep the timed replay undisturbed (a block's first warp starts it, its exit is within one macroblock of the block's end) */
-	__device__ __forceinline__ TraceScope(const PicJob &J, int kind) { t = J.trace ? J.trace + 2 * ((size_t)J.trace_base + kind + (J.trace_rep ? (size_t)*J.trace_rep * J.trace_rep_stride : 0)) : nullptr; if (t && threadIdx.x == 0) atomicMin(t, now()); }
-	__device__ __forceinline__ ~TraceScope() { if (t && threadIdx.x == 0) atomicMax(t + 1, now()); }
+	__device__ __forceinline__ TraceScope(const PicJob &J, int kind) { t = J.trace ? J.trace + 2 * ((size_t)J.trace_base + kind + (J.trace_rep ? (size_t)*J.trace_rep * J.trace_rep_stride : 0)) : nullptr; if (t && threadIdx.x == 0) atomicMin(t, now());
+		dk = -1;
+		if (J.diag && threadIdx.x == 0) { dk = kind; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); sm = sm < 160 ? sm : 159; atomicAdd(&g_diag_cnt[kind][sm], 1u); unsigned c = atomicAdd(&g_diag_cur[kind][sm], 1u) + 1; atomicMax(&g_diag_max[kind][sm], c); } }
+	__device__ __forceinline__ ~TraceScope() { if (t && threadIdx.x == 0) atomicMax(t + 1, now()); if (dk >= 0 && threadIdx.x == 0) atomicSub(&g_diag_cur[dk][sm], 1u); }
 };
 
 /* spin until flags[idx] == epoch (lane 0).  Bounded so that a bug cannot hang the GPU: gives up after ~0.2 s of SM
@@ -92,6 +98,24 @@ __device__ __forceinline__ bool wait_flag(const unsigned *flags, int idx, unsign
 	return true;
 }
 
+/* the same with acquire loads (no fence behind it): several lanes of a warp may each wait for their own flag, so the
+ * round trips to L2 overlap instead of adding up; a __syncwarp() behind the waits orders the other lanes' loads */
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ bool wait_flag_acquire(const unsigned *flags, int idx, unsigned epoch, unsigned *err) {
+	const unsigned *f = flags + idx;
+	unsigned spins = 0;
+	long long t0 = 0;
+	bool ok = true;
+	while (ok && ld_acquire_u32(f) != epoch) {
+		__nanosleep(64);
+		if ((++spins & 63) == 0) {
+			if (*(const volatile unsigned *)err) ok = false;
+			else if (t0 == 0) t0 = clock64();
+			else if (clock64() - t0 > 400000000ll) { atomicExch(err, 1u); ok = false; }
+		}
+	}
+	return ok;
+}
 /* spin until *p - need >= 0 (counters carry the picture epoch in their upper bits), bounded like wait_flag */
 __device__ __forceinline__ bool wait_progress(const unsigned *p, unsigned need, unsigned *err) {
 	const volatile unsigned *f = p;
