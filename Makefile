@@ -16,6 +16,15 @@ $(CSRC)/slice_dec.o: $(CSRC)/slice_dec.c $(wildcard $(CSRC)/*.h)
 	$(CC) $(CFLAGS) -c $< -o $@
 $(LIB): $(CSRC)/recon.o $(CSRC)/decoder.o $(CSRC)/slice_dec.o
 	$(NVCC) -shared -o $@ $^ -cudart shared
+# experiment builds of the runtime with other block geometries of the inter kernel (tools/gpu_variants.sh; not part of `all`)
+VARIANTS := w4 w8
+variants: $(foreach v,$(VARIANTS),edge264_b200/variants/$(v)/libedge264_b200.so)
+edge264_b200/variants/w8/libedge264_b200.so: VFLAGS := -DINTER_WARPS=8
+edge264_b200/variants/w4/libedge264_b200.so: VFLAGS := -DINTER_WARPS=4
+edge264_b200/variants/%/libedge264_b200.so: $(CSRC)/recon.cu $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(CSRC)/decoder.o $(CSRC)/slice_dec.o
+	mkdir -p $(dir $@)
+	$(NVCC) $(NVFLAGS) $(VFLAGS) -c $(CSRC)/recon.cu -o $(dir $@)recon.o
+	$(NVCC) -shared -o $@ $(dir $@)recon.o $(CSRC)/decoder.o $(CSRC)/slice_dec.o -cudart shared
 tools/gen264: tools/gen264.c $(wildcard $(CSRC)/*.h)
 	$(CC) $(CFLAGS) -O2 -o $@ $<
 tools/b200_decode: tools/e264_decode.c $(LIB)
@@ -26,4 +35,4 @@ oracle:
 	$(MAKE) -C oracle all
 clean:
 	rm -f $(CSRC)/*.o $(LIB) tools/gen264 tools/b200_decode tools/libe264bench.so
-.PHONY: all oracle clean
+.PHONY: all oracle clean variants

@@ -65,16 +65,15 @@ __device__ __forceinline__ void mc_load_chroma(const uint8_t *plane, int stride,
 	}
 }
 
-/* 8.4.2.3 on four packed samples; mode 1 default average (handled by the caller), 2 explicit weight on one prediction,
- * 3 weighted sum of both */
-__device__ __forceinline__ uint32_t wp_word(uint32_t a, uint32_t b, int mode, int w0, int w1, int o, int lw) {
+/* 8.4.2.3 on four packed samples in ONE form: ((a * wa + b * wb + rnd) >> sh) + o, clipped.  Explicit or implicit
+ * bi-prediction: wa = w0, wb = w1, rnd = 2^logWD, sh = logWD + 1; explicit weighting of a single prediction: wa = w, wb = 0,
+ * rnd = 2^(logWD-1) (0 when logWD = 0), sh = logWD (reference edge264_inter.c:1140-1180 keeps five variants). */
+__device__ __forceinline__ uint32_t wp_word(uint32_t a, uint32_t b, int wa, int wb, int rnd, int sh, int o) {
 	uint32_t r = 0;
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
 		const int pa = (a >> (8 * k)) & 255, pb = (b >> (8 * k)) & 255;
-		int v;
-		if (mode == 2) v = (lw >= 1 ? ((pa * w1 + (1 << (lw - 1))) >> lw) : pa * w1) + o;
-		else v = ((pa * w0 + pb * w1 + (1 << lw)) >> (lw + 1)) + o;
+		const int v = ((pa * wa + pb * wb + rnd) >> sh) + o;
 		r |= (uint32_t)min(max(v, 0), 255) << (8 * k);
 	}
 	return r;
@@ -98,8 +97,17 @@ __device__ __forceinline__ uint32_t add_res4(uint32_t p, const int16_t *res) {
  *      list-1 combination with the slice's weighting, residual, 128-bit row stores.
  * A thread-per-block version without the binning ran every class present in a macroblock one after the other (about
  * 2000 warp instructions per macroblock on random vectors, no faster than round 1's). */
-#define INTER_CHUNK 16
-#define INTER_WARPS 4
+/* Block geometry: INTER_WARPS warps take INTER_CHUNK macroblocks at a time (4 per warp).  The kernel's three phases are
+ * separated by block barriers, so all warps of a block execute the same part of the code: the bigger the block, the fewer
+ * different parts of the kernel (about 8 000 instructions, 130 KB) the SM's instruction cache has to hold at a time — and a
+ * 16-warp block at 128 registers per thread fills the SM's register file, so no block of another kernel shares the SM. */
+#ifndef INTER_WARPS
+#define INTER_WARPS 16      /* measured (profiles/r2_inter_geometry.txt), 32 streams: 4 warps 9.7 k, 8 warps 13.2 k, 16 warps 17.8 k frames/s */
+#endif
+#ifndef INTER_CHUNK
+#define INTER_CHUNK (4 * INTER_WARPS)
+#endif
+#define INTER_MINB0 (16 / INTER_WARPS)      /* blocks per SM at 128 registers per thread */
 struct __align__(16) InterSmem {
 	uint4 rec4[INTER_CHUNK][12];
 	uint32_t pred[INTER_CHUNK][2][16][8];          /* [macroblock][list][luma4x4BlkIdx]: four luma rows, 2x2 Cb, 2x2 Cr, (pad: 16-byte aligned entries) */
@@ -152,7 +160,8 @@ template <int MINB>
 __global__ void __launch_bounds__(INTER_WARPS * 32, MINB) e264_inter4_kernel(PicJob J) {
 	TraceScope trace_(J, 1);
 	reset_next_tickets(J);
-	__shared__ InterSmem sm;
+	extern __shared__ __align__(16) unsigned char inter_smem_raw[];
+	InterSmem &sm = *(InterSmem *)inter_smem_raw;
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	WarpSmem *ws = &sm.ws[w];
 	const int nmb = J.w_mbs * J.h_mbs;
@@ -239,35 +248,30 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, MINB) e264_inter4_kernel(Pic
 					if (r0 >= 0) { const uint4 a = *(const uint4 *)sm.pred[m][0][z]; const uint2 c2 = *(const uint2 *)(sm.pred[m][0][z] + 4); py[0] = a.x; py[1] = a.y; py[2] = a.z; py[3] = a.w; pcb = c2.x; pcr = c2.y; }
 					if (r1 >= 0) { const uint4 a = *(const uint4 *)sm.pred[m][1][z]; const uint2 c2 = *(const uint2 *)(sm.pred[m][1][z] + 4); qy[0] = a.x; qy[1] = a.y; qy[2] = a.z; qy[3] = a.w; qcb = c2.x; qcr = c2.y; }
 					const int wpm = sr->wp_mode;
-					if (r0 >= 0 && r1 >= 0) {
-						if (wpm == WP_DEFAULT) {
+					const bool bi = r0 >= 0 && r1 >= 0;
+					if (!bi && r0 < 0) {
 #pragma unroll
-							for (int k = 0; k < 4; k++) py[k] = mc_avg4(py[k], qy[k]);
-							pcb = mc_avg4(pcb, qcb); pcr = mc_avg4(pcr, qcr);
-						} else {
-							int w0[3], w1[3], o[3], lw[3];
+						for (int k = 0; k < 4; k++) py[k] = qy[k];
+						pcb = qcb; pcr = qcr;
+					}
+					if (bi && wpm == WP_DEFAULT) {
 #pragma unroll
-							for (int c = 0; c < 3; c++) {
-								if (wpm == WP_EXPLICIT) { w0[c] = sr->wp_w[0][r0 & 15][c]; w1[c] = sr->wp_w[1][r1 & 15][c]; o[c] = (sr->wp_o[0][r0 & 15][c] + sr->wp_o[1][r1 & 15][c] + 1) >> 1; lw[c] = c ? sr->chroma_log2_wd : sr->luma_log2_wd; }
-								else { w1[c] = sr->implicit_w1[r0 & 15][r1 & 15]; w0[c] = 64 - w1[c]; o[c] = 0; lw[c] = 5; }
-							}
+						for (int k = 0; k < 4; k++) py[k] = mc_avg4(py[k], qy[k]);
+						pcb = mc_avg4(pcb, qcb); pcr = mc_avg4(pcr, qcr);
+					} else if ((bi && wpm != WP_DEFAULT) || (wpm == WP_EXPLICIT && (r0 >= 0 || r1 >= 0))) {
+						/* one weighting body for every scheme: parameters per plane, then six words */
+						int wa[3], wb[3], o[3], sh[3], rnd[3];
+						const int ll = r0 >= 0 ? 0 : 1, ri = (ll ? r1 : r0) & 15;
 #pragma unroll
-							for (int k = 0; k < 4; k++) py[k] = wp_word(py[k], qy[k], 3, w0[0], w1[0], o[0], lw[0]);
-							pcb = wp_word(pcb, qcb, 3, w0[1], w1[1], o[1], lw[1]); pcr = wp_word(pcr, qcr, 3, w0[2], w1[2], o[2], lw[2]);
+						for (int c = 0; c < 3; c++) {
+							const int lw = c ? sr->chroma_log2_wd : sr->luma_log2_wd;
+							if (bi && wpm == WP_EXPLICIT) { wa[c] = sr->wp_w[0][r0 & 15][c]; wb[c] = sr->wp_w[1][r1 & 15][c]; o[c] = (sr->wp_o[0][r0 & 15][c] + sr->wp_o[1][r1 & 15][c] + 1) >> 1; sh[c] = lw + 1; rnd[c] = 1 << lw; }
+							else if (bi) { wb[c] = sr->implicit_w1[r0 & 15][r1 & 15]; wa[c] = 64 - wb[c]; o[c] = 0; sh[c] = 6; rnd[c] = 32; }
+							else { wa[c] = sr->wp_w[ll][ri][c]; wb[c] = 0; o[c] = sr->wp_o[ll][ri][c]; sh[c] = lw; rnd[c] = lw >= 1 ? 1 << (lw - 1) : 0; }
 						}
-					} else {
-						if (r0 < 0) {
 #pragma unroll
-							for (int k = 0; k < 4; k++) py[k] = qy[k];
-							pcb = qcb; pcr = qcr;
-						}
-						if (wpm == WP_EXPLICIT && (r0 >= 0 || r1 >= 0)) {
-							const int ll = r0 >= 0 ? 0 : 1, ri = (ll ? r1 : r0) & 15;
-#pragma unroll
-							for (int k = 0; k < 4; k++) py[k] = wp_word(py[k], 0, 2, 0, sr->wp_w[ll][ri][0], sr->wp_o[ll][ri][0], sr->luma_log2_wd);
-							pcb = wp_word(pcb, 0, 2, 0, sr->wp_w[ll][ri][1], sr->wp_o[ll][ri][1], sr->chroma_log2_wd);
-							pcr = wp_word(pcr, 0, 2, 0, sr->wp_w[ll][ri][2], sr->wp_o[ll][ri][2], sr->chroma_log2_wd);
-						}
+						for (int k = 0; k < 4; k++) py[k] = wp_word(py[k], qy[k], wa[0], wb[0], rnd[0], sh[0], o[0]);
+						pcb = wp_word(pcb, qcb, wa[1], wb[1], rnd[1], sh[1], o[1]); pcr = wp_word(pcr, qcr, wa[2], wb[2], rnd[2], sh[2], o[2]);
 					}
 					if (what == 2) {
 #pragma unroll

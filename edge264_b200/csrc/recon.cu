@@ -107,6 +107,11 @@ extern "C" int e264b_create(E264bDevice **out) {
 	c->launches = c->h2d_bytes = c->d2h_bytes = 0;
 	c->dev = dev;
 	CK(cudaFuncSetAttribute(e264_intra_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraRowsSmem)));
+	CK(cudaFuncSetAttribute(e264_inter4_kernel<INTER_MINB0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InterSmem)));
+#if INTER_WARPS == 4
+	CK(cudaFuncSetAttribute(e264_inter4_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InterSmem)));
+	CK(cudaFuncSetAttribute(e264_inter4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InterSmem)));
+#endif
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (int i = 0; i < E264_MAX_SLOTS; i++) CK(cudaEventCreateWithFlags(&c->rec_up[i], cudaEventDisableTiming | cudaEventBlockingSync));
 	for (int i = 0; i < NSTAGE; i++) CK(cudaEventCreateWithFlags(&c->st[i].done, cudaEventDisableTiming | cudaEventBlockingSync));
@@ -255,9 +260,12 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 	if (pd->n_intra < nmb && (mask & 1)) {
 		int ib = (nmb + INTER_CHUNK - 1) / INTER_CHUNK;
 		if (ib > cap) ib = cap;
-		if (minb >= 8) e264_inter4_kernel<8><<<ib, INTER_WARPS * 32, 0, c->stream>>>(J);
-		else if (minb >= 6) e264_inter4_kernel<6><<<ib, INTER_WARPS * 32, 0, c->stream>>>(J);
-		else e264_inter4_kernel<4><<<ib, INTER_WARPS * 32, 0, c->stream>>>(J);
+#if INTER_WARPS == 4
+		if (minb >= 8) e264_inter4_kernel<8><<<ib, INTER_WARPS * 32, sizeof(InterSmem), c->stream>>>(J);
+		else if (minb >= 6) e264_inter4_kernel<6><<<ib, INTER_WARPS * 32, sizeof(InterSmem), c->stream>>>(J);
+		else
+#endif
+		e264_inter4_kernel<INTER_MINB0><<<ib, INTER_WARPS * 32, sizeof(InterSmem), c->stream>>>(J);
 		c->launches++;
 	}
 	if (pd->n_intra > 0 && (mask & 2)) {
@@ -455,7 +463,7 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264
 		 * i - inflight has finished its own): beyond ~16 the kernels of more pictures only take each other's issue slots
 		 * and registers — measured 10.5 k frames/s with 16 streams in flight against 8.0 k with 32 */
 		const char *fe = getenv("E264B_REPLAY_INFLIGHT");
-		const int inflight = fe && atoi(fe) > 0 ? atoi(fe) : 16;
+		const int inflight = fe && atoi(fe) > 0 ? atoi(fe) : 12;
 		std::vector<cudaEvent_t> done(n);
 		for (int i = 0; i < n; i++) CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
 		for (int r = 0; r < reps; r++) for (int i = 0; i < n; i++) {

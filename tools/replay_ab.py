@@ -7,7 +7,7 @@ S = int(os.environ.get("S", "16")); steps = int(os.environ.get("STEPS", "3"))
 os.environ["E264B_KEEP"] = "1"
 bufs = bench.generate_streams(bench.CONFIGS["1080p"], [2000 + i for i in range(S)], 60, "/tmp/e264_bench")
 lib = bench.BenchLib(os.path.join(bench.ROOT, "tools", "libe264bench.so"))
-core = ctypes.CDLL(os.path.join(bench.ROOT, "edge264_b200", "libedge264_b200.so"))
+core = ctypes.CDLL(os.path.join(os.environ.get("E264_LIB_DIR", os.path.join(bench.ROOT, "edge264_b200")), "libedge264_b200.so"))   # variants: set LD_LIBRARY_PATH to the same directory
 core.e264b_of_decoder.restype = ctypes.c_void_p; core.e264b_of_decoder.argtypes = [ctypes.c_void_p]
 core.e264b_replay.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(bench.ReplayStats)]
 secs, frames, sums, decs = lib.run(bufs, min(S, 16), keep=True)
