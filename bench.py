@@ -98,24 +98,44 @@ KERNELS = ["(unused)", "e264_inter4_kernel", "e264_intra_kernel / e264_intra_row
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and clock-event (throttle) reasons during the timed regions (B200_PROFILING.md recipe).  NVML through
+    nvidia_ml_py when it is importable (a query costs microseconds, so the short device-timed replay gets tens of samples and
+    the CPU-bound e2e phase loses nothing to the sampler); otherwise one nvidia-smi process per second."""
     def __init__(self, gpu):
-        super().__init__(daemon=True); self.gpu = gpu; self.rows = []; self.stop = False
-    def run(self):
+        super().__init__(daemon=True); self.gpu = gpu; self.rows = []; self.stop = False; self.period = 0.5; self.nvml = None; self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit(); self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu); self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM); mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+            try: r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception: r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            act = lambda bit: "Active" if r & bit else "Not Active"
+            return [str(sm), str(mx), act(0x8), act(0x40), act(0x20), act(0x4)]      # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+        return [x.strip() for x in o.split(",")] if o else None
+    def run(self):
         while not self.stop:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
-                if o: self.rows.append([x.strip() for x in o.split(",")])
+                r = self.sample()
+                if r: self.rows.append(r + [self.phase])
             except Exception:
                 pass
-            time.sleep(1.0)   # each nvidia-smi call costs CPU that the parser threads need under the cgroup quota
+            time.sleep(self.period if self.nvml is not None else max(self.period, 1.0))
+    phase = "e2e"
     def summary(self):
         if not self.rows: return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        rows = [r for r in self.rows if r[-1] == "replay"] or self.rows      # the device-timed region when it was sampled
+        sm = sorted(int(r[0]) for r in rows if r[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 3 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons,
+                "samples": len(self.rows), "samples_in_replay": sum(1 for r in self.rows if r[-1] == "replay"), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def usable_cpus():
@@ -273,6 +293,7 @@ def main():
     for _ in range(args.warmup):
         core.e264b_replay(devs, S, 1, launch_threads, ctypes.byref(st))
     barrier()
+    sampler.phase = "replay"; sampler.period = 0.02
     rc = core.e264b_replay(devs, S, args.steps, launch_threads, ctypes.byref(st))
     barrier()
     if rc != 0 or any(core.e264b_error_flag(devs[i]) for i in range(S)):

@@ -217,6 +217,8 @@ struct Edge264Decoder {
 	HostBuf hb[E264_MAX_HOSTBUFS];
 	int outq[E264_MAX_HOSTBUFS]; int outq_n;
 	int pending_release;               /* host buffer handed out without borrow, released at next decode_NAL */
+	int sync_output;                   /* E264_SYNC_OUTPUT=1: get_frame always waits for the device (the behaviour before round 2's last step; A/B switch) */
+	int block_output;                  /* the last decode_NAL asked the application to fetch frames (ENOBUFS, end of stream): get_frame waits for the device */
 	/* scratch */
 	uint8_t *rbsp; size_t rbsp_cap;
 	SliceCtx sc;
@@ -240,6 +242,8 @@ typedef struct E264Backend {
 	int  (*wait)(void *ctx, uint64_t ticket);
 	/* fill a slot with a constant (non-existing frames of frame_num gaps) */
 	int  (*fill_slot)(void *ctx, int slot, int y, int c);
+	/* non-blocking form of wait: 0 = the picture is complete, EAGAIN = not yet, < 0 = device error */
+	int  (*poll)(void *ctx, uint64_t ticket);
 } E264Backend;
 const E264Backend *e264_default_backend(void);
 

@@ -1063,6 +1063,7 @@ Edge264Decoder *edge264_alloc(int n_threads, Edge264LogCb log_cb, void *log_arg,
 	d->n_builds = 1;
 	/* n_threads as in the reference (edge264.c:223-257): 0 = parse inside edge264_decode_NAL, < 0 = one worker per CPU up
 	 * to the limit, > 0 = that many workers (here they parse slice data ahead; reconstruction is the device's) */
+	{ const char *e = getenv("E264_SYNC_OUTPUT"); d->sync_output = e && atoi(e) != 0; d->block_output = d->sync_output; }
 	if (n_threads < 0) { long n = sysconf(_SC_NPROCESSORS_ONLN); n_threads = n < 1 ? 1 : (int)n; }
 	if (n_threads > E264_MAX_THREADS) n_threads = E264_MAX_THREADS;
 	if (n_threads > 0) {
@@ -1099,8 +1100,14 @@ void edge264_free(Edge264Decoder **pd) {
 	free(d->rbsp); free(d);
 }
 
+static int decode_NAL_inner(Edge264Decoder *d, const uint8_t *buf, const uint8_t *end, Edge264UnrefCb unref_cb, void *unref_arg);
 int edge264_decode_NAL(Edge264Decoder *d, const uint8_t *buf, const uint8_t *end, Edge264UnrefCb unref_cb, void *unref_arg) {
 	if (!d || !buf) return EINVAL;
+	const int r = decode_NAL_inner(d, buf, end, unref_cb, unref_arg);
+	d->block_output = r == ENOBUFS || r == ENODATA || buf >= end || d->sync_output;
+	return r;
+}
+static int decode_NAL_inner(Edge264Decoder *d, const uint8_t *buf, const uint8_t *end, Edge264UnrefCb unref_cb, void *unref_arg) {
 	if (d->pending_release >= 0) { d->hb[d->pending_release].state = 0; d->pending_release = -1; }
 	if (buf >= end) {
 		int r = bump_all(d);
@@ -1160,6 +1167,14 @@ int edge264_get_frame(Edge264Decoder *d, Edge264Frame *out, int borrow) {
 	int hbuf = d->outq[0];
 	HostBuf *hb = &d->hb[hbuf];
 	if (!__atomic_load_n(&hb->submitted, __ATOMIC_ACQUIRE)) return ENOMSG;   /* queued at insertion but still being parsed */
+	/* Like the reference in threaded mode (edge264.c:373: a frame whose last macroblock is not deblocked yet answers
+	 * ENOMSG), a picture still on the device is "not available yet" — unless the last decode_NAL told the application
+	 * to fetch frames (ENOBUFS, end of stream): then the call waits, so that no application loop ever has to poll. */
+	if (!d->block_output) {
+		int pr = d->be->poll(d->be_ctx, hb->ticket);
+		if (pr == EAGAIN) return ENOMSG;
+		if (pr) return EIO;
+	}
 	{ PROF_BEGIN; int wr = d->be->wait(d->be_ctx, hb->ticket); PROF_END(3); if (wr) return EIO; }
 	memmove(d->outq, d->outq + 1, (size_t)(--d->outq_n) * sizeof(int));
 	*out = d->out_fmt;

@@ -348,6 +348,15 @@ extern "C" int e264b_wait(E264bDevice *c, uint64_t ticket) {
 	return 0;
 }
 
+/* non-blocking: 0 = complete, EAGAIN = the picture (or a later one that took its ring slot) is still on the device */
+extern "C" int e264b_poll(E264bDevice *c, uint64_t ticket) {
+	if (ticket == 0) return 0;
+	cudaError_t q = cudaEventQuery(c->tick_ev[ticket % NTICK]);
+	if (q == cudaErrorNotReady) return EAGAIN;
+	if (q != cudaSuccess) { fprintf(stderr, "edge264_b200: cudaEventQuery: %s\n", cudaGetErrorString(q)); return -1; }
+	return c->h_err[ticket % NTICK] ? -1 : 0;
+}
+
 extern "C" int e264b_fill_slot(E264bDevice *c, int slot, int y, int cc) {
 	CK(cudaSetDevice(c->dev));
 	uint8_t *f = c->d_frames + (size_t)slot * c->g.frame_bytes;
@@ -460,10 +469,11 @@ extern "C" int e264b_replay(E264bDevice **cs, int n, int reps, int threads, E264
 	std::vector<int> rc(threads, 0);
 	if (use_graph) {
 		/* at most `inflight` streams have pictures on the GPU at a time (stream i starts a repetition when stream
-		 * i - inflight has finished its own): beyond ~16 the kernels of more pictures only take each other's issue slots
-		 * and registers — measured 10.5 k frames/s with 16 streams in flight against 8.0 k with 32 */
+		 * i - inflight has finished its own).  With 4-warp inter blocks more than 12-16 streams in flight only took each
+		 * other's instruction cache; with the 16-warp blocks the curve is flat from 16 on (16: 17.9 k, 24: 17.8 k, 32: 18.9 k
+		 * frames/s, profiles/r2_inflight.txt), so the default is the bench's batch */
 		const char *fe = getenv("E264B_REPLAY_INFLIGHT");
-		const int inflight = fe && atoi(fe) > 0 ? atoi(fe) : 12;
+		const int inflight = fe && atoi(fe) > 0 ? atoi(fe) : 32;
 		std::vector<cudaEvent_t> done(n);
 		for (int i = 0; i < n; i++) CK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
 		for (int r = 0; r < reps; r++) for (int i = 0; i < n; i++) {
@@ -603,6 +613,7 @@ static int be_acquire(void *ctx, int slot, E264Staging *out) { return e264b_acqu
 static int be_submit(void *ctx, const E264PicDesc *pd, uint8_t *out, uint64_t *t) { return e264b_submit((E264bDevice *)ctx, pd, out, t); }
 static int be_wait(void *ctx, uint64_t t) { return e264b_wait((E264bDevice *)ctx, t); }
 static int be_fill(void *ctx, int slot, int y, int c) { return e264b_fill_slot((E264bDevice *)ctx, slot, y, c); }
-static const E264Backend cuda_backend = {"cuda-sm_100a", be_create, be_destroy, be_configure, be_host_alloc, be_host_free, be_acquire, be_submit, be_wait, be_fill};
+static int be_poll(void *ctx, uint64_t t) { return e264b_poll((E264bDevice *)ctx, t); }
+static const E264Backend cuda_backend = {"cuda-sm_100a", be_create, be_destroy, be_configure, be_host_alloc, be_host_free, be_acquire, be_submit, be_wait, be_fill, be_poll};
 extern "C" const E264Backend *e264_default_backend(void) { return &cuda_backend; }
 extern "C" E264bDevice *e264b_of_decoder(Edge264Decoder *d) { return d ? (E264bDevice *)d->be_ctx : NULL; }

@@ -284,23 +284,26 @@ __device__ __noinline__ void residual_stage(WarpSmem *ws, const E264MbRec *r, co
 			for (int j = 0; j < 8; j++) ws->res[(y0 + j) * 16 + x] = (short)(a[j] >> 6);
 		}
 		__syncwarp();
-	} else if (lane < 16) {
-		int b = lane;
-		bool on = (coded >> b) & 1, dcov = i16 && (coded & CODED_Y_DC);
-		if (on || dcov) {
-			int idx = __popc(coded & ((1u << b) - 1));
-			int bx = blk_x(b), by = blk_y(b);
-			idct4x4(cf_luma + idx * 16, on, sr->scaling4x4[inter * 3], qpy, i16, ws->dc[by * 4 + bx], ws->res + by * 4 * 16 + bx * 4, 16);
-		}
 	}
-	/* --- chroma AC (+DC) --- */
-	if (lane >= 16 && lane < 24) {
-		int j = lane - 16, pl = j >> 2, i = j & 3;
-		bool on = (coded >> (16 + j)) & 1;
-		if (on || any_cdc) {
-			int idx = __popc((coded >> 16) & ((1u << j) - 1) & 0xff);
-			idct4x4(cf + idx * 16, on, sr->scaling4x4[1 + pl + inter * 3], r->qp[1 + pl], true, ws->dc[16 + pl * 4 + i], ws->res + 256 + pl * 64 + (i >> 1) * 4 * 8 + (i & 1) * 4, 8);
+	/* --- 4x4 blocks: luma on lanes 0..15 (unless the macroblock uses the 8x8 transform) and chroma AC (+DC) on lanes
+	 * 16..23 go through ONE call of the transform --- */
+	{
+		bool act = false, on = false, dcov = false;
+		const int16_t *src = cf; const uint8_t *scal = sr->scaling4x4[0]; int qp = qpy, dc = 0, stride = 16; int16_t *dst = ws->res;
+		if (lane < 16) {
+			if (!(r->flags & MBF_T8x8)) {
+				const int b = lane, bx = blk_x(b), by = blk_y(b);
+				on = (coded >> b) & 1; dcov = i16 && (coded & CODED_Y_DC); act = on || dcov;
+				src = cf_luma + __popc(coded & ((1u << b) - 1)) * 16; scal = sr->scaling4x4[inter * 3]; dcov = i16; dc = ws->dc[by * 4 + bx];
+				dst = ws->res + by * 4 * 16 + bx * 4;
+			}
+		} else if (lane < 24) {
+			const int j = lane - 16, pl = j >> 2, i = j & 3;
+			on = (coded >> (16 + j)) & 1; act = on || any_cdc; dcov = true;
+			src = cf + __popc((coded >> 16) & ((1u << j) - 1) & 0xff) * 16; scal = sr->scaling4x4[1 + pl + inter * 3]; qp = r->qp[1 + pl]; dc = ws->dc[16 + pl * 4 + i];
+			dst = ws->res + 256 + pl * 64 + (i >> 1) * 4 * 8 + (i & 1) * 4; stride = 8;
 		}
+		if (act) idct4x4(src, on, scal, qp, dcov, dc, dst, stride);
 	}
 	__syncwarp();
 }

@@ -34,6 +34,7 @@ void  e264b_host_free(E264bDevice *dev, void *p);
 int   e264b_acquire_staging(E264bDevice *dev, int slot, struct E264Staging *out);   /* pinned areas the parser fills; out->handle goes back in E264PicDesc.staging */
 int   e264b_submit(E264bDevice *dev, const struct E264PicDesc *pic, uint8_t *host_out, uint64_t *ticket);
 int   e264b_wait(E264bDevice *dev, uint64_t ticket);
+int   e264b_poll(E264bDevice *dev, uint64_t ticket);          /* 0 complete, EAGAIN still on the device, < 0 device error */
 int   e264b_fill_slot(E264bDevice *dev, int slot, int luma, int chroma);
 int   e264b_error_flag(E264bDevice *dev);            /* 1 if a dependency wait timed out on the device */
 void  e264b_stats(E264bDevice *dev, uint64_t *kernel_launches, uint64_t *h2d_bytes, uint64_t *d2h_bytes);

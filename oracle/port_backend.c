@@ -89,5 +89,6 @@ static int port_fill(void *ctx, int slot, int y, int cc) {
 	memset(f, y, (size_t)c->g.plane_y); memset(f + c->g.plane_y, cc, (size_t)c->g.frame_bytes - c->g.plane_y);
 	return 0;
 }
-static const E264Backend port_backend = {"oracle-port", port_create, port_destroy, port_configure, port_host_alloc, port_host_free, port_acquire, port_submit, port_wait, port_fill};
+static int port_poll(void *ctx, uint64_t ticket) { (void)ctx; (void)ticket; return 0; }
+static const E264Backend port_backend = {"oracle-port", port_create, port_destroy, port_configure, port_host_alloc, port_host_free, port_acquire, port_submit, port_wait, port_fill, port_poll};
 const E264Backend *e264_default_backend(void) { return &port_backend; }
