@@ -102,7 +102,7 @@ class ClockSampler(threading.Thread):
     nvidia_ml_py when it is importable (a query costs microseconds, so the short device-timed replay gets tens of samples and
     the CPU-bound e2e phase loses nothing to the sampler); otherwise one nvidia-smi process per second."""
     def __init__(self, gpu):
-        super().__init__(daemon=True); self.gpu = gpu; self.rows = []; self.stop = False; self.period = 0.5; self.nvml = None; self.h = None
+        super().__init__(daemon=True); self.gpu = gpu; self.rows = []; self.stop = False; self.period = 0.5; self.nvml = None; self.h = None; self.wake = threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit(); self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu); self.nvml = pynvml
@@ -126,8 +126,10 @@ class ClockSampler(threading.Thread):
                 if r: self.rows.append(r + [self.phase])
             except Exception:
                 pass
-            time.sleep(self.period if self.nvml is not None else max(self.period, 1.0))
+            self.wake.wait(self.period if self.nvml is not None else max(self.period, 1.0)); self.wake.clear()
     phase = "e2e"
+    def set_phase(self, phase, period):
+        self.phase = phase; self.period = period; self.wake.set()
     def summary(self):
         if not self.rows: return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
         rows = [r for r in self.rows if r[-1] == "replay"] or self.rows      # the device-timed region when it was sampled
@@ -293,13 +295,13 @@ def main():
     for _ in range(args.warmup):
         core.e264b_replay(devs, S, 1, launch_threads, ctypes.byref(st))
     barrier()
-    sampler.phase = "replay"; sampler.period = 0.02
+    sampler.set_phase("replay", 0.005)
     rc = core.e264b_replay(devs, S, args.steps, launch_threads, ctypes.byref(st))
     barrier()
     if rc != 0 or any(core.e264b_error_flag(devs[i]) for i in range(S)):
         raise SystemExit("bench.py: replay failed (CUDA error or dependency timeout)")
     step_ms = maxreduce(st.ms_total) / args.steps
-    sampler.stop = True; sampler.join(timeout=2)
+    sampler.stop = True; sampler.wake.set(); sampler.join(timeout=2)
     fps = world * frames_per_step / (step_ms / 1000)
 
     # ---- roofline from the timed pass: per-launch device spans, algorithmic bytes of SURVEY.md section 8(d) ----

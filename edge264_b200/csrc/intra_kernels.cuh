@@ -20,12 +20,14 @@
 #define IR_ROWS 8
 #define IR_RING 16
 #define IR_CHUNK 8
+#define IR_SLOTS 4      /* macroblocks the transform warp may be ahead of the prediction warp (residual / tile slots, coefficient buffers) */
+#define IR_RECS 8       /* record ring of a row */
 struct __align__(16) IntraRowsSmem {
-	WarpSmem ws[IR_ROWS][2];                    /* macroblocks x and x+1 of every row: residual from the row's transform warp, tile of its prediction warp */
-	uint4 recs[IR_ROWS][4][12];                 /* records of macroblocks x-1 .. x+2 of every row */
+	WarpSmem ws[IR_ROWS][IR_SLOTS];                    /* macroblocks x and x+1 of every row: residual from the row's transform warp, tile of its prediction warp */
+	uint4 recs[IR_ROWS][IR_RECS][12];           /* records of macroblocks x-4 .. x+3 of every row */
 	uint32_t ring[IR_ROWS][IR_RING][8];         /* bottom sample row of a finished macroblock: luma (4 words), Cb (2), Cr (2) */
-	int16_t coef[IR_ROWS][2][RES_COEF_MAX];     /* coefficient runs of macroblocks x, x+1 of every row (cp.async.bulk) */
-	unsigned long long bars[IR_ROWS][2];
+	int16_t coef[IR_ROWS][IR_SLOTS][RES_COEF_MAX];   /* coefficient runs of macroblocks x .. x+3 of every row (cp.async.bulk) */
+	unsigned long long bars[IR_ROWS][IR_SLOTS];
 	uint4 drecs[IR_ROWS][3][12];                /* deblocking digests of intra-only pictures: current, left and top record */
 	E264DbkMb ddg[IR_ROWS];
 	int done[IR_ROWS];                          /* macroblocks a row has put into its ring */
@@ -35,10 +37,12 @@ struct __align__(16) IntraRowsSmem {
 	int band;
 };
 
-/* The row's TRANSFORM warp: records two ahead, coefficient runs one ahead (cp.async.bulk), dequantisation and inverse
- * transforms into the residual of slot x & 1, at most two macroblocks ahead of the prediction warp.  In a picture without
- * inter macroblocks it also derives the row's deblocking digests (no inter kernel runs that would). */
-__device__ __forceinline__ void intra_row_transform(const PicJob &J, IntraRowsSmem &sm, int band, int w, int lane, unsigned (&parity)[2]) {
+/* The row's TRANSFORM warp: records four ahead (through a register, so the warp never waits for the load it has just
+ * issued), coefficient runs three ahead (cp.async.bulk; DRAM latency is longer than one macroblock of this warp's work),
+ * dequantisation and inverse transforms into the residual of slot x % IR_SLOTS, at most IR_SLOTS - 1 macroblocks ahead of
+ * the prediction warp.  In a picture without inter macroblocks it also derives the row's deblocking digests (no inter
+ * kernel runs that would). */
+__device__ __forceinline__ void intra_row_transform(const PicJob &J, IntraRowsSmem &sm, int band, int w, int lane, unsigned &parbits) {
 	const int W = J.w_mbs, H = J.h_mbs, nmb = W * H;
 	const int mby = band * IR_ROWS + w;
 	if (mby >= H) return;
@@ -46,40 +50,48 @@ __device__ __forceinline__ void intra_row_transform(const PicJob &J, IntraRowsSm
 	const volatile unsigned *errp = J.err;
 	volatile int *used = sm.used + w, *ready = sm.ready + w;
 	const bool digests = J.dbk != nullptr && J.n_intra == nmb;
-	if (lane < 12) sm.recs[w][0][lane] = __ldg((const uint4 *)rowrecs + lane);
-	if (W > 1 && lane >= 12 && lane < 24) sm.recs[w][1][lane - 12] = __ldg((const uint4 *)(rowrecs + 1) + lane - 12);
+	constexpr int AHEAD = IR_SLOTS - 1;          /* coefficient runs in flight ahead of the macroblock being transformed */
+	/* prologue: records 0 .. AHEAD in shared memory, record AHEAD + 1 in the register */
+	for (int x = 0; x <= AHEAD && x < W; x++) if (lane < 12) sm.recs[w][x % IR_RECS][lane] = __ldg((const uint4 *)(rowrecs + x) + lane);
+	uint4 recreg = make_uint4(0, 0, 0, 0);
+	if (AHEAD + 1 < W && lane < 12) recreg = __ldg((const uint4 *)(rowrecs + AHEAD + 1) + lane);
 	__syncwarp();
-	auto coef_issue = [&](int x) -> bool {       /* true: a copy is in flight into buffer x & 1 */
-		const E264MbRec *rr = (const E264MbRec *)sm.recs[w][x & 3];
+	auto coef_issue = [&](int x) -> bool {       /* true: a copy is in flight into buffer x % IR_SLOTS */
+		const E264MbRec *rr = (const E264MbRec *)sm.recs[w][x % IR_RECS];
 		if (rr->kind == MBK_INTER || rr->kind == MBK_IPCM || rr->coded == 0) return false;
-		if (lane == 0) tma_bulk_g2s(sm.coef[w][x & 1], J.coefs + rr->coef_off, (unsigned)rec_coef_count(rr) * 2u, &sm.bars[w][x & 1]);
+		if (lane == 0) tma_bulk_g2s(sm.coef[w][x % IR_SLOTS], J.coefs + rr->coef_off, (unsigned)rec_coef_count(rr) * 2u, &sm.bars[w][x % IR_SLOTS]);
 		return true;
 	};
-	bool pending = coef_issue(0);
+	unsigned pending = 0;                        /* bit x % IR_SLOTS: macroblock x has a copy in flight */
+	for (int x = 0; x < AHEAD && x < W; x++) if (coef_issue(x)) pending |= 1u << (x % IR_SLOTS);
 #pragma unroll 1
 	for (int mbx = 0; mbx < W; mbx++) {
-		/* slot mbx & 1 and record slot (mbx + 2) & 3 are free once the prediction warp is through with macroblock mbx - 2 */
+		const int sl = mbx % IR_SLOTS;
+		/* residual slot sl is free once the prediction warp is through with macroblock mbx - IR_SLOTS; the record slot written
+		 * below belonged to macroblock mbx + AHEAD + 1 - IR_RECS, older still */
 		if (lane == 0) {
 			unsigned spins = 0; bool bad = false;
-			while (*used < mbx - 1 && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
+			while (*used < mbx - IR_SLOTS + 1 && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
 			if (bad) atomicExch(J.err, 1u);
 			__threadfence_block();
 		}
 		__syncwarp();
-		const E264MbRec *r = (const E264MbRec *)sm.recs[w][mbx & 3];
-		WarpSmem *ws = &sm.ws[w][mbx & 1];
-		if (mbx + 2 < W && lane < 12) sm.recs[w][(mbx + 2) & 3][lane] = __ldg((const uint4 *)(rowrecs + mbx + 2) + lane);
-		const bool pending_next = mbx + 1 < W ? coef_issue(mbx + 1) : false;
+		const E264MbRec *r = (const E264MbRec *)sm.recs[w][mbx % IR_RECS];
+		WarpSmem *ws = &sm.ws[w][sl];
+		/* the record fetched one iteration ago goes to shared memory, the next one is requested */
+		if (mbx + AHEAD + 1 < W && lane < 12) sm.recs[w][(mbx + AHEAD + 1) % IR_RECS][lane] = recreg;
+		if (mbx + AHEAD + 2 < W && lane < 12) recreg = __ldg((const uint4 *)(rowrecs + mbx + AHEAD + 2) + lane);
+		__syncwarp();
+		if (mbx + AHEAD < W) { const int nb = (mbx + AHEAD) % IR_SLOTS; pending &= ~(1u << nb); if (coef_issue(mbx + AHEAD)) pending |= 1u << nb; }
 		const int kind = r->kind;
-		if (pending) {
-			if (!mbar_wait(&sm.bars[w][mbx & 1], parity[mbx & 1])) { if (lane == 0) atomicExch(J.err, 3u); }
-			parity[mbx & 1] ^= 1;
-			residual_stage(ws, r, J.slices + r->slice_idx, sm.coef[w][mbx & 1], lane);
+		if ((pending >> sl) & 1) {
+			if (!mbar_wait(&sm.bars[w][sl], (parbits >> sl) & 1)) { if (lane == 0) atomicExch(J.err, 3u); }
+			parbits ^= 1u << sl;
+			residual_stage(ws, r, J.slices + r->slice_idx, sm.coef[w][sl], lane);
 		} else if (kind != MBK_INTER && kind != MBK_IPCM) {
 			((uint4 *)ws->res)[lane] = make_uint4(0, 0, 0, 0);
 			if (lane < 16) ((uint4 *)ws->res)[32 + lane] = make_uint4(0, 0, 0, 0);
 		}
-		pending = pending_next;
 		__syncwarp();
 		if (lane == 0) { __threadfence_block(); *ready = mbx + 1; }
 		if (digests) dbk_digest_mb(J, sm.drecs[w], &sm.ddg[w], mby * W + mbx, lane);
@@ -131,9 +143,9 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 			*taken_me = mbx;
 		}
 		__syncwarp();
-		const E264MbRec *r = (const E264MbRec *)sm.recs[w][mbx & 3];
+		const E264MbRec *r = (const E264MbRec *)sm.recs[w][mbx % IR_RECS];
 		const int kind = r->kind;
-		WarpSmem *ws = &sm.ws[w][mbx & 1];
+		WarpSmem *ws = &sm.ws[w][mbx % IR_SLOTS];
 		/* ---- the row above into the tile ---- */
 		if (from_ring) {
 			if (lane < 4) *(uint32_t *)&YT(4 * lane, -1) = ring_in[mbx % IR_RING][lane];
@@ -180,7 +192,7 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 		}
 		/* right-most column becomes the next macroblock's left neighbour (the other slot's tile) */
 		{
-			WarpSmem *wn = &sm.ws[w][(mbx + 1) & 1];
+			WarpSmem *wn = &sm.ws[w][(mbx + 1) % IR_SLOTS];
 			if (lane < 16) wn->ytile[(lane + 1) * YT_STRIDE + 15] = YT(15, lane);
 			else if (lane < 24) wn->ctile[0][(lane - 16 + 1) * CT_STRIDE + 7] = CT(0, 7, lane - 16);
 			if (lane < 8) wn->ctile[1][(lane + 1) * CT_STRIDE + 7] = CT(1, 7, lane);
@@ -204,9 +216,9 @@ __global__ void __launch_bounds__(IR_ROWS * 64) e264_intra_rows_kernel(PicJob J)
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, w = wid & (IR_ROWS - 1);
 	const bool transform = wid >= IR_ROWS;
 	const int bands = (J.h_mbs + IR_ROWS - 1) / IR_ROWS;
-	unsigned parity[2] = {0, 0};
+	unsigned parbits = 0;
 	if (transform && lane == 0) {
-		mbar_init(&sm.bars[w][0], 1); mbar_init(&sm.bars[w][1], 1);
+		for (int k = 0; k < IR_SLOTS; k++) mbar_init(&sm.bars[w][k], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
@@ -218,7 +230,7 @@ __global__ void __launch_bounds__(IR_ROWS * 64) e264_intra_rows_kernel(PicJob J)
 		__syncthreads();
 		const int band = sm.band;
 		if (band >= bands) break;
-		if (transform) intra_row_transform(J, sm, band, w, lane, parity);
+		if (transform) intra_row_transform(J, sm, band, w, lane, parbits);
 		else intra_row_walk(J, sm, band, w, lane);
 	}
 }

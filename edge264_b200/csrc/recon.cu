@@ -336,6 +336,7 @@ extern "C" int e264b_submit(E264bDevice *c, const E264PicDesc *pd, uint8_t *host
 	return 0;
 }
 
+static_assert(sizeof(IntraRowsSmem) <= 227 * 1024 && sizeof(InterSmem) <= 227 * 1024, "dynamic shared memory of a block");
 extern "C" int e264b_wait(E264bDevice *c, uint64_t ticket) {
 	if (ticket == 0) return 0;
 	/* the ring slot holds this ticket or a later one of the same stream: either way it implies completion */
