@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, MINB) e264_inter4_kernel(Pic
 			return 2;
 		};
 		int what = coef_issue(w, 0);
+#pragma unroll 1
 		for (int i0 = 0; i0 < cnt * 32; i0 += INTER_WARPS * 32) {
 			const int item = i0 + tid, m = item >> 5, l = (item >> 4) & 1, z = item & 15;
 			int cls = -1;
@@ -198,19 +199,15 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, MINB) e264_inter4_kernel(Pic
 				const E264MbRec *r = (const E264MbRec *)sm.rec4[m];
 				if (r->kind == MBK_INTER && r->ref_idx[l][z >> 2] >= 0) cls = mc_class(r->mv[l][z][0] & 3, r->mv[l][z][1] & 3);
 			}
-#pragma unroll
-			for (int c = 0; c < 6; c++) {
-				const unsigned mask = __ballot_sync(0xffffffffu, cls == c);
-				if (mask) {
-					int base = 0;
-					if (lane == 0) base = atomicAdd(&sm.qn[c], __popc(mask));
-					base = __shfl_sync(0xffffffffu, base, 0);
-					if (cls == c) sm.queue[c][base + __popc(mask & ((1u << lane) - 1))] = (uint16_t)item;
-				}
-			}
+			/* queue position: the lanes of one class find each other with one match instruction, their first lane reserves the
+			 * run in the class queue */
+			const unsigned peers = __match_any_sync(0xffffffffu, cls);
+			const int leader = __ffs(peers) - 1;
+			int base = 0;
+			if (cls >= 0 && lane == leader) base = atomicAdd(&sm.qn[cls], __popc(peers));
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (cls >= 0) sm.queue[cls][base + __popc(peers & ((1u << lane) - 1))] = (uint16_t)item;
 		}
-		/* the chunk's deblocking digests (every macroblock, intra ones too): record-only work, a warp per macroblock */
-		if (J.dbk != nullptr) for (int m = w; m < cnt; m += INTER_WARPS) dbk_digest_mb(J, sm.drecs[w], &sm.ddg[w], mb0 + m, lane);
 		__syncthreads();
 		/* ---- 2. one class at a time, 32 items per warp pass: the groups of all classes form one list ---- */
 		{
@@ -230,8 +227,12 @@ __global__ void __launch_bounds__(INTER_WARPS * 32, MINB) e264_inter4_kernel(Pic
 		/* ---- 3. a warp per macroblock: inverse transform, weighting, residual, store ---- */
 		int b = 0;
 		bool failed = false;
+#pragma unroll 1
 		for (int m = w; m < cnt; m += INTER_WARPS, b ^= 1) {
 			const int what2 = coef_issue(m + INTER_WARPS, b ^ 1);
+			/* the macroblock's deblocking digest (every macroblock, intra ones too): record-only work whose loads of the
+			 * neighbour records are in flight together with the coefficient run requested above */
+			if (J.dbk != nullptr) dbk_digest_mb(J, sm.drecs[w], &sm.ddg[w], mb0 + m, lane);
 			if (what) {
 				const int mb = mb0 + m, mbx = mb % J.w_mbs, mby = mb / J.w_mbs;
 				const E264MbRec *r = (const E264MbRec *)sm.rec4[m];
