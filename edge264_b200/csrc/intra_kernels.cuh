@@ -63,6 +63,7 @@ __device__ __forceinline__ void intra_row_transform(const PicJob &J, IntraRowsSm
 		return true;
 	};
 	unsigned pending = 0;                        /* bit x % IR_SLOTS: macroblock x has a copy in flight */
+	RT_DECL
 	for (int x = 0; x < AHEAD && x < W; x++) if (coef_issue(x)) pending |= 1u << (x % IR_SLOTS);
 #pragma unroll 1
 	for (int mbx = 0; mbx < W; mbx++) {
@@ -76,6 +77,7 @@ __device__ __forceinline__ void intra_row_transform(const PicJob &J, IntraRowsSm
 			__threadfence_block();
 		}
 		__syncwarp();
+		RT_MARK(0)      /* waiting for a free slot */
 		const E264MbRec *r = (const E264MbRec *)sm.recs[w][mbx % IR_RECS];
 		WarpSmem *ws = &sm.ws[w][sl];
 		/* the record fetched one iteration ago goes to shared memory, the next one is requested */
@@ -84,9 +86,11 @@ __device__ __forceinline__ void intra_row_transform(const PicJob &J, IntraRowsSm
 		__syncwarp();
 		if (mbx + AHEAD < W) { const int nb = (mbx + AHEAD) % IR_SLOTS; pending &= ~(1u << nb); if (coef_issue(mbx + AHEAD)) pending |= 1u << nb; }
 		const int kind = r->kind;
+		RT_MARK(1)      /* records, coefficient copy issued */
 		if ((pending >> sl) & 1) {
 			if (!mbar_wait(&sm.bars[w][sl], (parbits >> sl) & 1)) { if (lane == 0) atomicExch(J.err, 3u); }
 			parbits ^= 1u << sl;
+			RT_MARK(2)  /* waiting for the coefficient run */
 			residual_stage(ws, r, J.slices + r->slice_idx, sm.coef[w][sl], lane);
 		} else if (kind != MBK_INTER && kind != MBK_IPCM) {
 			((uint4 *)ws->res)[lane] = make_uint4(0, 0, 0, 0);
@@ -94,8 +98,11 @@ __device__ __forceinline__ void intra_row_transform(const PicJob &J, IntraRowsSm
 		}
 		__syncwarp();
 		if (lane == 0) { __threadfence_block(); *ready = mbx + 1; }
+		RT_MARK(3)      /* inverse transforms */
 		if (digests) dbk_digest_mb(J, sm.drecs[w], &sm.ddg[w], mby * W + mbx, lane);
+		RT_MARK(4)      /* deblocking digest */
 	}
+	RT_FLUSH(0)
 }
 
 /* The row's PREDICTION warp: waits for the residual, for the row above (top-right neighbour finished) and for room in
@@ -119,6 +126,7 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 	uint8_t *dst = J.frames + (size_t)J.dst_slot * J.frame_bytes;
 	const int cpl = J.stride_c >> 1;
 	int avail = 0;                                            /* macroblocks of the row above the band known to be stored */
+	RT_DECL
 #pragma unroll 1
 	for (int mbx = 0; mbx < W; mbx++) {
 		uint8_t *Y = dst + (size_t)(mby * 16) * J.stride_y + mbx * 16;
@@ -127,6 +135,7 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 		if (lane == 0) {
 			unsigned spins = 0; bool bad = false;
 			while (*ready <= mbx && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
+			RT_MARK(0)  /* waiting for the residual */
 			const int need = min(mbx + 2, W);
 			if (from_ring) {
 				while (*done_in < need && !bad) { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
@@ -137,6 +146,7 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 				__threadfence();
 				avail = bad ? W : (int)(v - base);
 			}
+			RT_MARK(1)  /* waiting for the row above */
 			if (to_ring) while (*taken_next <= mbx - IR_RING + 1 && !bad)     /* entry mbx - RING is still the corner sample of the row below's macroblock mbx - RING + 1 */ { if ((++spins & 1023) == 0) bad = *errp != 0 || spins > (1u << 26); }
 			if (bad) atomicExch(J.err, 1u);
 			__threadfence_block();
@@ -160,6 +170,7 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 			if (lane < 18) { const int pl = lane / 9, cx = lane % 9 - 1; if (cx >= 0 || mbx > 0) CT(pl, cx, -1) = __ldcg(C + pl * cpl - J.stride_c + cx); }
 		}
 		__syncwarp();
+		RT_MARK(2)      /* ring room, hand-shake, row above into the tile */
 		/* ---- the macroblock ---- */
 		if (kind == MBK_INTER) {   /* reconstructed by the inter kernel: fetch its right column and bottom row for the neighbours to come */
 			if (lane < 16) YT(15, lane) = __ldcg(Y + (size_t)lane * J.stride_y + 15);
@@ -176,7 +187,9 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 				__syncwarp();
 			} else {
 				intra_luma(ws, r, lane);
+				RT_MARK(3)  /* luma prediction */
 				intra_chroma(ws, r, lane);
+				RT_MARK(4)  /* chroma prediction */
 			}
 			store_mb(ws, J, Y, C, lane);
 			if (to_ring) {
@@ -185,6 +198,7 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 			}
 		}
 		__syncwarp();
+		RT_MARK(5)      /* stores */
 		/* ---- publish: shared-memory counter for the row below in this band; global counter for the next band, one chunk late ---- */
 		if (lane == 0) {
 			if (to_ring) { __threadfence_block(); *done_out = mbx + 1; }
@@ -200,7 +214,9 @@ __device__ __forceinline__ void intra_row_walk(const PicJob &J, IntraRowsSmem &s
 		__syncwarp();
 		if (lane == 0) { __threadfence_block(); *used = mbx + 1; }
 		avail = __shfl_sync(0xffffffffu, avail, 0);
+		RT_MARK(6)      /* publication, column hand-over */
 	}
+	RT_FLUSH(8)
 	__syncwarp();
 	if (lane == 0) {
 		*taken_me = W + IR_RING;       /* nothing of the ring above is needed any more */

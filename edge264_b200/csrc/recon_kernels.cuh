@@ -8,6 +8,7 @@
  * Up to three launches per picture.  Arithmetic is restated from ITU-T H.264 with the reference's observable integer
  * widths; results are bit-exact with the reference decoder (tests/test_gpu_parity.py). */
 #pragma once
+#include <cstddef>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "records.h"
@@ -70,6 +71,17 @@ __device__ __forceinline__ void reset_next_tickets(const PicJob &J) { if (blockI
 /* measurement only (replay with E264B_DIAG=1): how the blocks of each kernel kind land on the SMs —
  * [kind][sm]: blocks started, blocks of this kind resident right now, the maximum of that */
 __device__ unsigned g_diag_cnt[4][160], g_diag_cur[4][160], g_diag_max[4][160];
+/* -DE264_ROWS_TIMING (make variants): SM cycles the warps of e264_intra_rows_kernel spend per part of a macroblock step */
+__device__ unsigned long long g_diag_phase[16];
+#ifdef E264_ROWS_TIMING
+#define RT_DECL unsigned rt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; unsigned rt_t = (unsigned)clock64();
+#define RT_MARK(k) { const unsigned rt_n = (unsigned)clock64(); rt_acc[k] += rt_n - rt_t; rt_t = rt_n; }
+#define RT_FLUSH(base) if (lane == 0) { for (int rt_k = 0; rt_k < 8; rt_k++) atomicAdd(&g_diag_phase[(base) + rt_k], (unsigned long long)rt_acc[rt_k]); }
+#else
+#define RT_DECL
+#define RT_MARK(k)
+#define RT_FLUSH(base)
+#endif
 /* measurement only: first-start / last-end timestamps of a launch, see e264b_replay */
 struct TraceScope {
 	unsigned long long *t; int dk; unsigned sm;
@@ -160,6 +172,7 @@ __device__ __forceinline__ bool mbar_wait(void *bar, unsigned parity) {
 /* residual                                                                                     */
 /* ------------------------------------------------------------------------------------------ */
 /* 4x4 inverse transform of 16 levels at c (16-byte aligned) -> residual written to dst[y*dstride+x] */
+static_assert(offsetof(E264SliceRec, scaling4x4) % 8 == 0 && sizeof(E264SliceRec) % 8 == 0, "idct4x4 loads a 4x4 scaling list as two 8-byte words");
 __device__ __noinline__ void idct4x4(const int16_t *c, bool have_levels, const uint8_t *scaling, int qp, bool dc_override, int dc, int16_t *dst, int dstride) {
 	int d[16];
 	if (have_levels) {
@@ -167,11 +180,17 @@ __device__ __noinline__ void idct4x4(const int16_t *c, bool have_levels, const u
 		int16_t lv[16];
 		*(uint4 *)lv = a; *(uint4 *)(lv + 8) = b;
 		int sh = qp / 6, m = qp - sh * 6;
+		/* the 16 weights arrive as two 8-byte loads (the lists sit at offset 904 + 16 k of 1128-byte slice records: 8-byte
+		 * aligned), the three normalisation values of this qp % 6 once */
+		const uint2 s01 = __ldg((const uint2 *)scaling), s23 = __ldg((const uint2 *)scaling + 1);
+		const uint32_t sw[4] = {s01.x, s01.y, s23.x, s23.y};
+		const int n0 = h264_norm4x4[m][0], n1 = h264_norm4x4[m][1], n2 = h264_norm4x4[m][2];
 #pragma unroll
 		for (int i = 0; i < 4; i++)
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
-				int ls = scaling[i * 4 + j] * norm4(m, i, j);
+				const int nrm = ((i & 1) && (j & 1)) ? n1 : (!(i & 1) && !(j & 1)) ? n0 : n2;
+				int ls = (int)((sw[i] >> (8 * j)) & 255u) * nrm;
 				d[i * 4 + j] = (int)(((unsigned)(lv[i * 4 + j] * ls) << sh) + 8u) >> 4;
 			}
 	} else {
