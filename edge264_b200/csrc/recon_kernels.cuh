@@ -378,20 +378,23 @@ __device__ __forceinline__ int intra_tap_apply(int E, int idx, int kind) {
 	return kind == 2 ? (a + 2 * b + c + 2) >> 2 : kind == 1 ? (a + b + 1) >> 1 : a;
 }
 
-/* one 4x4 block at tile coordinate (X0, Y0): lanes 0..15 return their predicted sample (x = lane & 3, y = lane >> 2) */
-__device__ __forceinline__ int pred4x4_warp(const WarpSmem *ws, int X0, int Y0, int imode, uint64_t taps, int lane) {
+/* one 4x4 block at tile coordinate (X0, Y0) per HALF-WARP: lane hl = lane & 15 of half `half` returns its predicted sample
+ * (x = hl & 3, y = hl >> 2); the two halves work on different blocks with different modes, so nothing here branches on
+ * the mode — the DC sum and the tap shuffles are both computed (a shuffle inside diverged code can hang) */
+__device__ __forceinline__ int pred4x4_half(const WarpSmem *ws, int X0, int Y0, int imode, uint64_t taps, int hl, int half) {
 	const int mode = imode & 15, un = imode >> 4;
 	const bool hasA = !(un & 1), hasB = !(un & 2);
-	const int e = min(lane, 14);
+	const int e = min(hl, 14);
 	int i = min(e - 6, 7); if ((un & 4) && i > 3) i = 3;          /* top-right unavailable: T4..T7 = T3 */
 	const int E = YT(X0 + (e <= 5 ? -1 : i), Y0 + (e <= 4 ? min(4 - e, 3) : -1));
-	if (mode == 2) {
-		int s = (lane < 15 && ((e >= 6 && e <= 9 && hasB) || (e >= 1 && e <= 4 && hasA))) ? E : 0;
-		s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4); s += __shfl_xor_sync(0xffffffffu, s, 8);
-		return (hasA && hasB) ? (s + 4) >> 3 : (hasA || hasB) ? (s + 2) >> 2 : 128;
-	}
+	int s = (hl < 15 && ((e >= 6 && e <= 9 && hasB) || (e >= 1 && e <= 4 && hasA))) ? E : 0;
+	s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4); s += __shfl_xor_sync(0xffffffffu, s, 8);
+	const int dc = (hasA && hasB) ? (s + 4) >> 3 : (hasA || hasB) ? (s + 2) >> 2 : 128;
 	const int ent = (int)(taps >> (6 * mode)) & 63;
-	return intra_tap_apply(E, ent & 15, ent >> 4);
+	const int idx = (ent & 15) + half * 16, kind = ent >> 4;
+	const int a = __shfl_sync(0xffffffffu, E, idx), b = __shfl_sync(0xffffffffu, E, (idx + 1) & 31), c = __shfl_sync(0xffffffffu, E, (idx + 2) & 31);
+	const int dir = kind == 2 ? (a + 2 * b + c + 2) >> 2 : kind == 1 ? (a + b + 1) >> 1 : a;
+	return mode == 2 ? dc : dir;
 }
 
 /* one 8x8 block: reference samples filtered in registers (8.3.2.2.1), then two samples per lane (rows y and y + 4) */
@@ -429,13 +432,19 @@ __device__ __forceinline__ uint32_t intra_add_res4(uint32_t p, uint32_t r01, uin
 
 __device__ __noinline__ void intra_luma(WarpSmem *ws, const E264MbRec *r, int lane) {
 	if (r->kind == MBK_I4x4) {
-		const uint64_t taps = __ldg(&e264_i4taps.v[lane & 15]);
+		/* the 16 blocks along anti-diagonals: block (x, y) in step x + 2 y, so its left, top, top-left and top-right
+		 * neighbours are finished (8.3.1.2: top-right counts only where it precedes in decoding order — the record's
+		 * availability bits say so); two blocks per step in the two half-warps, 10 steps instead of 16 */
+		const int hl = lane & 15, half = lane >> 4, x = hl & 3, y = hl >> 2;
+		const uint64_t taps = __ldg(&e264_i4taps.v[hl]);
 #pragma unroll 1
-		for (int b = 0; b < 16; b++) {
-			const int X0 = blk_x(b) * 4, Y0 = blk_y(b) * 4, x = lane & 3, y = (lane >> 2) & 3;
-			int v = pred4x4_warp(ws, X0, Y0, r->modes[b], taps, lane);
+		for (int st = 0; st < 10; st++) {
+			const int by = (st < 2 ? 0 : (st - 2) >> 1) + half, bx = st - 2 * by;
+			const bool on = bx >= 0 && bx < 4 && by < 4;
+			const int X0 = on ? bx * 4 : 0, Y0 = on ? by * 4 : 0;
+			int v = pred4x4_half(ws, X0, Y0, r->modes[on ? blk_z(bx, by) : 0], taps, hl, half);
 			v = clip255((short)(v + ws->res[(Y0 + y) * 16 + X0 + x]));
-			if (lane < 16) YT(X0 + x, Y0 + y) = (uint8_t)v;   /* the reads above touch only samples outside the block */
+			if (on) YT(X0 + x, Y0 + y) = (uint8_t)v;   /* the reads above touch only samples outside the two blocks of this step */
 			__syncwarp();
 		}
 	} else if (r->kind == MBK_I8x8) {
