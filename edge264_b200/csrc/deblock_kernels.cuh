@@ -408,3 +408,4 @@ __global__ void __launch_bounds__(DBK_PAIRS * 32, MINB) e264_deblock_kernel(PicJ
 		else dbk_walk<false>(J, &sm, t >> 1, wid, lane);
 	}
 }
+

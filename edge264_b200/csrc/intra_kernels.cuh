@@ -257,15 +257,22 @@ __global__ void __launch_bounds__(IR_ROWS * 64) e264_intra_rows_kernel(PicJob J)
  * only ever waits for entries drawn before its own.  Neighbours: A, D, B, C "reconstructed" flags — inter neighbours were
  * flagged by e264_inter4_kernel (kernel boundary), intra ones are flagged here after a fence.  The coefficient run is
  * fetched (cp.async.bulk) and inverse-transformed while the neighbours finish. */
+/* Block size: the kernel's span is the longest chain of dependent intra macroblocks, not its amount of work, and the inter
+ * kernel's blocks need a WHOLE SM: a few big blocks (INTRA_WARPS warps, several list entries per warp) leave most SMs to
+ * them, where many 4-warp blocks put one small, latency-bound block on nearly every SM. */
+#ifndef INTRA_WARPS
+#define INTRA_WARPS 16
+#endif
 struct __align__(16) IntraTkSmem {
-	WarpSmem ws[WARPS_PER_BLOCK];
-	int16_t coef[WARPS_PER_BLOCK][RES_COEF_MAX];
-	unsigned long long bars[WARPS_PER_BLOCK];
+	WarpSmem ws[INTRA_WARPS];
+	int16_t coef[INTRA_WARPS][RES_COEF_MAX];
+	unsigned long long bars[INTRA_WARPS];
 };
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) e264_intra_kernel(PicJob J) {
+__global__ void __launch_bounds__(INTRA_WARPS * 32) e264_intra_kernel(PicJob J) {
 	TraceScope trace_(J, 2);
 	reset_next_tickets(J);
-	__shared__ IntraTkSmem sm;
+	extern __shared__ __align__(16) unsigned char intra_tk_smem_raw[];
+	IntraTkSmem &sm = *(IntraTkSmem *)intra_tk_smem_raw;
 	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	WarpSmem *ws = &sm.ws[w];
 	const int nmb = J.w_mbs * J.h_mbs, W = J.w_mbs, cpl = J.stride_c >> 1;

@@ -108,6 +108,7 @@ extern "C" int e264b_create(E264bDevice **out) {
 	c->dev = dev;
 	CK(cudaFuncSetAttribute(e264_intra_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraRowsSmem)));
 	CK(cudaFuncSetAttribute(e264_inter4_kernel<INTER_MINB0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InterSmem)));
+	CK(cudaFuncSetAttribute(e264_intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(IntraTkSmem)));
 #if INTER_WARPS == 4
 	CK(cudaFuncSetAttribute(e264_inter4_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InterSmem)));
 	CK(cudaFuncSetAttribute(e264_inter4_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(InterSmem)));
@@ -240,14 +241,6 @@ static PicJob make_job(E264bDevice *c, const E264PicDesc *pd, int stage, const E
 	J.tickets = c->d_sync + (J.epoch & 1) * 4; J.tickets_next = c->d_sync + ((J.epoch + 1) & 1) * 4;    /* two sets, pictures alternate; every kernel clears the next picture's */
 	return J;
 }
-/* launch with a block-scheduling priority (experiment switch E264B_PRIO=inter,intra,deblock; lower = more urgent) */
-template <typename K> static void launch_prio(K kernel, int grid, int block, size_t smem, cudaStream_t st, int prio, const PicJob &J) {
-	cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
-	cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-	cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributePriority; at[0].val.priority = prio;
-	cfg.attrs = at; cfg.numAttrs = 1;
-	cudaLaunchKernelEx(&cfg, kernel, J);
-}
 static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd, int with_deblock) {
 	const int nmb = J.w_mbs * J.h_mbs;
 	const int cap = c->sm_count * 8;
@@ -263,8 +256,6 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 		if (dbk_smem > 0) { cudaFuncSetAttribute(e264_deblock_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, dbk_smem); cudaFuncSetAttribute(e264_deblock_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dbk_smem); cudaFuncSetAttribute(e264_deblock_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, dbk_smem); }
 	}
 	const int mask = J.trace ? only : 7;
-	static int prio_on = -1, prio[3] = {0, 0, 0};
-	if (prio_on < 0) { const char *e = getenv("E264B_PRIO"); prio_on = e && sscanf(e, "%d,%d,%d", &prio[0], &prio[1], &prio[2]) == 3; }
 	/* up to three launches per picture, nothing in between: inter macroblocks (inverse transform + prediction), intra
 	 * macroblocks (flags order them behind their neighbours), deblocking (its blocks derive the boundary strengths first) */
 	if (pd->n_intra < nmb && (mask & 1)) {
@@ -275,7 +266,6 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 		else if (minb >= 6) e264_inter4_kernel<6><<<ib, INTER_WARPS * 32, sizeof(InterSmem), c->stream>>>(J);
 		else
 #endif
-		if (prio_on) launch_prio(e264_inter4_kernel<INTER_MINB0>, ib, INTER_WARPS * 32, sizeof(InterSmem), c->stream, prio[0], J); else
 		e264_inter4_kernel<INTER_MINB0><<<ib, INTER_WARPS * 32, sizeof(InterSmem), c->stream>>>(J);
 		c->launches++;
 	}
@@ -283,14 +273,12 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 		if (J.rows_mode) {   /* intra pictures: bands of rows, hand-over through shared memory */
 			e264_intra_rows_kernel<<<(J.h_mbs + IR_ROWS - 1) / IR_ROWS, IR_ROWS * 64, sizeof(IntraRowsSmem), c->stream>>>(J);
 		} else {
-			/* the kernel's span is the longest chain of dependent intra macroblocks, not its amount of work: a warp takes
-			 * several list entries (E264B_INTRA_DIV, default 1) and a picture holds that many fewer blocks resident */
+			/* a warp takes several list entries (E264B_INTRA_DIV, default 2): see INTRA_WARPS */
 			static int idiv = -1;
-			if (idiv < 0) { const char *e = getenv("E264B_INTRA_DIV"); idiv = e && atoi(e) > 0 ? atoi(e) : 1; }
-			int ib = (pd->n_intra + WARPS_PER_BLOCK * idiv - 1) / (WARPS_PER_BLOCK * idiv);
+			if (idiv < 0) { const char *e = getenv("E264B_INTRA_DIV"); idiv = e && atoi(e) > 0 ? atoi(e) : 2; }
+			int ib = (pd->n_intra + INTRA_WARPS * idiv - 1) / (INTRA_WARPS * idiv);
 			if (ib > cap) ib = cap;
-			if (prio_on) launch_prio(e264_intra_kernel, ib, WARPS_PER_BLOCK * 32, 0, c->stream, prio[1], J); else
-			e264_intra_kernel<<<ib, WARPS_PER_BLOCK * 32, 0, c->stream>>>(J);
+			e264_intra_kernel<<<ib, INTRA_WARPS * 32, sizeof(IntraTkSmem), c->stream>>>(J);
 		}
 		c->launches++;
 	}
@@ -298,7 +286,6 @@ static int launch_picture(E264bDevice *c, const PicJob &J, const E264PicDesc *pd
 		const int bands = (J.h_mbs + 2 * DBK_PAIRS - 1) / (2 * DBK_PAIRS);
 		if (dm >= 5) e264_deblock_kernel<5><<<2 * bands, DBK_PAIRS * 32, dbk_smem, c->stream>>>(J);
 		else if (dm == 4) e264_deblock_kernel<4><<<2 * bands, DBK_PAIRS * 32, dbk_smem, c->stream>>>(J);
-		else if (prio_on) launch_prio(e264_deblock_kernel<2>, 2 * bands, DBK_PAIRS * 32, (size_t)dbk_smem, c->stream, prio[2], J);
 		else e264_deblock_kernel<2><<<2 * bands, DBK_PAIRS * 32, dbk_smem, c->stream>>>(J);
 		c->launches++;
 	}
