@@ -344,7 +344,7 @@ def main():
             "e2e": {"value": e2e_fps, "unit": "frames/s", "macroblocks_per_s": e2e_fps * mbpf, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "app_threads": app_threads, "decoder_n_threads": dec_threads, "usable_cpus": usable_cpus(), "cpus_per_rank": cpus, "bytes_per_unit": len(bufs[0]),
                     "saturated": "host CPUs (bitstream parsing)" if app_threads * max(1, dec_threads + 1) >= cpus else "streams in flight",
-                    "note": "edge264_decode_NAL/get_frame from host buffers; application threads sleep while get_frame waits for the GPU"},
+                    "note": "edge264_decode_NAL/get_frame from host buffers; bound by the host's CPUs (bitstream parsing) as soon as application threads x (1 + parse-ahead workers) reach the usable CPUs — on one host that is already the case at N = 1, so e2e follows the CPUs, not the number of GPUs; get_frame polls and only waits after ENOBUFS / at the end of a stream"},
             "roofline": roof}
     lib.free(decs)
 

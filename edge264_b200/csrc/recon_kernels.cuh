@@ -93,25 +93,10 @@ struct TraceScope {
 	__device__ __forceinline__ ~TraceScope() { if (t && threadIdx.x == 0) atomicMax(t + 1, now()); if (dk >= 0 && threadIdx.x == 0) atomicSub(&g_diag_cur[dk][sm], 1u); }
 };
 
-/* spin until flags[idx] == epoch (lane 0).  Bounded so that a bug cannot hang the GPU: gives up after ~0.2 s of SM
- * clocks, or at once when another warp has already raised the error flag. */
-__device__ __forceinline__ bool wait_flag(const unsigned *flags, int idx, unsigned epoch, unsigned *err) {
-	const volatile unsigned *f = flags + idx;
-	unsigned spins = 0;
-	long long t0 = 0;
-	while (*f != epoch) {
-		__nanosleep(64);
-		if ((++spins & 63) == 0) {
-			if (*(const volatile unsigned *)err) return false;
-			if (t0 == 0) t0 = clock64();
-			else if (clock64() - t0 > 400000000ll) { atomicExch(err, 1u); return false; }
-		}
-	}
-	return true;
-}
-
-/* the same with acquire loads (no fence behind it): several lanes of a warp may each wait for their own flag, so the
- * round trips to L2 overlap instead of adding up; a __syncwarp() behind the waits orders the other lanes' loads */
+/* Dependency waits are bounded so that a bug cannot hang the GPU: they give up after ~0.2 s of SM clocks, or at once when
+ * another warp has already raised the error flag. */
+/* spin until flags[idx] == epoch, with acquire loads (no fence behind it): several lanes of a warp may each wait for their
+ * own flag, so the round trips to L2 overlap instead of adding up; a __syncwarp() behind the waits orders the other lanes' loads */
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ bool wait_flag_acquire(const unsigned *flags, int idx, unsigned epoch, unsigned *err) {
 	const unsigned *f = flags + idx;
@@ -128,22 +113,6 @@ __device__ __forceinline__ bool wait_flag_acquire(const unsigned *flags, int idx
 	}
 	return ok;
 }
-/* spin until *p - need >= 0 (counters carry the picture epoch in their upper bits), bounded like wait_flag */
-__device__ __forceinline__ bool wait_progress(const unsigned *p, unsigned need, unsigned *err) {
-	const volatile unsigned *f = p;
-	unsigned spins = 0;
-	long long t0 = 0;
-	while ((int)(*f - need) < 0) {
-		__nanosleep(64);
-		if ((++spins & 63) == 0) {
-			if (*(const volatile unsigned *)err) return false;
-			if (t0 == 0) t0 = clock64();
-			else if (clock64() - t0 > 400000000ll) { atomicExch(err, 1u); return false; }
-		}
-	}
-	return true;
-}
-
 /* ---- shared-memory barrier + TMA helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP, UTMALDG) ---- */
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
