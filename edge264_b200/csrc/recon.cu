@@ -352,6 +352,7 @@ extern "C" int e264b_wait(E264bDevice *c, uint64_t ticket) {
 /* non-blocking: 0 = complete, EAGAIN = the picture (or a later one that took its ring slot) is still on the device */
 extern "C" int e264b_poll(E264bDevice *c, uint64_t ticket) {
 	if (ticket == 0) return 0;
+	CK(cudaSetDevice(c->dev));
 	cudaError_t q = cudaEventQuery(c->tick_ev[ticket % NTICK]);
 	if (q == cudaErrorNotReady) return EAGAIN;
 	if (q != cudaSuccess) { fprintf(stderr, "edge264_b200: cudaEventQuery: %s\n", cudaGetErrorString(q)); return -1; }
