@@ -1,17 +1,17 @@
 /* inter_kernels.cuh — inter macroblocks: inverse transform + motion compensation + weighting + residual in ONE kernel.
  *
- * One warp per macroblock (tickets), one THREAD per (4x4 luma block, reference list): lane = list * 16 + luma4x4BlkIdx.
- * The thread loads its own 9x9 luma window and two 3x3 chroma windows of the reference picture straight into
- * registers (aligned 32-bit loads + funnel shifts; the windows of neighbouring blocks overlap in L1/L2), interpolates
- * its 4x4 + 2x2 + 2x2 samples with the register arithmetic of mc_math.cuh (dp4a tap sums), and the list-1 thread hands
- * its prediction to the list-0 thread with shuffles for the weighted combination (reference edge264_inter.c:416-1251:
- * per-partition SIMD interpolation + five weighting schemes; here the unit is always the 4x4 block, which is what the
- * record carries a vector for — partition shapes never reach the device).
+ * The unit of prediction is always the 4x4 luma block and reference list (that is what the record carries a vector for —
+ * partition shapes never reach the device): an ITEM.  A thread handles one item: it loads the item's 9x9 luma window and
+ * two 3x3 chroma windows of the reference picture straight into registers (aligned 32-bit loads + funnel shifts; the
+ * windows of neighbouring blocks overlap in L1/L2) and interpolates 4x4 + 2x2 + 2x2 samples with the register arithmetic of
+ * mc_math.cuh (dp4a tap sums).  Items are binned by interpolation class so that a warp runs ONE class body on 32 items
+ * (reference edge264_inter.c:416-1251: per-partition SIMD interpolation + five weighting schemes).
  * The macroblock's coefficient run (16..816 bytes) arrives by cp.async.bulk on an mbarrier one macroblock ahead and is
  * inverse-transformed in shared memory (residual_stage), so the residual never travels through global memory.
- * Round 1's kernel (rectangles regrouped on the device, windows by cp.async.bulk.tensor into shared memory, one output
- * sample per lane and loop iteration) needed ~3600 warp instructions per macroblock and 77 us per 1080p picture against
- * 38 us here (profiles/README.md). */
+ * History: round 1's kernel (rectangles regrouped on the device, windows by cp.async.bulk.tensor into shared memory, one
+ * output sample per lane and loop iteration) needed ~3600 warp instructions per macroblock and 77 us per 1080p picture;
+ * this one 1630 and 39 us, and 35 k pictures/s with 32 streams in flight since its blocks are 16 warps in lock-step phases
+ * (profiles/r2_inter_geometry.txt). */
 #pragma once
 #include "recon_kernels.cuh"
 #include "deblock_kernels.cuh"
@@ -99,7 +99,7 @@ __device__ __forceinline__ uint32_t add_res4(uint32_t p, const int16_t *res) {
  * 2000 warp instructions per macroblock on random vectors, no faster than round 1's). */
 /* Block geometry: INTER_WARPS warps take INTER_CHUNK macroblocks at a time (4 per warp).  The kernel's three phases are
  * separated by block barriers, so all warps of a block execute the same part of the code: the bigger the block, the fewer
- * different parts of the kernel (about 8 000 instructions, 130 KB) the SM's instruction cache has to hold at a time — and a
+ * different parts of the kernel (12 400 instructions when this was measured, 5 600 now) the SM's instruction cache has to hold at a time — and a
  * 16-warp block at 128 registers per thread fills the SM's register file, so no block of another kernel shares the SM. */
 #ifndef INTER_WARPS
 #define INTER_WARPS 16      /* measured (profiles/r2_inter_geometry.txt), 32 streams: 4 warps 9.7 k, 8 warps 13.2 k, 16 warps 17.8 k frames/s */
