@@ -10,7 +10,8 @@
  *                         (raster macroblocks, vertical edges left to right, then horizontal edges top to bottom;
  *                         reference order edge264_deblock.c:537-891): macroblock (x, y) needs (x-1, y) complete,
  *                         (x, y-1) complete and the left edge of (x+1, y-1) done.  One warp walks two rows at once,
- *                         lanes 0-15 on row 2k at macroblock x, lanes 16-31 on row 2k+1 at macroblock x-2 — the same
+ *                         lanes 0-15 on row 2k at macroblock x, lanes 16-31 on row 2k+1 at macroblock x-1 (the rows above are
+ *                         needed by the horizontal pass only, and the vertical pass of x+1 above is what finalises x) — the same
  *                         instruction stream, no divergence — and hands the four bottom sample rows from the upper to
  *                         the lower row through a shared-memory ring.  Inside an iteration a lane owns a whole sample
  *                         ROW for the four vertical edges (registers only, no exchange between edges), the tile is
@@ -148,7 +149,8 @@ __device__ __forceinline__ int dbk_byte(uint32_t w, int k) { return (int)((w >> 
 __device__ __forceinline__ uint32_t dbk_pack(int a, int b, int c, int d) { return (uint32_t)a | (uint32_t)b << 8 | (uint32_t)c << 16 | (uint32_t)d << 24; }
 
 /* One warp = one pair of macroblock rows of the band, one kind of plane.  Hand-over of the bottom sample rows:
- *   upper row -> lower row of the warp: shared-memory ring, fixed lag of two iterations, no counters;
+ *   upper row -> lower row of the warp: shared-memory ring, fixed lag of one iteration (written before, read behind the
+ *     barrier between the two passes), no counters;
  *   lower row -> upper row of the next warp: the same ring with done/taken counters in shared memory (block-scope fences);
  *   last row of the band -> first row of the next band (another block): global memory, a progress counter per row
  *   published every DBK_CHUNK macroblocks (the only gpu-scope fences of the kernel, off the per-macroblock path). */
