@@ -2,6 +2,7 @@
  * the decoder's backend interface so that the host parser + record ABI can be validated against the
  * compiled reference decoder without a GPU (tests/test_oracle_vs_ref.py), and so that GPU output can
  * be compared with it picture by picture.  Linked only into oracle/liboracle_dec.so. */
+#include <errno.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -20,7 +21,9 @@ typedef struct PortCtx {
 	uint32_t *intra_list[PORT_NSTAGE];
 	int stage, n_stage;
 	int cur_slot;
+	uint64_t tick_seq; int polls[64]; int n_waits;      /* E264_PORT_LATE: see port_submit */
 } PortCtx;
+static int port_late(void) { static int v = -1; if (v < 0) { const char *e = getenv("E264_PORT_LATE"); v = e ? atoi(e) : 0; } return v; }
 
 static int port_create(void **ctx) { *ctx = calloc(1, sizeof(PortCtx)); return *ctx ? 0 : -1; }
 static void port_free_all(PortCtx *c) {
@@ -79,16 +82,29 @@ static int port_submit(void *ctx, const E264PicDesc *pd, uint8_t *host_out, uint
 	if (pd->staging < 0 || pd->staging >= c->n_stage) return -1;
 	if (!getenv("E264_NULL_RECON")) port_recon_picture(c->frames, pd, c->recs[pd->dst_slot], c->coefs[pd->staging], c->slices[pd->staging]);
 	if (!getenv("E264_NULL_RECON")) memcpy(host_out, c->frames + (size_t)pd->dst_slot * pd->frame_bytes, (size_t)pd->frame_bytes);
-	*ticket = 0;
+	/* E264_PORT_LATE=n (tests of the decoder's output logic): pictures get tickets and count as "still on the device" until
+	 * they have been polled n times or waited for, like a GPU that has not finished yet */
+	*ticket = port_late() ? ++c->tick_seq : 0;
+	if (*ticket) c->polls[*ticket % 64] = 0;
 	return 0;
 }
-static int port_wait(void *ctx, uint64_t ticket) { (void)ctx; (void)ticket; return 0; }
+static int g_port_waits;
+static int port_wait(void *ctx, uint64_t ticket) { PortCtx *c = (PortCtx *)ctx; if (ticket && c->polls[ticket % 64] < port_late()) { c->polls[ticket % 64] = 1 << 30; c->n_waits++; __atomic_add_fetch(&g_port_waits, 1, __ATOMIC_RELAXED); } return 0; }
 static int port_fill(void *ctx, int slot, int y, int cc) {
 	PortCtx *c = (PortCtx *)ctx;
 	uint8_t *f = c->frames + (size_t)slot * c->g.frame_bytes;
 	memset(f, y, (size_t)c->g.plane_y); memset(f + c->g.plane_y, cc, (size_t)c->g.frame_bytes - c->g.plane_y);
 	return 0;
 }
-static int port_poll(void *ctx, uint64_t ticket) { (void)ctx; (void)ticket; return 0; }
+static int port_poll(void *ctx, uint64_t ticket) {
+	PortCtx *c = (PortCtx *)ctx;
+	if (!ticket) return 0;
+	if (c->polls[ticket % 64] >= port_late()) return 0;
+	c->polls[ticket % 64]++;
+	return EAGAIN;
+}
+/* test hook: how often a decoder had to WAIT for a picture that was not finished (it may only do so after ENOBUFS / at the
+ * end of the stream) */
+int e264_port_waits(void) { return __atomic_load_n(&g_port_waits, __ATOMIC_RELAXED); }
 static const E264Backend port_backend = {"oracle-port", port_create, port_destroy, port_configure, port_host_alloc, port_host_free, port_acquire, port_submit, port_wait, port_fill, port_poll};
 const E264Backend *e264_default_backend(void) { return &port_backend; }
